@@ -1,0 +1,155 @@
+"""Pin the CPU oracle (oracle/mcnerf_oracle.py) against fixtures produced by running the
+UNMODIFIED reference modules (tests/golden/make_golden.py).  CPU only."""
+import torch
+import pytest
+
+from mc_nerf_b200 import synthetic as syn
+from oracle import mcnerf_oracle as orc
+from conftest import load_golden
+
+TOL = dict(rtol=1e-5, atol=1e-6)
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.fixture(scope="module")
+def mods():
+    return load_golden("modules.pt")
+
+
+def test_camera_model(mods):
+    c = mods["cam"]
+    w = c["w"]
+    K = orc.intrinsics_from_weights(w["weights_fx"], w["weights_fy"], w["weights_ux"], w["weights_uy"], c["H"], c["W"])
+    close(K, c["K"])
+    close(orc.se3_to_SE3(w["weights_pose"]), c["pose"])
+    close(orc.se3_to_SE3(w["weights_pose_intr"]), c["calib"])
+    close(orc.inverse_intrinsics(K), c["Kinv"])
+    b = mods["se3_big"]
+    close(orc.se3_to_SE3(b["wu"]), b["Rt"], rtol=1e-5, atol=1e-5)
+
+
+def test_rays_and_reprojection(mods):
+    c, r = mods["cam"], mods["rays"]
+    rd, ro = orc.get_rays(c["pose"][r["img_id"]], c["Kinv"][r["img_id"]], c["H"], c["W"])
+    close(rd, r["rays_d"])
+    close(ro, r["rays_o"])
+    close(orc.reproject(mods["reproj"]["wpts"], c["K"], c["calib"]), mods["reproj"]["out"], rtol=1e-5, atol=1e-4)
+
+
+def test_encoding(mods):
+    e = mods["enc"]
+    close(orc.sincos_encode(e["x"], e["L"]), e["plain"])
+    for r, ref in e["barf"].items():
+        w = orc.barf_weights(r, e["barf_start"], e["barf_end"], e["L"])
+        close(orc.sincos_encode(e["x"], e["L"], w), ref)
+
+
+def test_eval_sh(mods):
+    s = mods["sh"]
+    close(orc.eval_sh_deg2(s["sh"], s["dirs"]), s["out"])
+
+
+@pytest.mark.parametrize("name", ["small", "big"])
+def test_mlp_forward_backward(mods, name):
+    f = mods[f"mlp_{name}"]
+    dep, wid, skips = f["cfg"]
+    p = {k: v.clone().requires_grad_(True) for k, v in orc.init_mlp_params(dep, wid, skips, seed=f["seed"]).items()}
+    x = f["x_enc"].clone().requires_grad_(True)
+    d = f["dirs"].clone().requires_grad_(True)
+    out = orc.mlp_forward(p, x, d, dep, skips)
+    close(out, f["out"])
+    out.backward(f["gout"])
+    close(x.grad, f["g_x"], rtol=1e-4, atol=1e-6)
+    close(d.grad, f["g_dirs"], rtol=1e-4, atol=1e-6)
+    for k, v in p.items():
+        assert abs(float(v.grad.norm()) - f["g_params_norm"][k]) <= 1e-4 * max(1.0, f["g_params_norm"][k])
+        close(v.grad.reshape(-1)[:256], f["g_params_slice"][k], rtol=1e-4, atol=1e-6)
+        if f["g_params"] is not None:
+            close(v.grad, f["g_params"][k], rtol=1e-4, atol=1e-6)
+
+
+def test_compositing(mods):
+    s = mods["s2w"]
+    close(orc.sigma2weights(orc.z_deltas(s["z"]), s["sigmas"], s["noise"]), s["w"])
+    c = mods["composite"]
+    out4 = c["out4"].clone().requires_grad_(True)
+    rgb, dep, opa, _ = orc.composite(out4, c["rays_d"], c["z"], c["noise"], True)
+    close(rgb, c["rgb"])
+    close(dep, c["depth"])
+    close(opa, c["opacity"])
+    rgb.backward(c["g_rgb"])
+    close(out4.grad, c["g_out4"], rtol=1e-4, atol=1e-7)
+
+
+def _run_step(fx, full):
+    sp = syn.make_sys_param(**fx["sp_kw"])
+    cfg = orc.cfg_from_sys_param(sp)
+    if full:
+        i = fx["inputs"]
+        cam_w, pc, pf, batch, rng = i["cam_w"], i["pc"], i["pf"], i["batch"], i["rng"]
+    else:
+        cam_w = syn.init_camera_weights(sp)
+        pc = orc.init_mlp_params(*cfg["coarse"], seed=42)
+        pf = orc.init_mlp_params(*cfg["fine"], seed=43)
+        batch = syn.make_train_batch(sp, img_id=fx["img_id"])
+        rng = syn.draw_step_rng(sp, fx["n_rays"], seed=123)
+    cam = {k: v.clone().requires_grad_(True) for k, v in cam_w.items()}
+    pc = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    pf = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+    out = orc.train_step(cam, pc, pf, cfg, batch, rng, step_r=fx["step_r"], stage=fx["stage"])
+    return sp, cfg, cam, pc, pf, batch, rng, out
+
+
+@pytest.mark.parametrize("name", ["tiny.pt", "tiny_ft.pt"])
+def test_tiny_train_step(name):
+    fx = load_golden(name)
+    sp, cfg, cam, pc, pf, batch, rng, out = _run_step(fx, True)
+    close(out["rgb_c"], fx["rgb_c"])
+    close(out["rgb_f"], fx["rgb_f"])
+    close(out["loss"], fx["loss"])
+    for k, g in fx["g_cam"].items():
+        if g is None:
+            assert cam[k].grad is None or float(cam[k].grad.abs().max()) == 0.0
+        else:
+            close(cam[k].grad, g, rtol=1e-3, atol=1e-6)
+    for k, g in fx["g_mlp"].items():
+        net, pname = k.split(".", 2)[1:]
+        p = (pc if net == "nerf_coarse" else pf)[pname]
+        close(p.grad, g, rtol=1e-3, atol=1e-7)
+    # test-mode render of the same rays
+    with torch.no_grad():
+        pcd = {k: v.detach() for k, v in pc.items()}
+        pfd = {k: v.detach() for k, v in pf.items()}
+        rgb, dep, opa = orc.render_rays(pcd, pfd, cfg, fx["rays_d"], fx["rays_o"], rng, train=False)
+    close(rgb, fx["test"]["rgb"])
+    close(dep, fx["test"]["depth"], rtol=1e-5, atol=1e-5)
+    close(opa, fx["test"]["opacity"])
+
+
+def test_cfg1_train_step():
+    """BASELINE config 1 (110 cameras, 100x100, 1024 rays, 64+128 samples, both nets 8x256)."""
+    from tests_checksum import checksum
+    fx = load_golden("cfg1.pt")
+    sp, cfg, cam, pc, pf, batch, rng, out = _run_step(fx, False)
+    cs = fx["checksums"]
+    got = dict(gt=checksum(batch[0]), noise_f=checksum(rng["noise_f"]), jitter=checksum(rng["jitter"]),
+               rand_idx=checksum(rng["rand_idx"]), w_c0=checksum(pc["xyz_encoding_1.0.weight"].detach()),
+               w_f7=checksum(pf["xyz_encoding_8.0.weight"].detach()), pose_w=checksum(cam["weights_pose"].detach()))
+    for k in cs:
+        if not all(abs(a - b) <= 1e-6 * max(1.0, abs(b)) for a, b in zip(got[k], cs[k])):
+            pytest.skip(f"seeded input {k} differs on this torch build; fixture inputs cannot be regenerated")
+    close(out["loss"], fx["loss"], rtol=1e-5, atol=1e-6)
+    # the fine-sample gate is discontinuous (SURVEY §7 'hard parts'); CPU thread-count dependent
+    # summation order can flip a sample sitting on the threshold, so allow a handful of rays to move.
+    for k in ("rgb_c", "rgb_f"):
+        bad = ((out[k] - fx[k]).abs() > 1e-4).any(-1).sum().item()
+        assert bad <= 4, (k, bad)
+    for k, g in fx["g_cam"].items():
+        close(cam[k].grad, g, rtol=2e-2, atol=1e-5)
+    for k, n in fx["g_mlp_norm"].items():
+        net, pname = k.split(".", 2)[1:]
+        p = (pc if net == "nerf_coarse" else pf)[pname]
+        assert abs(float(p.grad.norm()) - n) <= 2e-3 * max(n, 1e-6), k
