@@ -1,0 +1,202 @@
+/*
+ * mcnerf.h - C ABI of libmcnerf.so: hand-written sm_100a CUDA kernels for the MC-NeRF
+ * train/render hot path (reference: SkylerGao/MC_NeRF, model/mc_nerf.py, model/net_block.py,
+ * model/net_utils.py - pure PyTorch, no FFI of its own).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; tensors are dense row-major
+ *    fp32 unless stated; index tensors are int32.
+ *  - every entry returns 0 on success, non-zero (a cudaError_t or MCNERF_E_*) on failure, never
+ *    throws, never allocates: the caller owns all buffers including workspaces.
+ *  - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and the call returns
+ *    without synchronising.
+ *  - gradient outputs named g_* are ACCUMULATED into (+=) when the doc says "accumulate",
+ *    otherwise overwritten.
+ *  - mcnerf_last_error() returns a thread-local description of the last failure.
+ *
+ * Each entry cites the reference lines it replaces ("ref:" = path in the reference repository).
+ */
+#ifndef MCNERF_H_
+#define MCNERF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCNERF_ABI_VERSION 1
+#define MCNERF_MAX_DEPTH 16
+#define MCNERF_MAX_FREQS 16
+
+#define MCNERF_E_ARG 10001      /* bad argument (shape / null pointer / unsupported size) */
+#define MCNERF_E_UNSUPPORTED 10002
+
+int mcnerf_abi_version(void);
+const char* mcnerf_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t mcnerf_launch_count(void);
+
+/* ------------------------------------------------------------------ camera model (a2-a4, a7)
+ * ref: model/mc_nerf.py:171-186 (add_weights2intr), :204-210 (inverse_intrinsic, closed form here),
+ *      :269-316 (se3_to_SE3 with the 11-term Taylor series A,B,C). */
+int mcnerf_intrinsics_fwd(const float* w_fx, const float* w_fy, const float* w_ux, const float* w_uy,
+                          int n_cam, int img_h, int img_w,
+                          float* K /*[n,3,3]*/, float* Kinv /*[n,3,3]*/, void* stream);
+/* g_w* overwritten. gK / gKinv may be NULL. */
+int mcnerf_intrinsics_bwd(const float* w_fx, const float* w_fy, const float* w_ux, const float* w_uy,
+                          int n_cam, int img_h, int img_w, const float* gK, const float* gKinv,
+                          float* g_fx, float* g_fy, float* g_ux, float* g_uy, void* stream);
+int mcnerf_se3_fwd(const float* wu /*[n,6]*/, int n, float* Rt /*[n,3,4] world->camera*/, void* stream);
+int mcnerf_se3_bwd(const float* wu, const float* gRt, int n, float* g_wu /*overwritten*/, void* stream);
+
+/* ------------------------------------------------------------------ ray generation (a5, a6)
+ * ref: model/mc_nerf.py:124-145 (get_rays), :229-256 (pix2cam, cam2world), :327-345 (gather of the
+ * randperm subset).  Ray r uses camera cam_id[r] (or `cam_const` when cam_id is NULL) and pixel
+ * pix[r] = y*img_w + x (or r itself when pix is NULL: a full image in row-major order). */
+int mcnerf_raygen_fwd(const float* Kinv, const float* Rt, const int32_t* cam_id, int cam_const,
+                      const int32_t* pix, int n_rays, int img_w,
+                      float* rays_o /*[n,3]*/, float* rays_d /*[n,3]*/, void* stream);
+/* accumulate into gKinv [n_cam,3,3] and gRt [n_cam,3,4] (fused per-camera reduction, G5). */
+int mcnerf_raygen_bwd(const float* Kinv, const float* Rt, const int32_t* cam_id, int cam_const,
+                      const int32_t* pix, int n_rays, int img_w,
+                      const float* g_rays_o, const float* g_rays_d,
+                      float* gKinv, float* gRt, void* stream);
+
+/* ------------------------------------------------------------------ sampling + encoding (a8-a10)
+ * ref: model/mc_nerf.py:599-602, 633-635 (z = linspace(near,far,S) + per-ray jitter, x = o + d z),
+ *      model/net_block.py:20-35 (sin/cos encoding, BARF window).
+ * Row m of the output encodes one sample.  Which sample:
+ *   sample_idx == NULL : m = ray*S + k            (dense; n_rows = n_rays*S)
+ *   sample_idx != NULL : sample_idx[m] = ray*S + k (n_rows read from *n_rows_dev if non-NULL, else n_rows)
+ * enc is [n_rows, ld_enc] with 3+6L valid columns (x,y,z, then per coordinate L sines, L cosines);
+ * band_w[L] are the BARF weights (all 1 when the window is off). */
+typedef struct {
+  float near_, far_;
+  int S;            /* samples per ray on this grid (coarse: Sc, fine: Sc*scale) */
+  int n_freqs;      /* L */
+  float band_w[MCNERF_MAX_FREQS];
+} mcnerf_sampling;
+
+int mcnerf_encode_rays_fwd(const float* rays_o, const float* rays_d, const float* jitter /*[n_rays] or NULL*/,
+                           int n_rays, const mcnerf_sampling* smp,
+                           const int32_t* sample_idx, int n_rows, const int32_t* n_rows_dev,
+                           float* enc, int ld_enc, void* stream);
+/* g_enc [n_rows, ld_enc] -> accumulate into g_rays_o, g_rays_d [n_rays,3]. */
+int mcnerf_encode_rays_bwd(const float* rays_o, const float* rays_d, const float* jitter,
+                           int n_rays, const mcnerf_sampling* smp,
+                           const int32_t* sample_idx, int n_rows, const int32_t* n_rows_dev,
+                           const float* g_enc, int ld_enc, float* g_rays_o, float* g_rays_d, void* stream);
+/* SinCosEmbedding.forward on explicit points x [n,3] (ref: model/net_block.py:20-35). */
+int mcnerf_encode_points_fwd(const float* x, int n, int n_freqs, const float* band_w_host,
+                             float* enc, int ld_enc, void* stream);
+int mcnerf_encode_points_bwd(const float* x, int n, int n_freqs, const float* band_w_host,
+                             const float* g_enc, int ld_enc, float* g_x /*[n,3] overwritten*/, void* stream);
+
+/* ------------------------------------------------------------------ NeRF MLP (a11, a12)
+ * ref: model/net_block.py:37-78 (CorseFine_NeRF), model/net_utils.py:103-191 (eval_sh, deg 2).
+ * Parameters are the reference's own tensors: row-major [out,in] fp32 weights and [out] biases. */
+typedef struct {
+  int depth, width, in_ch;     /* in_ch = 3+6L = 63 */
+  uint32_t skip_mask;          /* bit i set: layer i (0-based) takes cat([x_enc, h]) */
+  int sh_dim;                  /* 3*(deg+1)^2 = 27; only deg 2 is implemented */
+  const float* W[MCNERF_MAX_DEPTH];
+  const float* b[MCNERF_MAX_DEPTH];
+  const float *W_sigma0, *b_sigma0, *W_sigma2, *b_sigma2;
+  const float *W_sh0, *b_sh0, *W_sh2, *b_sh2;
+} mcnerf_mlp_params;
+
+typedef struct {               /* same shapes as the parameters; accumulated into */
+  float* W[MCNERF_MAX_DEPTH];
+  float* b[MCNERF_MAX_DEPTH];
+  float *W_sigma0, *b_sigma0, *W_sigma2, *b_sigma2;
+  float *W_sh0, *b_sh0, *W_sh2, *b_sh2;
+} mcnerf_mlp_grads;
+
+/* How row m finds its view direction: dirs[m] (per_row), dirs[ray_of_row[m]/S...]:
+ *   dir_idx == NULL && dir_S == 0 : dirs is [n_rows,3]
+ *   dir_idx == NULL && dir_S  > 0 : dirs is [n_rays,3], ray = m / dir_S
+ *   dir_idx != NULL               : dirs is [n_rays,3], ray = dir_idx[m] / dir_S  (dir_idx = sample_idx) */
+typedef struct {
+  const float* dirs;
+  const int32_t* dir_idx;
+  int dir_S;
+} mcnerf_dirs;
+
+/* workspace size in BYTES for n_rows rows (activations kept for the backward pass) */
+size_t mcnerf_mlp_f32_workspace(const mcnerf_mlp_params* p, int n_rows);
+/* fp32 CUDA-core path (exact-parity mode; any depth/width/skips).  out4 [n_rows,4] = (sigma_raw, r, g, b). */
+int mcnerf_mlp_f32_fwd(const mcnerf_mlp_params* p, const float* x_enc, int ld_enc, const mcnerf_dirs* d,
+                       int n_rows, const int32_t* n_rows_dev, float* out4, void* workspace, void* stream);
+/* g_x_enc [n_rows, ld_enc] overwritten (may be NULL); g_dirs accumulated: [n_rows,3] or [n_rays,3] matching `d`
+ * (may be NULL); parameter grads accumulated. */
+int mcnerf_mlp_f32_bwd(const mcnerf_mlp_params* p, const float* x_enc, int ld_enc, const mcnerf_dirs* d,
+                       int n_rows, const int32_t* n_rows_dev, const float* g_out4, void* workspace,
+                       const mcnerf_mlp_grads* g, float* g_x_enc, float* g_dirs, void* stream);
+/* eval_sh (deg 2) standalone: sh [n,3,9], dirs [n,3] -> out [n,3]  (ref: model/net_utils.py:103-191) */
+int mcnerf_eval_sh_fwd(const float* sh, const float* dirs, int n, float* out, void* stream);
+int mcnerf_eval_sh_bwd(const float* sh, const float* dirs, const float* g_out, int n,
+                       float* g_sh, float* g_dirs, void* stream);
+
+/* ------------------------------------------------------------------ compositing (a13, a14)
+ * ref: model/mc_nerf.py:705-736.  One warp per ray, warp-scan over samples.
+ * z values: z_vals [B,S] if non-NULL else near + k*(far-near)/(S-1) (+ jitter[ray]); delta_last = 1e10.
+ *  (i)  noise-free:  alpha = 1-exp(-softplus(sigma)*delta*|d|), T = exp(-excl.cumsum) -> depth, opacity
+ *  (ii) noisy:       w = alpha' * excl.cumprod(1-alpha'+1e-10), alpha' = 1-exp(-delta*softplus(sigma+noise))
+ *                    rgb = sum w c (+ 1 - sum w when white_back)
+ * out4 is [B,S,4]; noise [B,S] or NULL (= 0). */
+typedef struct {
+  float near_, far_;
+  int S;
+  int white_back;
+} mcnerf_composite_cfg;
+
+int mcnerf_composite_fwd(const float* out4, const float* noise, const float* rays_d, const float* jitter,
+                         const float* z_vals, int n_rays, const mcnerf_composite_cfg* cfg,
+                         float* rgb /*[B,3]*/, float* depth /*[B] or NULL*/, float* opacity /*[B] or NULL*/,
+                         float* weights /*[B,S] or NULL*/, void* stream);
+/* g_out4 [B,S,4] overwritten.  Only d/d(rgb) is propagated (the reference discards depth/opacity in training,
+ * ref: model/mc_nerf.py:590-591,646). */
+int mcnerf_composite_bwd(const float* out4, const float* noise, const float* jitter, const float* z_vals,
+                         int n_rays, const mcnerf_composite_cfg* cfg, const float* g_rgb,
+                         float* g_out4, void* stream);
+/* sigma2weights alone (ref: model/mc_nerf.py:729-736): sigma read with stride `sigma_stride` floats
+ * (4 to read it out of out4, 1 for a dense [B,S] tensor); also folds max(w) into *w_max (atomic; caller zeroes). */
+int mcnerf_sigma2weights(const float* sigma, int sigma_stride, const float* noise, const float* jitter,
+                         const float* z_vals, const float* deltas /*[B,S] or NULL (explicit deltas)*/,
+                         int n_rays, const mcnerf_composite_cfg* cfg,
+                         float* weights, float* w_max, void* stream);
+
+/* ------------------------------------------------------------------ fine-sample selection (a15)
+ * ref: model/mc_nerf.py:623-629, 663-667.  keep coarse sample (r,i) iff w[r,i] >= min(thresh, *w_max);
+ * emits flat fine indices r*Sf + i*scale + j (ray-major, ascending - the order torch.nonzero gives),
+ * *n_sel = count, sel_offsets[r] = first position of ray r (B+1 entries).  No host synchronisation. */
+int mcnerf_select_fine(const float* weights, const float* w_max, int n_rays, int Sc, int scale, float thresh,
+                       int32_t* sel_idx /*[B*Sc*scale] capacity*/, int32_t* sel_offsets /*[B+1]*/,
+                       int32_t* n_sel, void* stream);
+/* out_dense [B*Sf,4] = (sigma_default,1,1,1) everywhere, then out_dense[sel_idx[m]] = out_sel[m]
+ * (ref: model/mc_nerf.py:692-694, 700-701). */
+int mcnerf_scatter_fine(const float* out_sel, const int32_t* sel_idx, int n_sel, const int32_t* n_sel_dev,
+                        int n_dense_rows, float sigma_default, float* out_dense, void* stream);
+/* g_sel[m] = g_dense[sel_idx[m]] */
+int mcnerf_gather_fine(const float* g_dense, const int32_t* sel_idx, int n_sel, const int32_t* n_sel_dev,
+                       float* g_sel, void* stream);
+
+/* ------------------------------------------------------------------ loss seed + optimiser (f-1, f-2)
+ * ref: model/loss.py:33-43.  loss += mean((rgb_c-gt)^2) + mean((rgb_f-gt)^2) (atomic into *loss);
+ * g_c = 2(rgb_c-gt)/(3B)*grad_scale, g_f likewise.  gt_idx (may be NULL) gathers gt rows. */
+int mcnerf_rgb_loss(const float* rgb_c, const float* rgb_f, const float* gt, const int32_t* gt_idx, int n_rays,
+                    float grad_scale, float* loss, float* g_c, float* g_f, void* stream);
+/* ref: model/net_utils.py:10-101 (RAdam.step) on one flat buffer.  The host evaluates the scalar schedule
+ * (N_sma, step_size - incl. the 10-slot cache semantics) and passes it in:
+ *   mode 1 (N_sma >= 5): p -= wd*lr*p ; p -= step_size*lr * m/(sqrt(v)+eps)
+ *   mode 2 (degenerate): p -= wd*lr*p ; p -= step_size*lr * m
+ *   mode 0: moments only. */
+int mcnerf_radam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay,
+                      float step_size, int mode, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCNERF_H_ */

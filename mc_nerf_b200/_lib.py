@@ -1,0 +1,119 @@
+"""ctypes binding of libmcnerf.so (the C ABI declared in include/mcnerf.h).
+
+The prototypes are parsed from the header itself so the Python side cannot drift from the ABI.
+There is NO fallback: if the shared library is missing or a call fails, we raise.
+"""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+HEADER = os.path.join(ROOT, "include", "mcnerf.h")
+LIB_PATH = os.path.join(HERE, "csrc", "libmcnerf.so")
+
+MAX_DEPTH = 16
+MAX_FREQS = 16
+_fp = ctypes.c_void_p
+
+
+class Sampling(ctypes.Structure):
+    _fields_ = [("near_", ctypes.c_float), ("far_", ctypes.c_float), ("S", ctypes.c_int),
+                ("n_freqs", ctypes.c_int), ("band_w", ctypes.c_float * MAX_FREQS)]
+
+
+class MlpParams(ctypes.Structure):
+    _fields_ = [("depth", ctypes.c_int), ("width", ctypes.c_int), ("in_ch", ctypes.c_int),
+                ("skip_mask", ctypes.c_uint32), ("sh_dim", ctypes.c_int),
+                ("W", _fp * MAX_DEPTH), ("b", _fp * MAX_DEPTH),
+                ("W_sigma0", _fp), ("b_sigma0", _fp), ("W_sigma2", _fp), ("b_sigma2", _fp),
+                ("W_sh0", _fp), ("b_sh0", _fp), ("W_sh2", _fp), ("b_sh2", _fp)]
+
+
+class MlpGrads(ctypes.Structure):
+    _fields_ = [("W", _fp * MAX_DEPTH), ("b", _fp * MAX_DEPTH),
+                ("W_sigma0", _fp), ("b_sigma0", _fp), ("W_sigma2", _fp), ("b_sigma2", _fp),
+                ("W_sh0", _fp), ("b_sh0", _fp), ("W_sh2", _fp), ("b_sh2", _fp)]
+
+
+class Dirs(ctypes.Structure):
+    _fields_ = [("dirs", _fp), ("dir_idx", _fp), ("dir_S", ctypes.c_int)]
+
+
+class CompositeCfg(ctypes.Structure):
+    _fields_ = [("near_", ctypes.c_float), ("far_", ctypes.c_float), ("S", ctypes.c_int),
+                ("white_back", ctypes.c_int)]
+
+
+_STRUCTS = {"mcnerf_sampling": Sampling, "mcnerf_mlp_params": MlpParams, "mcnerf_mlp_grads": MlpGrads,
+            "mcnerf_dirs": Dirs, "mcnerf_composite_cfg": CompositeCfg}
+_SCALARS = {"int": ctypes.c_int, "float": ctypes.c_float, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
+            "uint64_t": ctypes.c_uint64, "uint32_t": ctypes.c_uint32, "void": None}
+
+
+def parse_header(path=HEADER):
+    """-> {name: (restype, [argtypes])} for every prototype in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", " ", src)
+    src = re.sub(r"^\s*#[^\n]*", " ", src, flags=re.M)
+    src = re.sub(r'extern\s+"C"\s*\{', " ", src)
+    src = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", " ", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"([\w\s\*]+?)\b(mcnerf_\w+)\s*\(([^;{}]*)\)\s*;", src):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        if "*" in ret:
+            restype = ctypes.c_char_p if "char" in ret else ctypes.c_void_p
+        else:
+            restype = _SCALARS[ret.replace("const", "").strip()]
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.replace("const", " ").split())
+                if "*" in a:
+                    base = a.split("*")[0].strip()
+                    argtypes.append(ctypes.POINTER(_STRUCTS[base]) if base in _STRUCTS else ctypes.c_void_p)
+                else:
+                    argtypes.append(_SCALARS[a.split()[0]])
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+class McnerfError(RuntimeError):
+    pass
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise McnerfError(
+                f"{LIB_PATH} is missing: build it with `python -m mc_nerf_b200.build` "
+                "(there is no CPU or PyTorch fallback for the MC-NeRF hot path)")
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.protos = parse_header()
+        for name, (restype, argtypes) in self.protos.items():
+            fn = getattr(self.cdll, name)      # AttributeError if the .so does not export a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if self.cdll.mcnerf_abi_version() != 1:
+            raise McnerfError("libmcnerf.so ABI version mismatch")
+
+    def call(self, name, *args):
+        """Call an int-returning entry; raise McnerfError(mcnerf_last_error()) on failure."""
+        rc = getattr(self.cdll, name)(*args)
+        if rc != 0:
+            msg = self.cdll.mcnerf_last_error()
+            raise McnerfError(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+    def launch_count(self):
+        return int(self.cdll.mcnerf_launch_count())
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = _Lib()
+    return _LIB

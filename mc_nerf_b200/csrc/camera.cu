@@ -1,0 +1,224 @@
+// Camera model: learnable intrinsics and se(3) extrinsics, forward and analytic backward.
+// One thread per camera (110 cameras: latency-bound, a single small launch replaces the reference's
+// ~150 tiny ATen launches + a 110-iteration torch.inverse loop).
+// ref: model/mc_nerf.py:171-186 (add_weights2intr), :204-210 (inverse_intrinsic), :269-316 (se3_to_SE3).
+#include "common.cuh"
+
+namespace {
+
+__global__ void intrinsics_fwd_k(const float* __restrict__ wfx, const float* __restrict__ wfy,
+                                 const float* __restrict__ wux, const float* __restrict__ wuy, int n, float H, float W,
+                                 float* __restrict__ K, float* __restrict__ Kinv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // sic: fy is scaled by the image WIDTH in the reference (model/mc_nerf.py:173)
+  float fx = fabsf(W * wfx[i]), fy = fabsf(W * wfy[i]);
+  float ux = fabsf(W * 0.5f * wux[i]), uy = fabsf(H * 0.5f * wuy[i]);
+  float* k = K + 9 * i;
+  k[0] = fx; k[1] = 0.f; k[2] = ux;
+  k[3] = 0.f; k[4] = fy; k[5] = uy;
+  k[6] = 0.f; k[7] = 0.f; k[8] = 1.f;
+  if (Kinv) {
+    float ifx = 1.f / fx, ify = 1.f / fy;
+    float* q = Kinv + 9 * i;
+    q[0] = ifx; q[1] = 0.f; q[2] = -ux * ifx;
+    q[3] = 0.f; q[4] = ify; q[5] = -uy * ify;
+    q[6] = 0.f; q[7] = 0.f; q[8] = 1.f;
+  }
+}
+
+__device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+__global__ void intrinsics_bwd_k(const float* __restrict__ wfx, const float* __restrict__ wfy,
+                                 const float* __restrict__ wux, const float* __restrict__ wuy, int n, float H, float W,
+                                 const float* __restrict__ gK, const float* __restrict__ gKinv,
+                                 float* __restrict__ gfx, float* __restrict__ gfy, float* __restrict__ gux,
+                                 float* __restrict__ guy) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float afx = W * wfx[i], afy = W * wfy[i], aux = W * 0.5f * wux[i], auy = H * 0.5f * wuy[i];
+  float fx = fabsf(afx), fy = fabsf(afy), ux = fabsf(aux), uy = fabsf(auy);
+  float d_fx = 0.f, d_fy = 0.f, d_ux = 0.f, d_uy = 0.f;
+  if (gK) {
+    const float* g = gK + 9 * i;
+    d_fx += g[0]; d_ux += g[2]; d_fy += g[4]; d_uy += g[5];
+  }
+  if (gKinv) {
+    const float* g = gKinv + 9 * i;
+    float ifx = 1.f / fx, ify = 1.f / fy;
+    // Kinv00 = 1/fx, Kinv02 = -ux/fx, Kinv11 = 1/fy, Kinv12 = -uy/fy
+    d_fx += -g[0] * ifx * ifx + g[2] * ux * ifx * ifx;
+    d_ux += -g[2] * ifx;
+    d_fy += -g[4] * ify * ify + g[5] * uy * ify * ify;
+    d_uy += -g[5] * ify;
+  }
+  gfx[i] = d_fx * sgn(afx) * W;
+  gfy[i] = d_fy * sgn(afy) * W;
+  gux[i] = d_ux * sgn(aux) * W * 0.5f;
+  guy[i] = d_uy * sgn(auy) * H * 0.5f;
+}
+
+// 11-term series (nth = 10) of A = sin t / t, B = (1 - cos t)/t^2, C = (t - sin t)/t^3 and their
+// derivatives with respect to t.  The reference evaluates exactly these truncated series, so closed
+// forms would DIVERGE from it for large angles.
+struct Series { float A, B, C, dA, dB, dC; };
+__device__ Series taylor_abc(float t) {
+  Series s = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float t2 = t * t;
+  float p = 1.f;       // t^(2i)
+  float pm1 = 0.f;     // t^(2i-1)
+  double dA = 1.0, dB = 1.0, dC = 1.0;
+  for (int i = 0; i <= 10; ++i) {
+    if (i > 0) dA *= (double)((2 * i) * (2 * i + 1));
+    dB *= (double)((2 * i + 1) * (2 * i + 2));
+    dC *= (double)((2 * i + 2) * (2 * i + 3));
+    float sg = (i & 1) ? -1.f : 1.f;
+    s.A += sg * p / (float)dA;
+    s.B += sg * p / (float)dB;
+    s.C += sg * p / (float)dC;
+    if (i > 0) {
+      float c = sg * (float)(2 * i) * pm1;
+      s.dA += c / (float)dA;
+      s.dB += c / (float)dB;
+      s.dC += c / (float)dC;
+    }
+    pm1 = p * t;       // t^(2i+1)
+    p = p * t2;
+  }
+  return s;
+}
+
+__device__ __forceinline__ void skew(const float w[3], float wx[9]) {
+  wx[0] = 0.f;   wx[1] = -w[2]; wx[2] = w[1];
+  wx[3] = w[2];  wx[4] = 0.f;   wx[5] = -w[0];
+  wx[6] = -w[1]; wx[7] = w[0];  wx[8] = 0.f;
+}
+__device__ __forceinline__ void mat3_mul(const float a[9], const float b[9], float c[9]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+
+__global__ void se3_fwd_k(const float* __restrict__ wu, int n, float* __restrict__ Rt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float w[3] = {wu[6 * i], wu[6 * i + 1], wu[6 * i + 2]};
+  float u[3] = {wu[6 * i + 3], wu[6 * i + 4], wu[6 * i + 5]};
+  float th = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  Series s = taylor_abc(th);
+  float wx[9], wx2[9];
+  skew(w, wx);
+  mat3_mul(wx, wx, wx2);
+  float* o = Rt + 12 * i;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float t = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float I = (r == c) ? 1.f : 0.f;
+      o[4 * r + c] = I + s.A * wx[3 * r + c] + s.B * wx2[3 * r + c];
+      float V = I + s.B * wx[3 * r + c] + s.C * wx2[3 * r + c];
+      t += V * u[c];
+    }
+    o[4 * r + 3] = t;
+  }
+}
+
+__global__ void se3_bwd_k(const float* __restrict__ wu, const float* __restrict__ gRt, int n, float* __restrict__ gwu) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float w[3] = {wu[6 * i], wu[6 * i + 1], wu[6 * i + 2]};
+  float u[3] = {wu[6 * i + 3], wu[6 * i + 4], wu[6 * i + 5]};
+  float th = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  Series s = taylor_abc(th);
+  float wx[9], wx2[9];
+  skew(w, wx);
+  mat3_mul(wx, wx, wx2);
+  const float* g = gRt + 12 * i;
+  float gR[9], gt[3], gV[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gR[3 * r + c] = g[4 * r + c];
+    gt[r] = g[4 * r + 3];
+  }
+  // t = V u  ->  gu = V^T gt, gV = gt u^T
+  float gu[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float V = ((r == c) ? 1.f : 0.f) + s.B * wx[3 * r + c] + s.C * wx2[3 * r + c];
+      gu[c] += V * gt[r];
+      gV[3 * r + c] = gt[r] * u[c];
+    }
+  float gA = 0.f, gB = 0.f, gC = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    gA += gR[k] * wx[k];
+    gB += gR[k] * wx2[k] + gV[k] * wx[k];
+    gC += gV[k] * wx2[k];
+  }
+  // d<G, wx^2>/d wx = G wx^T + wx^T G
+  float P[9];   // P = B*gR + C*gV  (the coefficient matrix of wx^2)
+  float G[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    P[k] = s.B * gR[k] + s.C * gV[k];
+    G[k] = s.A * gR[k] + s.B * gV[k];
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) a += P[3 * r + k] * wx[3 * c + k] + wx[3 * k + r] * P[3 * k + c];
+      G[3 * r + c] += a;
+    }
+  float gw[3] = {G[7] - G[5], G[2] - G[6], G[3] - G[1]};
+  float gth = gA * s.dA + gB * s.dB + gC * s.dC;
+  // theta = |w| (norm backward; NaN at w = 0 exactly as torch's norm backward gives 0/0 -> we return 0 there)
+  float inv = th > 0.f ? 1.f / th : 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    gwu[6 * i + k] = gw[k] + gth * w[k] * inv;
+    gwu[6 * i + 3 + k] = gu[k];
+  }
+}
+
+}  // namespace
+
+extern "C" int mcnerf_intrinsics_fwd(const float* w_fx, const float* w_fy, const float* w_ux, const float* w_uy,
+                                     int n_cam, int img_h, int img_w, float* K, float* Kinv, void* stream) {
+  MC_ARG(w_fx && w_fy && w_ux && w_uy && K && n_cam > 0);
+  intrinsics_fwd_k<<<cdiv(n_cam, 128), 128, 0, (cudaStream_t)stream>>>(w_fx, w_fy, w_ux, w_uy, n_cam, (float)img_h,
+                                                                        (float)img_w, K, Kinv);
+  MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcnerf_intrinsics_bwd(const float* w_fx, const float* w_fy, const float* w_ux, const float* w_uy,
+                                     int n_cam, int img_h, int img_w, const float* gK, const float* gKinv,
+                                     float* g_fx, float* g_fy, float* g_ux, float* g_uy, void* stream) {
+  MC_ARG(w_fx && w_fy && w_ux && w_uy && g_fx && g_fy && g_ux && g_uy && n_cam > 0);
+  intrinsics_bwd_k<<<cdiv(n_cam, 128), 128, 0, (cudaStream_t)stream>>>(w_fx, w_fy, w_ux, w_uy, n_cam, (float)img_h,
+                                                                        (float)img_w, gK, gKinv, g_fx, g_fy, g_ux, g_uy);
+  MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcnerf_se3_fwd(const float* wu, int n, float* Rt, void* stream) {
+  MC_ARG(wu && Rt && n > 0);
+  se3_fwd_k<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(wu, n, Rt);
+  MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcnerf_se3_bwd(const float* wu, const float* gRt, int n, float* g_wu, void* stream) {
+  MC_ARG(wu && gRt && g_wu && n > 0);
+  se3_bwd_k<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(wu, gRt, n, g_wu);
+  MC_LAUNCHED();
+  return 0;
+}

@@ -1,0 +1,430 @@
+// fp32 CUDA-core NeRF MLP (exact-parity mode): any depth / width / skip set, forward and backward.
+// ref: model/net_block.py:37-78 (CorseFine_NeRF), model/net_utils.py:103-191 (eval_sh deg 2).
+// Layer-by-layer strided SGEMM tiles (128x64x16, 8x4 register micro-tile) with fused bias / ReLU /
+// ReLU-mask epilogues.  The bf16 tcgen05 path (mlp_tc.cu) is the throughput path; this one exists so that
+// every configuration the reference's config.yaml can express runs, and so parity can be shown at fp32.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, NT = 256, PAD = 4;
+enum { F_ACCUM = 1, F_RELU = 2, F_ATOMIC = 4 };
+
+struct Gemm {
+  const float* A; int64_t sAi, sAr;    // A(i,r) = A[i*sAi + r*sAr]
+  const float* B; int64_t sBj, sBr;    // B(j,r)
+  float* C; int64_t ldc;               // C(i,j) = C[i*ldc + j]
+  int M, N, R;                         // extents of i, j and the reduction index r
+  const float* bias;                   // [N] or null
+  const float* mask; int64_t ldm;      // multiply by (mask(i,j) > 0) or null
+  int flags;
+  const int32_t* rows_dev;             // device row count (clamps M, or R when rows_on_r)
+  int rows_on_r;
+};
+
+__global__ void __launch_bounds__(NT) sgemm_k(Gemm g) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  int M = g.M, R = g.R;
+  if (g.rows_dev) {
+    int rows = *g.rows_dev;
+    if (g.rows_on_r) R = min(R, rows); else M = min(M, rows);
+  }
+  const int i0 = blockIdx.x * BM, j0 = blockIdx.y * BN;
+  if (i0 >= M) return;
+  // split the reduction range over gridDim.z
+  int rchunk = (R + gridDim.z - 1) / gridDim.z;
+  rchunk = (rchunk + BK - 1) / BK * BK;
+  const int r_begin = blockIdx.z * rchunk;
+  const int r_end = min(R, r_begin + rchunk);
+  if (r_begin >= r_end) return;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const bool a_r_contig = (g.sAr == 1), b_r_contig = (g.sBr == 1);
+  for (int r0 = r_begin; r0 < r_end; r0 += BK) {
+    // A tile: BM x BK = 2048 elements, 8 per thread
+#pragma unroll
+    for (int e = 0; e < (BM * BK) / NT; ++e) {
+      int idx = e * NT + t;
+      int i, r;
+      if (a_r_contig) { i = idx / BK; r = idx % BK; } else { r = idx / BM; i = idx % BM; }
+      int gi = i0 + i, gr = r0 + r;
+      As[r][i] = (gi < M && gr < r_end) ? g.A[gi * g.sAi + gr * g.sAr] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < (BN * BK) / NT; ++e) {
+      int idx = e * NT + t;
+      int j, r;
+      if (b_r_contig) { j = idx / BK; r = idx % BK; } else { r = idx / BN; j = idx % BN; }
+      int gj = j0 + j, gr = r0 + r;
+      Bs[r][j] = (gj < g.N && gr < r_end) ? g.B[gj * g.sBj + gr * g.sBr] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < BK; ++r) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[r][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[r][ty * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[r][tx * 4]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    int gi = i0 + ty * 8 + a;
+    if (gi >= M) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int gj = j0 + tx * 4 + c;
+      if (gj >= g.N) continue;
+      float* dst = g.C + gi * g.ldc + gj;
+      float v = acc[a][c];
+      if (g.flags & F_ATOMIC) { atomicAdd(dst, v); continue; }
+      if (g.flags & F_ACCUM) v += *dst;
+      if (g.bias) v += g.bias[gj];
+      if (g.flags & F_RELU) v = fmaxf(v, 0.f);
+      if (g.mask) v = (g.mask[gi * g.ldm + gj] > 0.f) ? v : 0.f;
+      *dst = v;
+    }
+  }
+}
+
+// column sums: out[j] += sum_i X[i*ld + j]
+__global__ void colsum_k(const float* __restrict__ X, int64_t ld, int M, int N, const int32_t* __restrict__ rows_dev,
+                         float* __restrict__ out) {
+  if (rows_dev) M = min(M, *rows_dev);
+  __shared__ float sm[8][33];
+  int j = blockIdx.x * 32 + threadIdx.x;
+  int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  int i_begin = blockIdx.y * rows_per, i_end = min(M, i_begin + rows_per);
+  float s = 0.f;
+  if (j < N)
+    for (int i = i_begin + threadIdx.y; i < i_end; i += 8) s += X[i * ld + j];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < N) {
+    float tot = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tot += sm[y][threadIdx.x];
+    atomicAdd(out + j, tot);
+  }
+}
+
+// ---- SH (deg 2) colour head.  ref: model/net_utils.py:154-169, model/net_block.py:75-77
+__constant__ float kC0 = 0.28209479177387814f;
+__constant__ float kC1 = 0.4886025119029199f;
+__constant__ float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                             -1.0925484305920792f, 0.5462742152960396f};
+
+__device__ __forceinline__ void sh_basis(float x, float y, float z, float Y[9]) {
+  Y[0] = kC0; Y[1] = -kC1 * y; Y[2] = kC1 * z; Y[3] = -kC1 * x;
+  Y[4] = kC2[0] * (x * y); Y[5] = kC2[1] * (y * z); Y[6] = kC2[2] * (2.f * z * z - x * x - y * y);
+  Y[7] = kC2[3] * (x * z); Y[8] = kC2[4] * (x * x - y * y);
+}
+// d(sum_b Y_b s_b)/d(x,y,z)
+__device__ __forceinline__ void sh_basis_grad(float x, float y, float z, const float s[9], float g[3]) {
+  g[0] = -kC1 * s[3] + kC2[0] * y * s[4] - 2.f * kC2[2] * x * s[6] + kC2[3] * z * s[7] + 2.f * kC2[4] * x * s[8];
+  g[1] = -kC1 * s[1] + kC2[0] * x * s[4] + kC2[1] * z * s[5] - 2.f * kC2[2] * y * s[6] - 2.f * kC2[4] * y * s[8];
+  g[2] = kC1 * s[2] + kC2[1] * y * s[5] + 4.f * kC2[2] * z * s[6] + kC2[3] * x * s[7];
+}
+
+__device__ __forceinline__ int dir_row(const mcnerf_dirs& d, int m) {
+  if (d.dir_idx) return d.dir_idx[m] / d.dir_S;
+  if (d.dir_S > 0) return m / d.dir_S;
+  return m;
+}
+
+__global__ void head_fwd_k(const float* __restrict__ sig, const float* __restrict__ sh, int ld_sh, mcnerf_dirs d,
+                           int n, const int32_t* __restrict__ rows_dev, float4* __restrict__ out4) {
+  if (rows_dev) n = min(n, *rows_dev);
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  int dr = dir_row(d, m);
+  float Y[9];
+  sh_basis(d.dirs[3 * dr], d.dirs[3 * dr + 1], d.dirs[3 * dr + 2], Y);
+  const float* s = sh + (size_t)m * ld_sh;
+  float c[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float v = 0.f;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) v += Y[b] * s[9 * ch + b];
+    c[ch] = sigmoid_f(v);
+  }
+  out4[m] = make_float4(sig[m], c[0], c[1], c[2]);
+}
+
+__global__ void head_bwd_k(const float4* __restrict__ out4, const float* __restrict__ sh, int ld_sh, mcnerf_dirs d,
+                           int n, const int32_t* __restrict__ rows_dev, const float4* __restrict__ g_out4,
+                           float* __restrict__ g_sig, float* __restrict__ g_sh, float* __restrict__ g_dirs) {
+  if (rows_dev) n = min(n, *rows_dev);
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  int dr = dir_row(d, m);
+  float x = d.dirs[3 * dr], y = d.dirs[3 * dr + 1], z = d.dirs[3 * dr + 2];
+  float Y[9];
+  sh_basis(x, y, z, Y);
+  float4 o = out4[m], g = g_out4[m];
+  g_sig[m] = g.x;
+  float gc[3] = {g.y * o.y * (1.f - o.y), g.z * o.z * (1.f - o.z), g.w * o.w * (1.f - o.w)};
+  const float* s = sh + (size_t)m * ld_sh;
+  float* gs = g_sh + (size_t)m * ld_sh;
+  float comb[9];
+#pragma unroll
+  for (int b = 0; b < 9; ++b) comb[b] = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+      gs[9 * ch + b] = gc[ch] * Y[b];
+      comb[b] += gc[ch] * s[9 * ch + b];
+    }
+  if (g_dirs) {
+    float gd[3];
+    sh_basis_grad(x, y, z, comb, gd);
+    if (d.dir_idx || d.dir_S > 0) {
+      atomicAdd(g_dirs + 3 * dr, gd[0]); atomicAdd(g_dirs + 3 * dr + 1, gd[1]); atomicAdd(g_dirs + 3 * dr + 2, gd[2]);
+    } else {
+      g_dirs[3 * m] += gd[0]; g_dirs[3 * m + 1] += gd[1]; g_dirs[3 * m + 2] += gd[2];
+    }
+  }
+}
+
+__global__ void eval_sh_fwd_k(const float* __restrict__ sh, const float* __restrict__ dirs, int n,
+                              float* __restrict__ out) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  float Y[9];
+  sh_basis(dirs[3 * m], dirs[3 * m + 1], dirs[3 * m + 2], Y);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float v = 0.f;
+#pragma unroll
+    for (int b = 0; b < 9; ++b) v += Y[b] * sh[(size_t)m * 27 + 9 * ch + b];
+    out[3 * m + ch] = v;
+  }
+}
+
+__global__ void eval_sh_bwd_k(const float* __restrict__ sh, const float* __restrict__ dirs,
+                              const float* __restrict__ g_out, int n, float* __restrict__ g_sh,
+                              float* __restrict__ g_dirs) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  float x = dirs[3 * m], y = dirs[3 * m + 1], z = dirs[3 * m + 2];
+  float Y[9], comb[9];
+  sh_basis(x, y, z, Y);
+#pragma unroll
+  for (int b = 0; b < 9; ++b) comb[b] = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float g = g_out[3 * m + ch];
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+      g_sh[(size_t)m * 27 + 9 * ch + b] = g * Y[b];
+      comb[b] += g * sh[(size_t)m * 27 + 9 * ch + b];
+    }
+  }
+  float gd[3];
+  sh_basis_grad(x, y, z, comb, gd);
+  g_dirs[3 * m] = gd[0]; g_dirs[3 * m + 1] = gd[1]; g_dirs[3 * m + 2] = gd[2];
+}
+
+// --------------------------------------------------------------------------- host-side plan
+struct Plan {
+  cudaStream_t st;
+  int M;
+  const int32_t* rows_dev;
+  int err = 0;
+
+  void gemm(Gemm g, int splits = 1) {
+    if (err) return;
+    g.rows_dev = rows_dev;
+    dim3 grid(cdiv(g.M, BM), cdiv(g.N, BN), splits);
+    sgemm_k<<<grid, NT, 0, st>>>(g);
+    mcnerf_count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { mcnerf_set_error("sgemm launch: %s", cudaGetErrorString(e)); err = (int)e; }
+  }
+  // Y[M,N] = act(X[M,K] W[N,K]^T (+Y) (+b))
+  void fwd(const float* X, int64_t ldx, int K, const float* W, int64_t ldw, int N, const float* b, float* Y,
+           int64_t ldy, int flags) {
+    Gemm g{X, ldx, 1, W, ldw, 1, Y, ldy, M, N, K, b, nullptr, 0, flags, nullptr, 0};
+    gemm(g);
+  }
+  // dX[M,K] = (dY[M,N] W[N,K]) (+dX) (* mask)
+  void dgrad(const float* dY, int64_t ldy, int N, const float* W, int64_t ldw, int K, float* dX, int64_t ldx,
+             const float* mask, int64_t ldm, int flags) {
+    Gemm g{dY, ldy, 1, W, 1, ldw, dX, ldx, M, K, N, nullptr, mask, ldm, flags, nullptr, 0};
+    gemm(g);
+  }
+  // dW[N,K] += dY[M,N]^T X[M,K]
+  void wgrad(const float* dY, int64_t ldy, int N, const float* X, int64_t ldx, int K, float* dW, int64_t ldw) {
+    Gemm g{dY, 1, ldy, X, 1, ldx, dW, ldw, N, K, M, nullptr, nullptr, 0, F_ATOMIC, nullptr, 1};
+    int tiles = cdiv(N, BM) * cdiv(K, BN);
+    int splits = max(1, min(cdiv(M, 4 * BK), (148 * 4) / tiles));
+    gemm(g, splits);
+  }
+  void bgrad(const float* dY, int64_t ldy, int N, float* db) {
+    if (err) return;
+    dim3 grid(cdiv(N, 32), max(1, min(cdiv(M, 256), 64)));
+    colsum_k<<<grid, dim3(32, 8), 0, st>>>(dY, ldy, M, N, rows_dev, db);
+    mcnerf_count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { mcnerf_set_error("colsum launch: %s", cudaGetErrorString(e)); err = (int)e; }
+  }
+};
+
+constexpr int LD_SH = 28;
+
+struct Workspace {
+  float* h[MCNERF_MAX_DEPTH];
+  float *s0, *c0, *sh, *sig, *bufA, *bufB, *g_sh, *g_sig;
+};
+
+size_t ws_floats(const mcnerf_mlp_params* p, int64_t n) {
+  return (size_t)n * ((size_t)p->width * (p->depth + 4) + 2 * LD_SH + 2);
+}
+
+Workspace carve(const mcnerf_mlp_params* p, int64_t n, void* ws) {
+  Workspace w;
+  float* f = (float*)ws;
+  size_t W = p->width;
+  for (int i = 0; i < p->depth; ++i) { w.h[i] = f; f += n * W; }
+  w.s0 = f; f += n * W;
+  w.c0 = f; f += n * W;
+  w.bufA = f; f += n * W;
+  w.bufB = f; f += n * W;
+  w.sh = f; f += n * LD_SH;
+  w.g_sh = f; f += n * LD_SH;
+  w.sig = f; f += n;
+  w.g_sig = f; f += n;
+  return w;
+}
+
+int check_params(const mcnerf_mlp_params* p) {
+  MC_ARG(p && p->depth >= 1 && p->depth <= MCNERF_MAX_DEPTH && p->width >= 1 && p->in_ch >= 3 && p->sh_dim == 27);
+  MC_ARG((p->skip_mask & 1u) == 0);
+  for (int i = 0; i < p->depth; ++i) MC_ARG(p->W[i] && p->b[i]);
+  MC_ARG(p->W_sigma0 && p->b_sigma0 && p->W_sigma2 && p->b_sigma2 && p->W_sh0 && p->b_sh0 && p->W_sh2 && p->b_sh2);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t mcnerf_mlp_f32_workspace(const mcnerf_mlp_params* p, int n_rows) {
+  if (!p || n_rows <= 0) return 0;
+  return ws_floats(p, n_rows) * sizeof(float);
+}
+
+extern "C" int mcnerf_mlp_f32_fwd(const mcnerf_mlp_params* p, const float* x_enc, int ld_enc, const mcnerf_dirs* d,
+                                  int n_rows, const int32_t* n_rows_dev, float* out4, void* workspace, void* stream) {
+  if (int e = check_params(p)) return e;
+  MC_ARG(x_enc && d && d->dirs && out4 && workspace && n_rows >= 0 && ld_enc >= p->in_ch);
+  MC_ARG(((uintptr_t)out4 & 15) == 0);
+  if (n_rows == 0) return 0;
+  Workspace w = carve(p, n_rows, workspace);
+  Plan pl{(cudaStream_t)stream, n_rows, n_rows_dev};
+  const int W = p->width, C = p->in_ch;
+  for (int i = 0; i < p->depth; ++i) {
+    if (i == 0) {
+      pl.fwd(x_enc, ld_enc, C, p->W[0], C, W, p->b[0], w.h[0], W, F_RELU);
+    } else if (p->skip_mask >> i & 1u) {
+      pl.fwd(x_enc, ld_enc, C, p->W[i], C + W, W, nullptr, w.h[i], W, 0);
+      pl.fwd(w.h[i - 1], W, W, p->W[i] + C, C + W, W, p->b[i], w.h[i], W, F_ACCUM | F_RELU);
+    } else {
+      pl.fwd(w.h[i - 1], W, W, p->W[i], W, W, p->b[i], w.h[i], W, F_RELU);
+    }
+  }
+  const float* h = w.h[p->depth - 1];
+  pl.fwd(h, W, W, p->W_sigma0, W, W, p->b_sigma0, w.s0, W, F_RELU);
+  pl.fwd(w.s0, W, W, p->W_sigma2, W, 1, p->b_sigma2, w.sig, 1, 0);
+  pl.fwd(h, W, W, p->W_sh0, W, W, p->b_sh0, w.c0, W, F_RELU);
+  pl.fwd(w.c0, W, W, p->W_sh2, W, 27, p->b_sh2, w.sh, LD_SH, 0);
+  if (pl.err) return pl.err;
+  head_fwd_k<<<cdiv(n_rows, 256), 256, 0, pl.st>>>(w.sig, w.sh, LD_SH, *d, n_rows, n_rows_dev, (float4*)out4);
+  MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcnerf_mlp_f32_bwd(const mcnerf_mlp_params* p, const float* x_enc, int ld_enc, const mcnerf_dirs* d,
+                                  int n_rows, const int32_t* n_rows_dev, const float* g_out4, void* workspace,
+                                  const mcnerf_mlp_grads* g, float* g_x_enc, float* g_dirs, void* stream) {
+  if (int e = check_params(p)) return e;
+  MC_ARG(x_enc && d && d->dirs && g_out4 && workspace && g && n_rows >= 0 && ld_enc >= p->in_ch);
+  if (n_rows == 0) return 0;
+  Workspace w = carve(p, n_rows, workspace);
+  Plan pl{(cudaStream_t)stream, n_rows, n_rows_dev};
+  const int W = p->width, C = p->in_ch, D = p->depth;
+  // the forward pass left out4 unknown to us: recompute the head output from sig/sh for the sigmoid derivative
+  // by re-running head_fwd into bufA's first 4 columns' worth of space (n_rows*4 floats <= n_rows*W).
+  MC_ARG(W >= 4);
+  head_fwd_k<<<cdiv(n_rows, 256), 256, 0, pl.st>>>(w.sig, w.sh, LD_SH, *d, n_rows, n_rows_dev, (float4*)w.bufA);
+  MC_LAUNCHED();
+  head_bwd_k<<<cdiv(n_rows, 256), 256, 0, pl.st>>>((const float4*)w.bufA, w.sh, LD_SH, *d, n_rows, n_rows_dev,
+                                                    (const float4*)g_out4, w.g_sig, w.g_sh, g_dirs);
+  MC_LAUNCHED();
+  const float* h = w.h[D - 1];
+  // sigma branch
+  pl.wgrad(w.g_sig, 1, 1, w.s0, W, W, g->W_sigma2, W);
+  pl.bgrad(w.g_sig, 1, 1, g->b_sigma2);
+  pl.dgrad(w.g_sig, 1, 1, p->W_sigma2, W, W, w.bufA, W, w.s0, W, 0);            // d_s0 (masked by s0 > 0)
+  pl.wgrad(w.bufA, W, W, h, W, W, g->W_sigma0, W);
+  pl.bgrad(w.bufA, W, W, g->b_sigma0);
+  pl.dgrad(w.bufA, W, W, p->W_sigma0, W, W, w.bufB, W, nullptr, 0, 0);          // d_h (partial, unmasked)
+  // colour branch
+  pl.wgrad(w.g_sh, LD_SH, 27, w.c0, W, W, g->W_sh2, W);
+  pl.bgrad(w.g_sh, LD_SH, 27, g->b_sh2);
+  pl.dgrad(w.g_sh, LD_SH, 27, p->W_sh2, W, W, w.bufA, W, w.c0, W, 0);           // d_c0
+  pl.wgrad(w.bufA, W, W, h, W, W, g->W_sh0, W);
+  pl.bgrad(w.bufA, W, W, g->b_sh0);
+  pl.dgrad(w.bufA, W, W, p->W_sh0, W, W, w.bufB, W, h, W, F_ACCUM);             // d_h total, masked by h > 0
+  float* cur = w.bufB;
+  float* nxt = w.bufA;
+  bool gx_written = false;
+  for (int i = D - 1; i >= 0; --i) {
+    pl.bgrad(cur, W, W, g->b[i]);
+    if (i == 0) {
+      pl.wgrad(cur, W, W, x_enc, ld_enc, C, g->W[0], C);
+      if (g_x_enc) pl.dgrad(cur, W, W, p->W[0], C, C, g_x_enc, ld_enc, nullptr, 0, gx_written ? F_ACCUM : 0);
+    } else if (p->skip_mask >> i & 1u) {
+      pl.wgrad(cur, W, W, x_enc, ld_enc, C, g->W[i], C + W);
+      pl.wgrad(cur, W, W, w.h[i - 1], W, W, g->W[i] + C, C + W);
+      if (g_x_enc) {
+        pl.dgrad(cur, W, W, p->W[i], C + W, C, g_x_enc, ld_enc, nullptr, 0, gx_written ? F_ACCUM : 0);
+        gx_written = true;
+      }
+      pl.dgrad(cur, W, W, p->W[i] + C, C + W, W, nxt, W, w.h[i - 1], W, 0);
+    } else {
+      pl.wgrad(cur, W, W, w.h[i - 1], W, W, g->W[i], W);
+      pl.dgrad(cur, W, W, p->W[i], W, W, nxt, W, w.h[i - 1], W, 0);
+    }
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  return pl.err;
+}
+
+extern "C" int mcnerf_eval_sh_fwd(const float* sh, const float* dirs, int n, float* out, void* stream) {
+  MC_ARG(sh && dirs && out && n >= 0);
+  if (n == 0) return 0;
+  eval_sh_fwd_k<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(sh, dirs, n, out);
+  MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcnerf_eval_sh_bwd(const float* sh, const float* dirs, const float* g_out, int n, float* g_sh,
+                                  float* g_dirs, void* stream) {
+  MC_ARG(sh && dirs && g_out && g_sh && g_dirs && n >= 0);
+  if (n == 0) return 0;
+  eval_sh_bwd_k<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(sh, dirs, g_out, n, g_sh, g_dirs);
+  MC_LAUNCHED();
+  return 0;
+}

@@ -1,0 +1,355 @@
+"""PyTorch-facing wrappers over the C ABI: thin functions that pass raw device pointers + the current
+stream to libmcnerf.so, and torch.autograd.Functions at the granularity of the reference's modules.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all arithmetic of the hot path
+happens in the CUDA library.  Nothing in this file computes on the CPU or falls back to torch ops.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import CompositeCfg, Dirs, MlpGrads, MlpParams, Sampling, lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=torch.float32):
+    """device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.McnerfError("libmcnerf kernels need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.McnerfError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.McnerfError("expected a contiguous tensor")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _c(t):
+    return t.contiguous() if t is not None else None
+
+
+def _f32(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def make_sampling(near, far, S, n_freqs, band_w=None):
+    s = Sampling()
+    s.near_, s.far_, s.S, s.n_freqs = float(near), float(far), int(S), int(n_freqs)
+    for k in range(_lib.MAX_FREQS):
+        s.band_w[k] = float(band_w[k]) if (band_w is not None and k < n_freqs) else 1.0
+    return s
+
+
+def make_composite_cfg(near, far, S, white_back):
+    c = CompositeCfg()
+    c.near_, c.far_, c.S, c.white_back = float(near), float(far), int(S), int(bool(white_back))
+    return c
+
+
+def barf_band_weights(step_r, barf_start, barf_end, n_freqs):
+    """Host-side evaluation of the 10 BARF window weights (ref: model/net_block.py:26-29).
+    Returned as Python floats computed in fp32 the way torch does it."""
+    alpha = (step_r - barf_start) / (barf_end - barf_start) * n_freqs
+    k = torch.arange(n_freqs, dtype=torch.float32)
+    w = (1 - (alpha - k).clamp_(min=0, max=1).mul_(torch.pi).cos_()) / 2
+    return [float(x) for x in w]
+
+# --------------------------------------------------------------------------- camera
+
+
+class IntrinsicsFn(torch.autograd.Function):
+    """(w_fx, w_fy, w_ux, w_uy) -> K [n,3,3], Kinv [n,3,3].  ref: model/mc_nerf.py:171-186, 204-210."""
+
+    @staticmethod
+    def forward(ctx, w_fx, w_fy, w_ux, w_uy, img_h, img_w):
+        ws = [_f32(w) for w in (w_fx, w_fy, w_ux, w_uy)]
+        n = ws[0].shape[0]
+        K = torch.empty(n, 3, 3, device=ws[0].device)
+        Kinv = torch.empty_like(K)
+        lib().call("mcnerf_intrinsics_fwd", *[_p(w) for w in ws], n, img_h, img_w, _p(K), _p(Kinv), _stream())
+        ctx.save_for_backward(*ws)
+        ctx.hw = (img_h, img_w)
+        return K, Kinv
+
+    @staticmethod
+    def backward(ctx, gK, gKinv):
+        ws = ctx.saved_tensors
+        n = ws[0].shape[0]
+        gs = [torch.empty_like(ws[0]) for _ in range(4)]
+        gK = _f32(gK) if gK is not None else None
+        gKinv = _f32(gKinv) if gKinv is not None else None
+        lib().call("mcnerf_intrinsics_bwd", *[_p(w) for w in ws], n, ctx.hw[0], ctx.hw[1], _p(gK), _p(gKinv),
+                   *[_p(g) for g in gs], _stream())
+        return gs[0], gs[1], gs[2], gs[3], None, None
+
+
+class SE3Fn(torch.autograd.Function):
+    """se(3) twist [n,6] -> world->camera [n,3,4].  ref: model/mc_nerf.py:269-316."""
+
+    @staticmethod
+    def forward(ctx, wu):
+        wu = _f32(wu)
+        shape = wu.shape[:-1]
+        flat = wu.reshape(-1, 6)
+        Rt = torch.empty(flat.shape[0], 3, 4, device=wu.device)
+        lib().call("mcnerf_se3_fwd", _p(flat), flat.shape[0], _p(Rt), _stream())
+        ctx.save_for_backward(flat)
+        ctx.shape = shape
+        return Rt.reshape(*shape, 3, 4)
+
+    @staticmethod
+    def backward(ctx, gRt):
+        (flat,) = ctx.saved_tensors
+        g = torch.empty_like(flat)
+        lib().call("mcnerf_se3_bwd", _p(flat), _p(_f32(gRt).reshape(-1, 3, 4)), flat.shape[0], _p(g), _stream())
+        return g.reshape(*ctx.shape, 6)
+
+
+class RaygenFn(torch.autograd.Function):
+    """(Kinv [n,3,3], Rt [n,3,4], cam, pix) -> rays_o, rays_d [B,3].  ref: model/mc_nerf.py:124-145, 327-345.
+    `cam` is an int or an int32 tensor [B]; `pix` is None (whole image, row-major) or an int32 tensor [B]."""
+
+    @staticmethod
+    def forward(ctx, Kinv, Rt, cam, pix, n_rays, img_w):
+        Kinv, Rt = _f32(Kinv), _f32(Rt)
+        cam_t = cam if torch.is_tensor(cam) else None
+        cam_c = 0 if cam_t is not None else int(cam)
+        ro = torch.empty(n_rays, 3, device=Kinv.device)
+        rd = torch.empty_like(ro)
+        lib().call("mcnerf_raygen_fwd", _p(Kinv), _p(Rt), _p(cam_t, torch.int32), cam_c, _p(pix, torch.int32),
+                   n_rays, img_w, _p(ro), _p(rd), _stream())
+        ctx.save_for_backward(Kinv, Rt, cam_t, pix)
+        ctx.meta = (cam_c, n_rays, img_w)
+        return ro, rd
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        Kinv, Rt, cam_t, pix = ctx.saved_tensors
+        cam_c, n_rays, img_w = ctx.meta
+        gK = torch.zeros_like(Kinv)
+        gRt = torch.zeros_like(Rt)
+        g_o = _f32(g_o) if g_o is not None else torch.zeros(n_rays, 3, device=Kinv.device)
+        g_d = _f32(g_d) if g_d is not None else torch.zeros(n_rays, 3, device=Kinv.device)
+        lib().call("mcnerf_raygen_bwd", _p(Kinv), _p(Rt), _p(cam_t, torch.int32), cam_c, _p(pix, torch.int32),
+                   n_rays, img_w, _p(g_o), _p(g_d), _p(gK), _p(gRt), _stream())
+        return gK, gRt, None, None, None, None
+
+# --------------------------------------------------------------------------- encoding
+
+
+class EncodePointsFn(torch.autograd.Function):
+    """SinCosEmbedding.forward on explicit points.  ref: model/net_block.py:20-35."""
+
+    @staticmethod
+    def forward(ctx, x, n_freqs, band_w):
+        x = _f32(x)
+        n = x.shape[0]
+        enc = torch.empty(n, 3 + 6 * n_freqs, device=x.device)
+        bw = (ctypes.c_float * n_freqs)(*band_w) if band_w is not None else None
+        lib().call("mcnerf_encode_points_fwd", _p(x), n, n_freqs, ctypes.cast(bw, ctypes.c_void_p) if bw else None,
+                   _p(enc), enc.shape[1], _stream())
+        ctx.save_for_backward(x)
+        ctx.meta = (n_freqs, band_w)
+        return enc
+
+    @staticmethod
+    def backward(ctx, g_enc):
+        (x,) = ctx.saved_tensors
+        n_freqs, band_w = ctx.meta
+        g_enc = _f32(g_enc)
+        gx = torch.empty_like(x)
+        bw = (ctypes.c_float * n_freqs)(*band_w) if band_w is not None else None
+        lib().call("mcnerf_encode_points_bwd", _p(x), x.shape[0], n_freqs,
+                   ctypes.cast(bw, ctypes.c_void_p) if bw else None, _p(g_enc), g_enc.shape[1], _p(gx), _stream())
+        return gx, None, None
+
+# --------------------------------------------------------------------------- MLP
+
+TRUNK = "xyz_encoding_{}.0.{}"
+HEAD_KEYS = [("W_sigma0", "sigma.0.weight"), ("b_sigma0", "sigma.0.bias"), ("W_sigma2", "sigma.2.weight"),
+             ("b_sigma2", "sigma.2.bias"), ("W_sh0", "sh.0.weight"), ("b_sh0", "sh.0.bias"),
+             ("W_sh2", "sh.2.weight"), ("b_sh2", "sh.2.bias")]
+
+
+def param_names(depth):
+    """state_dict key order of CorseFine_NeRF (ref: model/net_block.py:51-65)."""
+    names = []
+    for i in range(depth):
+        names += [TRUNK.format(i + 1, "weight"), TRUNK.format(i + 1, "bias")]
+    return names + [k for _, k in HEAD_KEYS]
+
+
+def fill_mlp_struct(struct, tensors, depth):
+    """tensors: dict name -> contiguous fp32 CUDA tensor."""
+    for i in range(depth):
+        struct.W[i] = tensors[TRUNK.format(i + 1, "weight")].data_ptr()
+        struct.b[i] = tensors[TRUNK.format(i + 1, "bias")].data_ptr()
+    for field, key in HEAD_KEYS:
+        setattr(struct, field, tensors[key].data_ptr())
+    return struct
+
+
+def make_mlp_params(tensors, depth, width, skips, in_ch=63, sh_dim=27):
+    p = MlpParams()
+    p.depth, p.width, p.in_ch, p.sh_dim = depth, width, in_ch, sh_dim
+    p.skip_mask = sum(1 << int(s) for s in skips if 0 < int(s) < depth)
+    return fill_mlp_struct(p, tensors, depth)
+
+
+def make_dirs(dirs, dir_idx=None, dir_S=0):
+    d = Dirs()
+    d.dirs = dirs.data_ptr()
+    d.dir_idx = dir_idx.data_ptr() if dir_idx is not None else None
+    d.dir_S = int(dir_S)
+    return d
+
+
+def mlp_f32_workspace(params_struct, n_rows, device):
+    nbytes = lib().cdll.mcnerf_mlp_f32_workspace(ctypes.byref(params_struct), int(n_rows))
+    return torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+
+
+class MLPFn(torch.autograd.Function):
+    """CorseFine_NeRF.forward(x_enc [M,63], dirs [M,3]) -> [M,4].  ref: model/net_block.py:67-78.
+    Differentiable in x_enc, dirs and every parameter (passed flat in param_names(depth) order)."""
+
+    @staticmethod
+    def forward(ctx, x_enc, dirs, depth, width, skips, *params):
+        x_enc, dirs = _f32(x_enc), _f32(dirs)
+        names = param_names(depth)
+        tensors = {k: _f32(v) for k, v in zip(names, params)}
+        M = x_enc.shape[0]
+        ps = make_mlp_params(tensors, depth, width, skips, in_ch=x_enc.shape[1])
+        out4 = torch.empty(M, 4, device=x_enc.device)
+        ws = mlp_f32_workspace(ps, max(M, 1), x_enc.device)
+        d = make_dirs(dirs)
+        lib().call("mcnerf_mlp_f32_fwd", ctypes.byref(ps), _p(x_enc), x_enc.shape[1], ctypes.byref(d), M, None,
+                   _p(out4), _p(ws), _stream())
+        ctx.save_for_backward(x_enc, dirs, ws, *[tensors[k] for k in names])
+        ctx.meta = (depth, width, tuple(skips))
+        return out4
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x_enc, dirs, ws, *plist = ctx.saved_tensors
+        depth, width, skips = ctx.meta
+        names = param_names(depth)
+        tensors = dict(zip(names, plist))
+        ps = make_mlp_params(tensors, depth, width, skips, in_ch=x_enc.shape[1])
+        grads = {k: torch.zeros_like(v) for k, v in tensors.items()}
+        gs = fill_mlp_struct(MlpGrads(), grads, depth)
+        M = x_enc.shape[0]
+        g_x = torch.empty_like(x_enc)
+        g_d = torch.zeros_like(dirs)
+        d = make_dirs(dirs)
+        lib().call("mcnerf_mlp_f32_bwd", ctypes.byref(ps), _p(x_enc), x_enc.shape[1], ctypes.byref(d), M, None,
+                   _p(_f32(g_out)), _p(ws), ctypes.byref(gs), _p(g_x), _p(g_d), _stream())
+        return (g_x, g_d, None, None, None) + tuple(grads[k] for k in names)
+
+
+class EvalSHFn(torch.autograd.Function):
+    """eval_sh(deg=2): sh [n,3,9], dirs [n,3] -> [n,3].  ref: model/net_utils.py:103-191."""
+
+    @staticmethod
+    def forward(ctx, sh, dirs):
+        sh, dirs = _f32(sh), _f32(dirs)
+        n = dirs.shape[0]
+        out = torch.empty(n, 3, device=sh.device)
+        lib().call("mcnerf_eval_sh_fwd", _p(sh), _p(dirs), n, _p(out), _stream())
+        ctx.save_for_backward(sh, dirs)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        sh, dirs = ctx.saved_tensors
+        g_sh, g_d = torch.empty_like(sh), torch.empty_like(dirs)
+        lib().call("mcnerf_eval_sh_bwd", _p(sh), _p(dirs), _p(_f32(g)), dirs.shape[0], _p(g_sh), _p(g_d), _stream())
+        return g_sh, g_d
+
+# --------------------------------------------------------------------------- compositing / selection
+
+
+class CompositeFn(torch.autograd.Function):
+    """Tail of NeRF_Model.inference: out4 [B,S,4] -> rgb [B,3], depth [B,1], opacity [B,1].
+    ref: model/mc_nerf.py:705-727.  Gradient flows from rgb into out4 only (the reference discards
+    depth/opacity in training, model/mc_nerf.py:590-591)."""
+
+    @staticmethod
+    def forward(ctx, out4, noise, rays_d, z_vals, jitter, near, far, white_back):
+        out4 = _f32(out4)
+        B, S = out4.shape[0], out4.shape[1]
+        cfg = make_composite_cfg(near, far, S, white_back)
+        noise = _f32(noise) if noise is not None else None
+        z_vals = _f32(z_vals) if z_vals is not None else None
+        jitter = _f32(jitter).reshape(-1) if jitter is not None else None
+        rgb = torch.empty(B, 3, device=out4.device)
+        depth = torch.empty(B, 1, device=out4.device)
+        opacity = torch.empty(B, 1, device=out4.device)
+        lib().call("mcnerf_composite_fwd", _p(out4), _p(noise), _p(_f32(rays_d)), _p(jitter), _p(z_vals), B,
+                   ctypes.byref(cfg), _p(rgb), _p(depth), _p(opacity), None, _stream())
+        ctx.save_for_backward(out4, noise, z_vals, jitter)
+        ctx.cfg = (near, far, S, white_back)
+        ctx.mark_non_differentiable(depth, opacity)
+        return rgb, depth, opacity
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_opacity):
+        out4, noise, z_vals, jitter = ctx.saved_tensors
+        near, far, S, white_back = ctx.cfg
+        cfg = make_composite_cfg(near, far, S, white_back)
+        g_out4 = torch.empty_like(out4)
+        lib().call("mcnerf_composite_bwd", _p(out4), _p(noise), _p(jitter), _p(z_vals), out4.shape[0],
+                   ctypes.byref(cfg), _p(_f32(g_rgb)), _p(g_out4), _stream())
+        return g_out4, None, None, None, None, None, None, None
+
+
+def sigma2weights(sigmas, noise, deltas=None, jitter=None, near=0.0, far=1.0, sigma_stride=1, n_rays=None, S=None,
+                  w_max=None):
+    """ref: model/mc_nerf.py:729-736.  Forward only (the reference uses its gradient only through the
+    compositing above, which CompositeFn covers)."""
+    if n_rays is None:
+        n_rays, S = sigmas.shape[0], sigmas.shape[1]
+    cfg = make_composite_cfg(near, far, S, True)
+    w = torch.empty(n_rays, S, device=sigmas.device)
+    lib().call("mcnerf_sigma2weights", _p(sigmas), sigma_stride, _p(noise), _p(jitter), None, _p(deltas), n_rays,
+               ctypes.byref(cfg), _p(w), _p(w_max), _stream())
+    return w
+
+
+def select_fine(weights, w_max, scale, thresh):
+    """-> (sel_idx int32 [B*Sc*scale] capacity, sel_offsets int32 [B+1], n_sel int32 [1]); no host sync."""
+    B, Sc = weights.shape
+    dev = weights.device
+    sel_idx = torch.empty(B * Sc * scale, dtype=torch.int32, device=dev)
+    offs = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    n_sel = torch.empty(1, dtype=torch.int32, device=dev)
+    lib().call("mcnerf_select_fine", _p(weights), _p(w_max), B, Sc, scale, float(thresh), _p(sel_idx, torch.int32),
+               _p(offs, torch.int32), _p(n_sel, torch.int32), _stream())
+    return sel_idx, offs, n_sel
+
+
+class ScatterFineFn(torch.autograd.Function):
+    """out_dense[B*Sf,4] = defaults; out_dense[idx] = out_sel.  ref: model/mc_nerf.py:692-694, 700-701."""
+
+    @staticmethod
+    def forward(ctx, out_sel, idx, n_dense, sigma_default):
+        out_sel = _f32(out_sel)
+        dense = torch.empty(n_dense, 4, device=idx.device)
+        n = out_sel.shape[0]
+        lib().call("mcnerf_scatter_fine", _p(out_sel) if n else None, _p(idx, torch.int32) if n else None, n, None,
+                   n_dense, float(sigma_default), _p(dense), _stream())
+        ctx.save_for_backward(idx)
+        ctx.n = n
+        return dense
+
+    @staticmethod
+    def backward(ctx, g_dense):
+        (idx,) = ctx.saved_tensors
+        g_sel = torch.empty(ctx.n, 4, device=g_dense.device)
+        lib().call("mcnerf_gather_fine", _p(_f32(g_dense)), _p(idx, torch.int32), ctx.n, None, _p(g_sel), _stream())
+        return g_sel, None, None, None

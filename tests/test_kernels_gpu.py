@@ -1,0 +1,257 @@
+"""GPU parity tests: every C-ABI kernel against the CPU oracle (and the reference's golden vectors)
+on identical inputs.  Tolerances are fp32 (the fp32 path only differs from the CPU by summation order
+and libm ulps); the bf16 tensor-core path has its own file.  Run with `-m gpu` on a B200."""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import mcnerf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def ops():
+    from mc_nerf_b200 import ops as _ops
+    return _ops
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    torch.testing.assert_close(a.cpu(), b.cpu(), rtol=rtol, atol=atol)
+
+
+@pytest.fixture(scope="module")
+def mods():
+    return load_golden("modules.pt")
+
+
+def test_library_loads_and_counts_launches():
+    from mc_nerf_b200._lib import lib
+    n0 = lib().launch_count()
+    ops().SE3Fn.apply(torch.ones(3, 6, device=DEV))
+    torch.cuda.synchronize()
+    assert lib().launch_count() == n0 + 1
+
+
+def test_camera_model_golden(mods):
+    c = mods["cam"]
+    w = {k: v.to(DEV).requires_grad_(True) for k, v in c["w"].items()}
+    K, Kinv = ops().IntrinsicsFn.apply(w["weights_fx"], w["weights_fy"], w["weights_ux"], w["weights_uy"], c["H"], c["W"])
+    close(K, c["K"])
+    close(Kinv, c["Kinv"], rtol=1e-5, atol=1e-6)
+    close(ops().SE3Fn.apply(w["weights_pose"]), c["pose"])
+    close(ops().SE3Fn.apply(w["weights_pose_intr"]), c["calib"])
+    b = mods["se3_big"]
+    close(ops().SE3Fn.apply(b["wu"].to(DEV)), b["Rt"], rtol=1e-5, atol=2e-5)
+
+
+def test_camera_model_backward():
+    g = torch.Generator().manual_seed(1)
+    n = 7
+    wu = (torch.randn(n, 6, generator=g) * 1.2)
+    fx, fy = torch.rand(n, generator=g) + 0.5, -(torch.rand(n, generator=g) + 0.5)
+    ux, uy = torch.rand(n, generator=g) + 0.5, torch.rand(n, generator=g) + 0.5
+    gRt, gK, gKi = torch.randn(n, 3, 4, generator=g), torch.randn(n, 3, 3, generator=g), torch.randn(n, 3, 3, generator=g)
+    # oracle
+    lw = [t.clone().requires_grad_(True) for t in (wu, fx, fy, ux, uy)]
+    Rt = orc.se3_to_SE3(lw[0])
+    K = orc.intrinsics_from_weights(lw[1], lw[2], lw[3], lw[4], 12, 16)
+    Ki = orc.inverse_intrinsics(K)
+    ((Rt * gRt).sum() + (K * gK).sum() + (Ki * gKi).sum()).backward()
+    # kernels
+    dw = [t.to(DEV).requires_grad_(True) for t in (wu, fx, fy, ux, uy)]
+    Rt2 = ops().SE3Fn.apply(dw[0])
+    K2, Ki2 = ops().IntrinsicsFn.apply(dw[1], dw[2], dw[3], dw[4], 12, 16)
+    ((Rt2 * gRt.to(DEV)).sum() + (K2 * gK.to(DEV)).sum() + (Ki2 * gKi.to(DEV)).sum()).backward()
+    for a, b in zip(dw, lw):
+        close(a.grad, b.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_raygen_golden_and_backward(mods):
+    c, r = mods["cam"], mods["rays"]
+    H, W = c["H"], c["W"]
+    Kinv = c["Kinv"].to(DEV).requires_grad_(True)
+    pose = c["pose"].to(DEV).requires_grad_(True)
+    ro, rd = ops().RaygenFn.apply(Kinv, pose, r["img_id"], None, H * W, W)
+    close(rd, r["rays_d"], rtol=1e-5, atol=1e-6)
+    close(ro, r["rays_o"], rtol=1e-5, atol=1e-6)
+    # backward vs oracle autograd, random pixel subset and mixed cameras
+    g = torch.Generator().manual_seed(2)
+    B = 200
+    cam = torch.randint(0, 6, (B,), generator=g, dtype=torch.int32)
+    pix = torch.randint(0, H * W, (B,), generator=g, dtype=torch.int32)
+    go, gd = torch.randn(B, 3, generator=g), torch.randn(B, 3, generator=g)
+    Ki_c, P_c = c["Kinv"].clone().requires_grad_(True), c["pose"].clone().requires_grad_(True)
+    ros, rds = [], []
+    for cam_i in range(6):
+        d_all, o_all = orc.get_rays(P_c[cam_i], Ki_c[cam_i], H, W)
+        ros.append(o_all)
+        rds.append(d_all)
+    ro_ref = torch.stack(ros)[cam.long(), pix.long()]
+    rd_ref = torch.stack(rds)[cam.long(), pix.long()]
+    ((ro_ref * go).sum() + (rd_ref * gd).sum()).backward()
+    ro2, rd2 = ops().RaygenFn.apply(Kinv, pose, cam.to(DEV), pix.to(DEV), B, W)
+    close(ro2, ro_ref.detach())
+    close(rd2, rd_ref.detach())
+    ((ro2 * go.to(DEV)).sum() + (rd2 * gd.to(DEV)).sum()).backward()
+    close(Kinv.grad, Ki_c.grad, rtol=1e-4, atol=1e-4)
+    close(pose.grad, P_c.grad, rtol=1e-4, atol=1e-4)
+    # uniform-camera warp-reduced path
+    Kinv.grad = None
+    pose.grad = None
+    ro3, rd3 = ops().RaygenFn.apply(Kinv, pose, 4, pix.to(DEV), B, W)
+    ((ro3 * go.to(DEV)).sum() + (rd3 * gd.to(DEV)).sum()).backward()
+    Ki_c.grad = None
+    P_c.grad = None
+    d_all, o_all = orc.get_rays(P_c[4], Ki_c[4], H, W)
+    ((o_all[pix.long()] * go).sum() + (d_all[pix.long()] * gd).sum()).backward()
+    close(Kinv.grad, Ki_c.grad, rtol=1e-4, atol=1e-4)
+    close(pose.grad, P_c.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_encoding_golden_and_backward(mods):
+    e = mods["enc"]
+    x = e["x"].to(DEV).requires_grad_(True)
+    enc = ops().EncodePointsFn.apply(x, e["L"], None)
+    # arguments reach ~7*512 rad: sin/cos of a float32 argument, 2 ulp libm differences -> 1e-6 absolute
+    close(enc, e["plain"], rtol=1e-5, atol=2e-6)
+    for r, ref in e["barf"].items():
+        bw = ops().barf_band_weights(r, e["barf_start"], e["barf_end"], e["L"])
+        close(ops().EncodePointsFn.apply(x, e["L"], bw), ref, rtol=1e-5, atol=2e-6)
+    g = torch.randn(enc.shape, generator=torch.Generator().manual_seed(3))
+    bw = ops().barf_band_weights(0.5, e["barf_start"], e["barf_end"], e["L"])
+    ops().EncodePointsFn.apply(x, e["L"], bw).backward(g.to(DEV))
+    xc = e["x"].clone().requires_grad_(True)
+    orc.sincos_encode(xc, e["L"], orc.barf_weights(0.5, e["barf_start"], e["barf_end"], e["L"])).backward(g)
+    close(x.grad, xc.grad, rtol=1e-4, atol=1e-3)   # grads carry a 2^k factor (up to 512 * |g|)
+
+
+def test_eval_sh_golden_and_backward(mods):
+    s = mods["sh"]
+    sh, d = s["sh"].to(DEV).requires_grad_(True), s["dirs"].to(DEV).requires_grad_(True)
+    out = ops().EvalSHFn.apply(sh, d)
+    close(out, s["out"])
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(4))
+    out.backward(g.to(DEV))
+    shc, dc = s["sh"].clone().requires_grad_(True), s["dirs"].clone().requires_grad_(True)
+    orc.eval_sh_deg2(shc, dc).backward(g)
+    close(sh.grad, shc.grad)
+    close(d.grad, dc.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["small", "big"])
+def test_mlp_f32_golden(mods, name):
+    f = mods[f"mlp_{name}"]
+    dep, wid, skips = f["cfg"]
+    p = orc.init_mlp_params(dep, wid, skips, seed=f["seed"])
+    names = ops().param_names(dep)
+    plist = [p[k].to(DEV).requires_grad_(True) for k in names]
+    x = f["x_enc"].to(DEV).requires_grad_(True)
+    d = f["dirs"].to(DEV).requires_grad_(True)
+    out = ops().MLPFn.apply(x, d, dep, wid, skips, *plist)
+    close(out, f["out"], rtol=1e-4, atol=2e-5)
+    out.backward(f["gout"].to(DEV))
+    close(x.grad, f["g_x"], rtol=1e-3, atol=2e-5)
+    close(d.grad, f["g_dirs"], rtol=1e-3, atol=2e-5)
+    for k, t in zip(names, plist):
+        n = f["g_params_norm"][k]
+        assert abs(float(t.grad.norm()) - n) <= 1e-3 * max(1.0, n), k
+        close(t.grad.reshape(-1)[:256], f["g_params_slice"][k], rtol=1e-3, atol=2e-5)
+        if f["g_params"] is not None:
+            close(t.grad, f["g_params"][k], rtol=1e-3, atol=2e-5)
+
+
+def test_mlp_f32_ragged_rows():
+    """row counts that are not tile multiples, a single row, and zero rows."""
+    dep, wid, skips = 3, 32, (1,)
+    p = orc.init_mlp_params(dep, wid, skips, seed=9)
+    names = ops().param_names(dep)
+    plist = [p[k].to(DEV) for k in names]
+    g = torch.Generator().manual_seed(5)
+    for M in (1, 129, 300):
+        x = torch.randn(M, 63, generator=g)
+        d = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+        out = ops().MLPFn.apply(x.to(DEV), d.to(DEV), dep, wid, skips, *plist)
+        close(out, orc.mlp_forward(p, x, d, dep, skips), rtol=1e-4, atol=1e-5)
+    out = ops().MLPFn.apply(torch.zeros(0, 63, device=DEV), torch.zeros(0, 3, device=DEV), dep, wid, skips, *plist)
+    assert out.shape == (0, 4)
+
+
+def test_compositing_golden(mods):
+    c = mods["composite"]
+    out4 = c["out4"].to(DEV).requires_grad_(True)
+    rgb, dep, opa = ops().CompositeFn.apply(out4, c["noise"].to(DEV), c["rays_d"].to(DEV), c["z"].to(DEV), None,
+                                            1.0, 8.0, True)
+    close(rgb, c["rgb"])
+    close(dep, c["depth"], rtol=1e-5, atol=1e-5)
+    close(opa, c["opacity"])
+    rgb.backward(c["g_rgb"].to(DEV))
+    close(out4.grad, c["g_out4"], rtol=1e-4, atol=1e-6)
+    s = mods["s2w"]
+    w = ops().sigma2weights(s["sigmas"].to(DEV).contiguous(), s["noise"].to(DEV), deltas=orc.z_deltas(s["z"]).to(DEV).contiguous())
+    close(w, s["w"])
+
+
+@pytest.mark.parametrize("S,B", [(8, 5), (64, 33), (128, 17), (640, 3)])
+def test_compositing_sizes(S, B):
+    """one chunk, two lanes/ray, four lanes/ray and the reference default of 640 fine samples;
+    z from (near, far, jitter) instead of an explicit tensor."""
+    g = torch.Generator().manual_seed(S)
+    out4 = torch.cat([torch.randn(B, S, 1, generator=g) * 3 - 1, torch.rand(B, S, 3, generator=g)], -1)
+    rays_d = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1)
+    jit = torch.rand(B, 1, generator=g) * (7.0 / S)
+    noise = torch.randn(B, S, generator=g)
+    z = torch.linspace(1.0, 8.0, S).expand(B, -1) + jit
+    o_c = out4.clone().requires_grad_(True)
+    rgb_r, dep_r, opa_r, w_r = orc.composite(o_c, rays_d, z, noise, True)
+    grgb = torch.randn(B, 3, generator=g)
+    rgb_r.backward(grgb)
+    o_d = out4.to(DEV).requires_grad_(True)
+    rgb, dep, opa = ops().CompositeFn.apply(o_d, noise.to(DEV), rays_d.to(DEV), None, jit.to(DEV), 1.0, 8.0, True)
+    close(rgb, rgb_r.detach(), rtol=1e-4, atol=2e-6)
+    close(dep, dep_r.detach(), rtol=1e-4, atol=1e-5)
+    close(opa, opa_r.detach(), rtol=1e-4, atol=2e-6)
+    rgb.backward(grgb.to(DEV))
+    close(o_d.grad, o_c.grad, rtol=1e-3, atol=2e-6)
+
+
+def test_selection_matches_nonzero():
+    g = torch.Generator().manual_seed(6)
+    for B, Sc, scale, thresh in ((37, 64, 2, 1e-3), (5, 8, 2, 1e-3), (9, 128, 5, 1e-3), (4, 16, 3, 10.0)):
+        w = torch.rand(B, Sc, generator=g) * (torch.rand(B, Sc, generator=g) < 0.3)
+        if thresh > 1:
+            w = w * 0 + torch.rand(B, Sc, generator=g) * 1e-6       # max(w) < thresh: threshold becomes the max
+        ref = orc.select_fine(w, thresh, scale)
+        wd = w.to(DEV)
+        wmax = wd.max().reshape(1).clone()
+        idx, offs, n = ops().select_fine(wd, wmax, scale, thresh)
+        n = int(n.item())
+        assert n == ref.shape[0]
+        flat_ref = (ref[:, 0] * (Sc * scale) + ref[:, 1]).int()
+        assert torch.equal(idx[:n].cpu(), flat_ref)
+        cnt = torch.bincount(ref[:, 0], minlength=B)
+        assert torch.equal(offs.cpu()[1:] - offs.cpu()[:-1], cnt.int())
+    # nothing selected is impossible (max always passes); everything selected:
+    w = torch.ones(3, 8)
+    idx, offs, n = ops().select_fine(w.to(DEV), torch.ones(1, device=DEV), 2, 1e-3)
+    assert int(n.item()) == 48 and torch.equal(idx.cpu(), torch.arange(48, dtype=torch.int32))
+
+
+def test_scatter_gather_fine():
+    g = torch.Generator().manual_seed(7)
+    n_dense = 50
+    idx = torch.randperm(n_dense, generator=g)[:20].sort().values.int()
+    src = torch.randn(20, 4, generator=g)
+    s = src.to(DEV).requires_grad_(True)
+    dense = ops().ScatterFineFn.apply(s, idx.to(DEV), n_dense, -20.0)
+    ref = torch.cat([torch.full((n_dense, 1), -20.0), torch.ones(n_dense, 3)], 1)
+    ref[idx.long()] = src
+    assert torch.equal(dense.cpu(), ref)
+    gd = torch.randn(n_dense, 4, generator=g)
+    dense.backward(gd.to(DEV))
+    assert torch.equal(s.grad.cpu(), gd[idx.long()])
+    empty = ops().ScatterFineFn.apply(torch.zeros(0, 4, device=DEV), torch.zeros(0, dtype=torch.int32, device=DEV), 6, -20.0)
+    assert torch.equal(empty.cpu(), ref[:6] * 0 + torch.tensor([-20.0, 1, 1, 1]))
