@@ -73,7 +73,10 @@ composite_fwd_k(const float4* __restrict__ out4, const float* __restrict__ noise
     // (i) noise-free transmittance
     float tau = live ? softplus_f(o.x) * (dl * len) : 0.f;
     float tau_inc = scan_add_incl(tau, lane);
-    float T = expf(-(tau_carry + tau_inc - tau));
+    // exclusive prefix by shifting, NOT tau_inc - tau: the last sample's tau is ~1e10 and would cancel
+    float tau_exc = __shfl_up_sync(0xffffffffu, tau_inc, 1);
+    if (lane == 0) tau_exc = 0.f;
+    float T = expf(-(tau_carry + tau_exc));
     float pa = live ? T * (1.f - expf(-tau)) : 0.f;
     acc_op += pa;
     acc_dp += pa * zk;

@@ -328,9 +328,9 @@ extern "C" size_t mcnerf_mlp_f32_workspace(const mcnerf_mlp_params* p, int n_row
 extern "C" int mcnerf_mlp_f32_fwd(const mcnerf_mlp_params* p, const float* x_enc, int ld_enc, const mcnerf_dirs* d,
                                   int n_rows, const int32_t* n_rows_dev, float* out4, void* workspace, void* stream) {
   if (int e = check_params(p)) return e;
-  MC_ARG(x_enc && d && d->dirs && out4 && workspace && n_rows >= 0 && ld_enc >= p->in_ch);
-  MC_ARG(((uintptr_t)out4 & 15) == 0);
   if (n_rows == 0) return 0;
+  MC_ARG(x_enc && d && d->dirs && out4 && workspace && n_rows > 0 && ld_enc >= p->in_ch);
+  MC_ARG(((uintptr_t)out4 & 15) == 0 && p->width % 4 == 0);
   Workspace w = carve(p, n_rows, workspace);
   Plan pl{(cudaStream_t)stream, n_rows, n_rows_dev};
   const int W = p->width, C = p->in_ch;
@@ -359,8 +359,8 @@ extern "C" int mcnerf_mlp_f32_bwd(const mcnerf_mlp_params* p, const float* x_enc
                                   int n_rows, const int32_t* n_rows_dev, const float* g_out4, void* workspace,
                                   const mcnerf_mlp_grads* g, float* g_x_enc, float* g_dirs, void* stream) {
   if (int e = check_params(p)) return e;
-  MC_ARG(x_enc && d && d->dirs && g_out4 && workspace && g && n_rows >= 0 && ld_enc >= p->in_ch);
   if (n_rows == 0) return 0;
+  MC_ARG(x_enc && d && d->dirs && g_out4 && workspace && g && n_rows > 0 && ld_enc >= p->in_ch);
   Workspace w = carve(p, n_rows, workspace);
   Plan pl{(cudaStream_t)stream, n_rows, n_rows_dev};
   const int W = p->width, C = p->in_ch, D = p->depth;

@@ -293,8 +293,8 @@ extern "C" int mcnerf_encode_points_fwd(const float* x, int n, int n_freqs, cons
                                         int ld_enc, void* stream) {
   mcnerf_sampling s;
   if (int e = points_sampling(n_freqs, band_w_host, &s)) return e;
-  MC_ARG(x && enc && n >= 0 && ld_enc >= 3 + 6 * n_freqs);
   if (n == 0) return 0;
+  MC_ARG(x && enc && n > 0 && ld_enc >= 3 + 6 * n_freqs);
   encode_points_fwd_k<<<cdiv(3 * (int64_t)n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, s, enc, ld_enc);
   MC_LAUNCHED();
   return 0;
@@ -304,8 +304,8 @@ extern "C" int mcnerf_encode_points_bwd(const float* x, int n, int n_freqs, cons
                                         const float* g_enc, int ld_enc, float* g_x, void* stream) {
   mcnerf_sampling s;
   if (int e = points_sampling(n_freqs, band_w_host, &s)) return e;
-  MC_ARG(x && g_enc && g_x && n >= 0 && ld_enc >= 3 + 6 * n_freqs);
   if (n == 0) return 0;
+  MC_ARG(x && g_enc && g_x && n > 0 && ld_enc >= 3 + 6 * n_freqs);
   encode_points_bwd_k<<<cdiv(3 * (int64_t)n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, s, g_enc, ld_enc, g_x);
   MC_LAUNCHED();
   return 0;

@@ -228,8 +228,9 @@ class MLPFn(torch.autograd.Function):
         out4 = torch.empty(M, 4, device=x_enc.device)
         ws = mlp_f32_workspace(ps, max(M, 1), x_enc.device)
         d = make_dirs(dirs)
-        lib().call("mcnerf_mlp_f32_fwd", ctypes.byref(ps), _p(x_enc), x_enc.shape[1], ctypes.byref(d), M, None,
-                   _p(out4), _p(ws), _stream())
+        if M > 0:
+            lib().call("mcnerf_mlp_f32_fwd", ctypes.byref(ps), _p(x_enc), x_enc.shape[1], ctypes.byref(d), M, None,
+                       _p(out4), _p(ws), _stream())
         ctx.save_for_backward(x_enc, dirs, ws, *[tensors[k] for k in names])
         ctx.meta = (depth, width, tuple(skips))
         return out4
@@ -247,8 +248,9 @@ class MLPFn(torch.autograd.Function):
         g_x = torch.empty_like(x_enc)
         g_d = torch.zeros_like(dirs)
         d = make_dirs(dirs)
-        lib().call("mcnerf_mlp_f32_bwd", ctypes.byref(ps), _p(x_enc), x_enc.shape[1], ctypes.byref(d), M, None,
-                   _p(_f32(g_out)), _p(ws), ctypes.byref(gs), _p(g_x), _p(g_d), _stream())
+        if M > 0:
+            lib().call("mcnerf_mlp_f32_bwd", ctypes.byref(ps), _p(x_enc), x_enc.shape[1], ctypes.byref(d), M, None,
+                       _p(_f32(g_out)), _p(ws), ctypes.byref(gs), _p(g_x), _p(g_d), _stream())
         return (g_x, g_d, None, None, None) + tuple(grads[k] for k in names)
 
 

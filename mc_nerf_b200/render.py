@@ -1,0 +1,188 @@
+"""Fused coarse+fine renderer: one autograd node for NeRF_Model.render_rays_train / render_rays_test.
+
+Forward  : sample+encode (coarse grid) -> coarse MLP -> compositing -> selection weights (fresh noise)
+           -> device-side threshold/compaction (no host sync) -> sample+encode (selected fine samples)
+           -> fine MLP -> scatter into defaults -> compositing.
+Backward : compositing bwd -> gather -> MLP bwd (dgrad + wgrad) -> encoding bwd -> per-ray (dL/do, dL/dd),
+           for the fine and then the coarse branch.
+
+ref: model/mc_nerf.py:598-736.  Random draws (jitter, three noise tensors) are explicit arguments so that the
+caller decides where they come from (torch's generator in the reference's draw order, or fixtures in tests).
+"""
+import ctypes
+
+import torch
+
+from . import ops
+from ._lib import MlpGrads, lib
+
+_p, _stream = ops._p, ops._stream
+
+
+class RenderCfg:
+    """Static renderer configuration (the sys_param keys NeRF_Model reads, ref: model/mc_nerf.py:547-571)."""
+
+    def __init__(self, near, far, Sc, scale, n_freqs, white_back, sigma_default, thresh,
+                 coarse, fine, precision="fp32"):
+        self.near, self.far, self.Sc, self.scale = float(near), float(far), int(Sc), int(scale)
+        self.Sf = self.Sc * self.scale
+        self.n_freqs, self.white_back = int(n_freqs), bool(white_back)
+        self.sigma_default, self.thresh = float(sigma_default), float(thresh)
+        self.coarse, self.fine = coarse, fine            # (depth, width, skips)
+        self.in_ch = 3 + 6 * self.n_freqs
+        self.precision = precision
+
+    @staticmethod
+    def from_sys_param(sp, precision="fp32"):
+        return RenderCfg(sp["near"], sp["far"], sp["samples"], sp["scale"], sp["emb_freqs_xyz"], sp["white_back"],
+                         sp["sigma_default"], sp["sample_weight_thresh"],
+                         (sp["coarse_MLP_depth"], sp["coarse_MLP_width"], tuple(sp["coarse_MLP_skip"])),
+                         (sp["fine_MLP_depth"], sp["fine_MLP_width"], tuple(sp["fine_MLP_skip"])), precision)
+
+
+def _branch_fwd(cfg, net, tensors, rays_o, rays_d, jitter, S, band_w, sel_idx, n_rows, n_rows_dev):
+    """encode + MLP for one branch.  Returns (out4 [n_rows,4], saved-for-backward tuple)."""
+    depth, width, skips = net
+    dev = rays_o.device
+    B = rays_o.shape[0]
+    smp = ops.make_sampling(cfg.near, cfg.far, S, cfg.n_freqs, band_w)
+    enc = torch.empty(n_rows, cfg.in_ch, device=dev)
+    lib().call("mcnerf_encode_rays_fwd", _p(rays_o), _p(rays_d), _p(jitter), B, ctypes.byref(smp),
+               _p(sel_idx, torch.int32), n_rows, _p(n_rows_dev, torch.int32), _p(enc), cfg.in_ch, _stream())
+    ps = ops.make_mlp_params(tensors, depth, width, skips, in_ch=cfg.in_ch)
+    ws = ops.mlp_f32_workspace(ps, n_rows, dev)
+    d = ops.make_dirs(rays_d, sel_idx, S)
+    out4 = torch.empty(n_rows, 4, device=dev)
+    lib().call("mcnerf_mlp_f32_fwd", ctypes.byref(ps), _p(enc), cfg.in_ch, ctypes.byref(d), n_rows,
+               _p(n_rows_dev, torch.int32), _p(out4), _p(ws), _stream())
+    return out4, (enc, ws)
+
+
+def _branch_bwd(cfg, net, tensors, grads, rays_o, rays_d, jitter, S, band_w, sel_idx, n_rows, n_rows_dev,
+                saved, g_out4, g_rays_o, g_rays_d):
+    depth, width, skips = net
+    enc, ws = saved
+    B = rays_o.shape[0]
+    ps = ops.make_mlp_params(tensors, depth, width, skips, in_ch=cfg.in_ch)
+    gs = ops.fill_mlp_struct(MlpGrads(), grads, depth)
+    d = ops.make_dirs(rays_d, sel_idx, S)
+    g_enc = torch.empty_like(enc)
+    lib().call("mcnerf_mlp_f32_bwd", ctypes.byref(ps), _p(enc), cfg.in_ch, ctypes.byref(d), n_rows,
+               _p(n_rows_dev, torch.int32), _p(g_out4), _p(ws), ctypes.byref(gs), _p(g_enc), _p(g_rays_d), _stream())
+    smp = ops.make_sampling(cfg.near, cfg.far, S, cfg.n_freqs, band_w)
+    lib().call("mcnerf_encode_rays_bwd", _p(rays_o), _p(rays_d), _p(jitter), B, ctypes.byref(smp),
+               _p(sel_idx, torch.int32), n_rows, _p(n_rows_dev, torch.int32), _p(g_enc), cfg.in_ch,
+               _p(g_rays_o), _p(g_rays_d), _stream())
+
+
+def select_and_cap(cfg, out_c, noise_sel, jitter, B, train, cap_perm=None):
+    """Selection weights with their own noise draw, device-side compaction; the reference's train-only
+    128-per-ray cap (model/mc_nerf.py:630-632) is reproduced when it can trigger (Sf > 128)."""
+    dev = out_c.device
+    w_max = torch.zeros(1, device=dev)
+    w_sel = ops.sigma2weights(out_c, noise_sel, jitter=jitter, near=cfg.near, far=cfg.far, sigma_stride=4,
+                              n_rays=B, S=cfg.Sc, w_max=w_max)
+    sel_idx, offs, n_sel = ops.select_fine(w_sel, w_max, cfg.scale, cfg.thresh)
+    n_rows, n_rows_dev = B * cfg.Sf, n_sel
+    if train and cfg.Sf > 128:
+        n = int(n_sel.item())                      # the reference synchronises here too
+        if n > B * 128:
+            perm = cap_perm if cap_perm is not None else torch.randperm(n)     # CPU generator, as the reference
+            keep = perm[:B * 128].to(dev)
+            sel_idx = sel_idx[:n][keep].contiguous()
+            n_rows, n_rows_dev = B * 128, None
+        else:
+            n_rows, n_rows_dev = n, None
+    return sel_idx, n_rows, n_rows_dev, w_sel
+
+
+class RenderFn(torch.autograd.Function):
+    """(rays_d, rays_o, *coarse params, *fine params) -> rgb_c, rgb_f, depth_f, opacity_f  (all [B,*])."""
+
+    @staticmethod
+    def forward(ctx, cfg, train, band_w, rng, cap_perm, rays_d, rays_o, *params):
+        rays_d, rays_o = ops._f32(rays_d), ops._f32(rays_o)
+        B, dev = rays_d.shape[0], rays_d.device
+        nc = len(ops.param_names(cfg.coarse[0]))
+        tc = {k: ops._f32(v) for k, v in zip(ops.param_names(cfg.coarse[0]), params[:nc])}
+        tf = {k: ops._f32(v) for k, v in zip(ops.param_names(cfg.fine[0]), params[nc:])}
+        jitter = ops._f32(rng["jitter"]).reshape(-1) if (train and rng.get("jitter") is not None) else None
+        noise_c, noise_sel, noise_f = (ops._f32(rng[k]) for k in ("noise_c", "noise_sel", "noise_f"))
+        # coarse
+        out_c, saved_c = _branch_fwd(cfg, cfg.coarse, tc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None)
+        cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
+        rgb_c = torch.empty(B, 3, device=dev)
+        lib().call("mcnerf_composite_fwd", _p(out_c), _p(noise_c), _p(rays_d), _p(jitter), None, B,
+                   ctypes.byref(cc), _p(rgb_c), None, None, None, _stream())
+        # selection
+        sel_idx, n_rows, n_rows_dev, _ = select_and_cap(cfg, out_c, noise_sel, jitter, B, train, cap_perm)
+        # fine
+        if n_rows > 0:
+            out_sel, saved_f = _branch_fwd(cfg, cfg.fine, tf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx,
+                                           n_rows, n_rows_dev)
+        else:
+            out_sel, saved_f = torch.empty(0, 4, device=dev), None
+        dense = torch.empty(B * cfg.Sf, 4, device=dev)
+        lib().call("mcnerf_scatter_fine", _p(out_sel) if n_rows else None, _p(sel_idx, torch.int32) if n_rows else None,
+                   n_rows, _p(n_rows_dev, torch.int32), B * cfg.Sf, cfg.sigma_default, _p(dense), _stream())
+        cf = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sf, cfg.white_back)
+        rgb_f = torch.empty(B, 3, device=dev)
+        depth_f = torch.empty(B, 1, device=dev)
+        opa_f = torch.empty(B, 1, device=dev)
+        lib().call("mcnerf_composite_fwd", _p(dense), _p(noise_f), _p(rays_d), _p(jitter), None, B,
+                   ctypes.byref(cf), _p(rgb_f), _p(depth_f), _p(opa_f), None, _stream())
+        ctx.cfg, ctx.band_w, ctx.n_rows = cfg, band_w, n_rows
+        ctx.tc, ctx.tf = tc, tf
+        ctx.saved = (rays_d, rays_o, jitter, noise_c, noise_f, out_c, saved_c, sel_idx, n_rows_dev, dense, saved_f)
+        ctx.mark_non_differentiable(depth_f, opa_f)
+        return rgb_c, rgb_f, depth_f, opa_f
+
+    @staticmethod
+    def backward(ctx, g_rgb_c, g_rgb_f, _gd, _go):
+        cfg, band_w, n_rows = ctx.cfg, ctx.band_w, ctx.n_rows
+        rays_d, rays_o, jitter, noise_c, noise_f, out_c, saved_c, sel_idx, n_rows_dev, dense, saved_f = ctx.saved
+        B, dev = rays_d.shape[0], rays_d.device
+        tc, tf = ctx.tc, ctx.tf
+        gc = {k: torch.zeros_like(v) for k, v in tc.items()}
+        gf = {k: torch.zeros_like(v) for k, v in tf.items()}
+        g_o = torch.zeros_like(rays_o)
+        g_d = torch.zeros_like(rays_d)
+        if g_rgb_f is not None and n_rows > 0:
+            cf = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sf, cfg.white_back)
+            g_dense = torch.empty_like(dense)
+            lib().call("mcnerf_composite_bwd", _p(dense), _p(noise_f), _p(jitter), None, B, ctypes.byref(cf),
+                       _p(ops._f32(g_rgb_f)), _p(g_dense), _stream())
+            g_sel = torch.empty(n_rows, 4, device=dev)
+            lib().call("mcnerf_gather_fine", _p(g_dense), _p(sel_idx, torch.int32), n_rows,
+                       _p(n_rows_dev, torch.int32), _p(g_sel), _stream())
+            _branch_bwd(cfg, cfg.fine, tf, gf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx, n_rows, n_rows_dev,
+                        saved_f, g_sel, g_o, g_d)
+        if g_rgb_c is not None:
+            cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
+            g_out_c = torch.empty_like(out_c)
+            lib().call("mcnerf_composite_bwd", _p(out_c), _p(noise_c), _p(jitter), None, B, ctypes.byref(cc),
+                       _p(ops._f32(g_rgb_c)), _p(g_out_c), _stream())
+            _branch_bwd(cfg, cfg.coarse, tc, gc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
+                        saved_c, g_out_c, g_o, g_d)
+        pg = [gc[k] for k in ops.param_names(cfg.coarse[0])] + [gf[k] for k in ops.param_names(cfg.fine[0])]
+        return (None, None, None, None, None, g_d, g_o) + tuple(pg)
+
+
+def draw_rng(cfg, B, device, train):
+    """The reference's draws in the reference's order from torch's current generator:
+    uniform_[B,1] (train only) -> randn[B,Sc] -> randn[B,Sc] -> randn[B,Sf]."""
+    rng = {}
+    if train:
+        rng["jitter"] = torch.empty(B, 1, device=device).uniform_(0.0, (cfg.far - cfg.near) / cfg.Sc)
+    rng["noise_c"] = torch.randn((B, cfg.Sc), device=device)
+    rng["noise_sel"] = torch.randn((B, cfg.Sc), device=device)
+    rng["noise_f"] = torch.randn((B, cfg.Sf), device=device)
+    return rng
+
+
+def render(cfg, params_c, params_f, rays_d, rays_o, train, band_w=None, rng=None, cap_perm=None):
+    """params_*: dicts of the reference's state_dict names -> tensors (leaf Parameters are fine)."""
+    if rng is None:
+        rng = draw_rng(cfg, rays_d.shape[0], rays_d.device, train)
+    plist = [params_c[k] for k in ops.param_names(cfg.coarse[0])] + [params_f[k] for k in ops.param_names(cfg.fine[0])]
+    return RenderFn.apply(cfg, train, band_w, rng, cap_perm, rays_d, rays_o, *plist)

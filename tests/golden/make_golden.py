@@ -212,8 +212,28 @@ def make_step(name, sp_kw, n_rays, stage, step_r, img_id, full):
     return fx
 
 
+def make_radam():
+    """Trajectory of the reference's RAdam (model/net_utils.py:10-101) over 14 steps: crosses the N_sma >= 5
+    switch (step 6) and wraps the 10-slot step-size cache."""
+    g = torch.Generator().manual_seed(8)
+    p0 = [torch.randn(37, 5, generator=g), torch.randn(11, generator=g)]
+    p = [t.clone().requires_grad_(True) for t in p0]
+    lr, wd = 5e-3, 4e-4
+    opt = net_utils.RAdam([dict(params=p[:1]), dict(params=p[1:], lr=lr * 0.5)], lr=lr, weight_decay=wd)
+    grads, traj = [], {}
+    for step in range(14):
+        gs = [torch.randn(t.shape, generator=g) for t in p]
+        for t, gg in zip(p, gs):
+            t.grad = gg.clone()
+        opt.step()
+        grads.append(gs)
+        traj[step] = [t.detach().clone() for t in p]
+    return dict(p0=p0, lr=lr, wd=wd, grads=grads, traj=traj)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
+    torch.save(make_radam(), os.path.join(HERE, "radam.pt"))
     torch.save(make_modules(), os.path.join(HERE, "modules.pt"))
     tiny_kw = dict(n_cam=5, img_h=10, img_w=12, batch=24, samples=8, scale=2, coarse=(3, 32, (1,)), fine=(4, 64, (2,)))
     torch.save(make_step("tiny", tiny_kw, 24, "GLOBAL_OPTIM_EPOCH", 0.5, 3, True), os.path.join(HERE, "tiny.pt"))

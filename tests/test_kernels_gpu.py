@@ -45,7 +45,9 @@ def test_camera_model_golden(mods):
     close(ops().SE3Fn.apply(w["weights_pose"]), c["pose"])
     close(ops().SE3Fn.apply(w["weights_pose_intr"]), c["calib"])
     b = mods["se3_big"]
-    close(ops().SE3Fn.apply(b["wu"].to(DEV)), b["Rt"], rtol=1e-5, atol=2e-5)
+    # |w| up to ~9 rad: the truncated alternating series cancels ~1e3x, so fp32 evaluation order shows
+    # (terms reach 1e2 with a result of order 1: ~1e-5 relative to the largest term)
+    close(ops().SE3Fn.apply(b["wu"].to(DEV)), b["Rt"], rtol=1e-4, atol=2e-4)
 
 
 def test_camera_model_backward():

@@ -1,0 +1,182 @@
+"""GPU parity of the drop-in model package (MC_Model / NeRF_Model / MC_NeRF_Loss / RAdam) against the
+golden fixtures produced by the unmodified reference, through the reference's own call sequence
+(main.py:79-85): model(data, epoch, epoch_type, ratio) -> loss -> backward."""
+import pytest
+import torch
+
+from conftest import load_golden
+from mc_nerf_b200 import synthetic as syn
+from oracle import mcnerf_oracle as orc
+from replay import Replay
+from tests_checksum import checksum
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    torch.testing.assert_close(a.detach().cpu(), b.detach().cpu(), rtol=rtol, atol=atol)
+
+
+def build_model(sp_kw, cam_w, pc, pf, mode=0):
+    from mc_nerf_b200.model import MC_Model
+    sp = syn.make_sys_param(device=DEV, mode=mode, **sp_kw)
+    m = MC_Model(sp).to(DEV)
+    with torch.no_grad():
+        for k, v in cam_w.items():
+            getattr(m, k).copy_(v)
+    m.nerf.nerf_coarse.load_state_dict(pc)
+    m.nerf.nerf_fine.load_state_dict(pf)
+    return sp, m
+
+
+def run_step(fx, full):
+    from mc_nerf_b200.model import MC_NeRF_Loss
+    if full:
+        i = fx["inputs"]
+        cam_w, pc, pf, batch, rng = i["cam_w"], i["pc"], i["pf"], i["batch"], dict(i["rng"])
+        sp0 = syn.make_sys_param(**fx["sp_kw"])
+        H, W = sp0["data_img_h"], sp0["data_img_w"]
+        rest = torch.tensor([p for p in range(H * W) if p not in set(rng["rand_idx"].tolist())], dtype=torch.long)
+        rng["perm"] = torch.cat([rng["rand_idx"], rest])
+    else:
+        sp0 = syn.make_sys_param(**fx["sp_kw"])
+        cfg = orc.cfg_from_sys_param(sp0)
+        cam_w = syn.init_camera_weights(sp0)
+        pc = orc.init_mlp_params(*cfg["coarse"], seed=42)
+        pf = orc.init_mlp_params(*cfg["fine"], seed=43)
+        batch = syn.make_train_batch(sp0, img_id=fx["img_id"])
+        rng = syn.draw_step_rng(sp0, fx["n_rays"], seed=123)
+    sp, m = build_model(fx["sp_kw"], cam_w, pc, pf)
+    loss_fn = MC_NeRF_Loss(sp)
+    with Replay(randn=[rng["noise_c"], rng["noise_sel"], rng["noise_f"]], randperm=[rng["perm"]],
+                uniform=[rng["jitter"]]):
+        loss_dict, intr_show, pose_show, rays_valid = m(batch, 25, fx["stage"], fx["step_r"])
+        loss = loss_fn(loss_dict, fx["stage"])
+    loss.backward()
+    return sp, m, loss_dict, loss, rays_valid, (cam_w, pc, pf, batch, rng)
+
+
+@pytest.mark.parametrize("name", ["tiny.pt", "tiny_ft.pt"])
+def test_tiny_train_step_matches_reference(name):
+    fx = load_golden(name)
+    sp, m, loss_dict, loss, rays_valid, _ = run_step(fx, True)
+    close(loss_dict["rgb"][0], fx["rgb_c"], rtol=1e-4, atol=2e-6)
+    close(loss_dict["rgb"][1], fx["rgb_f"], rtol=1e-4, atol=2e-6)
+    close(loss_dict["rgb"][2], fx["gt_sel"])
+    close(loss_dict["intr"][0], fx["reproj"], rtol=1e-4, atol=1e-3)
+    close(loss, fx["loss"], rtol=1e-5, atol=1e-6)
+    named = dict(m.named_parameters())
+    for k, g in fx["g_cam"].items():
+        if g is None:
+            assert named[k].grad is None or float(named[k].grad.abs().max()) == 0.0, k
+        else:
+            close(named[k].grad, g, rtol=2e-3, atol=2e-6)
+    for k, g in fx["g_mlp"].items():
+        close(named[k].grad, g, rtol=2e-3, atol=2e-7)
+    # lazily produced validation rays equal a direct full-image generation
+    rd, ro, rgbs = rays_valid
+    assert rd.shape == (sp["data_img_h"] * sp["data_img_w"], 3) and rgbs.shape[-1] == 3
+    rd2, ro2 = orc.get_rays(sp["valid_pose"][fx["img_id"]].cpu(), sp["intr_mat_inv"][2][fx["img_id"]].cpu(),
+                            sp["data_img_h"], sp["data_img_w"])
+    close(rd, rd2)
+    close(ro, ro2)
+
+
+def test_tiny_test_render_matches_reference():
+    fx = load_golden("tiny.pt")
+    i = fx["inputs"]
+    sp, m = build_model(fx["sp_kw"], i["cam_w"], i["pc"], i["pf"])
+    rng = i["rng"]
+    with torch.no_grad(), Replay(randn=[rng["noise_c"], rng["noise_sel"], rng["noise_f"]]):
+        rgb, dep, opa = m.nerf.render_rays_test(fx["rays_d"].to(DEV), fx["rays_o"].to(DEV), m.nerf.nerf_coarse,
+                                                m.nerf.nerf_fine)
+    close(rgb, fx["test"]["rgb"], rtol=1e-4, atol=2e-6)
+    close(dep, fx["test"]["depth"], rtol=1e-4, atol=1e-5)
+    close(opa, fx["test"]["opacity"], rtol=1e-4, atol=2e-6)
+
+
+def test_cfg1_train_step_matches_reference():
+    """BASELINE config 1: 110 cameras, 100x100, 1024 rays, 64+128 samples, both nets 8x256, fp32 path."""
+    fx = load_golden("cfg1.pt")
+    sp, m, loss_dict, loss, _, (cam_w, pc, pf, batch, rng) = run_step(fx, False)
+    cs = fx["checksums"]
+    got = dict(gt=checksum(batch[0]), noise_f=checksum(rng["noise_f"]), jitter=checksum(rng["jitter"]),
+               rand_idx=checksum(rng["rand_idx"]), w_c0=checksum(pc["xyz_encoding_1.0.weight"]),
+               w_f7=checksum(pf["xyz_encoding_8.0.weight"]), pose_w=checksum(cam_w["weights_pose"]))
+    for k in cs:
+        if not all(abs(a - b) <= 1e-6 * max(1.0, abs(b)) for a, b in zip(got[k], cs[k])):
+            pytest.skip(f"seeded input {k} differs on this torch build")
+    close(loss, fx["loss"], rtol=1e-4, atol=1e-5)
+    # the fine-sample gate is discontinuous: allow a handful of rays whose gate flipped
+    for key, idx in (("rgb_c", 0), ("rgb_f", 1)):
+        bad = ((loss_dict["rgb"][idx].detach().cpu() - fx[key]).abs() > 1e-4).any(-1).sum().item()
+        assert bad <= 4, (key, bad)
+    named = dict(m.named_parameters())
+    for k, g in fx["g_cam"].items():
+        close(named[k].grad, g, rtol=3e-2, atol=2e-5)
+    for k, n in fx["g_mlp_norm"].items():
+        assert abs(float(named[k].grad.norm()) - n) <= 5e-3 * max(n, 1e-6), k
+        close(named[k].grad.reshape(-1)[:64], fx["g_mlp_slice"][k], rtol=5e-2, atol=1e-6)
+
+
+def test_module_level_inference_path():
+    """NeRF_Model.inference / sigma2weights with the reference's argument lists (idx_render as int64 pairs)."""
+    fx = load_golden("tiny.pt")
+    i = fx["inputs"]
+    sp, m = build_model(fx["sp_kw"], i["cam_w"], i["pc"], i["pf"])
+    cfg = orc.cfg_from_sys_param(syn.make_sys_param(**fx["sp_kw"]))
+    rng = i["rng"]
+    rd, ro = fx["rays_d"], fx["rays_o"]
+    B, Sc = rd.shape[0], cfg["Sc"]
+    aux = orc.render_rays(i["pc"], i["pf"], cfg, rd, ro, rng, train=False, return_aux=True)
+    nm = m.nerf
+    z_c = nm.z_vals_c.clone().expand(B, -1)
+    xyz = ro.to(DEV).unsqueeze(1) + rd.to(DEV).unsqueeze(1) * z_c.unsqueeze(2)
+    with torch.no_grad(), Replay(randn=[rng["noise_c"]]):
+        rgb, sig, _, dep, opa = nm.inference(nm.nerf_coarse, nm.emmbedding_xyz, 1, xyz, rd.to(DEV), z_c)
+    close(rgb, aux["rgb_c"], rtol=1e-4, atol=2e-6)
+    close(sig, aux["out_c"][..., 0], rtol=1e-4, atol=2e-5)
+    close(dep, aux["depth_c"], rtol=1e-4, atol=1e-5)
+    with Replay(randn=[rng["noise_sel"]]):
+        w = nm.sigma2weights(orc.z_deltas(z_c.cpu()).to(DEV), sig)
+    close(w, aux["w_sel"], rtol=1e-4, atol=1e-6)
+    z_f = nm.z_vals_f.clone().expand(B, -1)
+    xyz_f = ro.to(DEV).unsqueeze(1) + rd.to(DEV).unsqueeze(1) * z_f.unsqueeze(2)
+    with torch.no_grad(), Replay(randn=[rng["noise_f"]]):
+        rgb_f, _, _, dep_f, opa_f = nm.inference(nm.nerf_fine, nm.emmbedding_xyz, 1, xyz_f, rd.to(DEV), z_f,
+                                                 idx_render=aux["idx"].to(DEV), coarse=False)
+    close(rgb_f, aux["rgb_f"], rtol=1e-4, atol=2e-6)
+    close(opa_f, aux["opacity_f"], rtol=1e-4, atol=2e-6)
+
+
+def test_checkpoint_roundtrip_names_and_shapes(tmp_path):
+    """state_dict keys/shapes are the reference's (54 tensors at 8x256/8x256); save_model + rewrite_nerf_ckpt."""
+    sp_kw = dict(n_cam=4, img_h=8, img_w=8, batch=8, samples=8, scale=2)
+    sp0 = syn.make_sys_param(**sp_kw)
+    cfg = orc.cfg_from_sys_param(sp0)
+    pc, pf = orc.init_mlp_params(*cfg["coarse"], seed=1), orc.init_mlp_params(*cfg["fine"], seed=2)
+    sp, m = build_model(sp_kw, syn.init_camera_weights(sp0), pc, pf)
+    sd = m.state_dict()
+    assert len(sd) == 54 and sd["nerf.nerf_fine.xyz_encoding_5.0.weight"].shape == (256, 319)
+    assert sum(v.numel() for v in sd.values()) == 2 * 631836 + 4 * 16
+    m.nerf.weights_pth = str(tmp_path)
+    m.nerf.save_model(m, 3)
+    ck = torch.load(m.nerf.file_path, map_location="cpu")
+    assert set(ck) == {"model_nerf"}
+    re_c = m.nerf.rewrite_nerf_ckpt(ck, coarse=True)
+    assert set(re_c) == set(pc) and torch.equal(re_c["sigma.2.weight"], pc["sigma.2.weight"])
+
+
+def test_radam_matches_reference_trajectory():
+    from mc_nerf_b200.model import RAdam
+    fx = load_golden("radam.pt")
+    p = [t.clone().to(DEV).requires_grad_(True) for t in fx["p0"]]
+    opt = RAdam([dict(params=p[:1]), dict(params=p[1:], lr=fx["lr"] * 0.5)], lr=fx["lr"], weight_decay=fx["wd"])
+    for step, grads in enumerate(fx["grads"]):
+        for t, g in zip(p, grads):
+            t.grad = g.to(DEV)
+        opt.step()
+        if step in fx["traj"]:
+            for t, ref in zip(p, fx["traj"][step]):
+                close(t, ref, rtol=2e-5, atol=1e-7)
