@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""MC-NeRF hot-path benchmark (BASELINE.json metric: train rays/s at 64+128 samples/ray).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+One "step" = one full train step of the reference's GLOBAL_OPTIM stage through the drop-in API exactly as
+reference main.py:79-85 drives it: optimizer.zero_grad -> MC_Model(data, epoch, stage, ratio) -> MC_NeRF_Loss
+-> backward -> RAdam.step, on the BASELINE configs[1] workload (110 cameras, 800x800 images, 4096 rays/batch,
+64 coarse + 128 fine samples, both MLPs 8x256, random-init weights, synthetic Ball rig).
+
+ value : rays/s with the step's inputs already resident in HBM (CUDA-event timed, max over ranks)
+ e2e   : the same steps with HOST (pinned) inputs: H2D of the image/calibration tensors and the D2H read of
+         the loss are inside the timed region
+ N > 1 : one process per GPU (torchrun), each rank renders its own camera's 4096 rays (the reference's DDP
+         semantic: weak scaling) and gradients are all-reduced by NCCL through DistributedDataParallel.
+ --impl reference : the CPU oracle port of the reference's path (oracle/), all host threads, bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train_rays_per_sec_64c_128f"
+UNIT = "rays/s"
+N_CAM, IMG, RAYS, SC, SCALE = 110, 800, 4096, 64, 2
+MACS_PER_EVAL = 629248          # GEMM MACs per MLP evaluation (8x256, skip[4], sigma + SH-27 heads)
+STAGE, RATIO = "GLOBAL_OPTIM_EPOCH", 0.5
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured (sustained)")
+    return dict(hbm=6650.0, tensor=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
+        if not rows:
+            return None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[2:]) if v.lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(int(r[0]) for r in rows), sm_max_mhz=int(rows[0][1]), reasons=reasons,
+                    samples=len(rows))
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------------------------- ours
+def build_workload(device, rank, precision, rays=RAYS, img=IMG):
+    from mc_nerf_b200 import synthetic as syn
+    from mc_nerf_b200.model import MC_Model, MC_NeRF_Loss, RAdam
+    sp = syn.make_sys_param(n_cam=N_CAM, img_h=img, img_w=img, batch=rays, samples=SC, scale=SCALE, device=device,
+                            with_images=False)
+    sp["mlp_precision"] = precision
+    torch.manual_seed(42 + rank)                      # reference main.py:273-277
+    model = MC_Model(sp).to(device)
+    with torch.no_grad():
+        for k, v in syn.init_camera_weights(sp).items():
+            getattr(model, k).copy_(v)
+    loss_fn = MC_NeRF_Loss(sp)
+    # reference main.py:191-195 (the GLOBAL_OPTIM optimiser: every parameter, stage-2 lr, weight decay)
+    opt = RAdam([p for p in model.parameters()], lr=5e-4, eps=1e-8, weight_decay=4e-4)
+    batch = syn.make_train_batch(sp, img_id=(3 + 7 * rank) % N_CAM, seed=11 + rank)
+    return sp, model, loss_fn, opt, batch
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the MC-NeRF hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    from mc_nerf_b200._lib import lib
+    sp, model, loss_fn, opt, batch = build_workload(device, rank, args.precision, args.rays, args.img)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+    dev_batch = tuple(t.to(device) for t in batch)
+    host_batch = tuple(t.pin_memory() for t in batch)
+
+    def step(data, read_loss):
+        opt.zero_grad()
+        loss_dict, _, _, _ = net(data, 25, STAGE, RATIO)
+        loss = loss_fn(loss_dict, STAGE)
+        loss.backward()
+        opt.step()
+        return loss.item() if read_loss else loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(data, read_loss, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            last = step(data, read_loss)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev_batch, False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = lib().launch_count()
+    ms, last = timed(dev_batch, False, args.steps)
+    launches = lib().launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        step(host_batch, True)
+    ms_e2e, _ = timed(host_batch, True, args.steps)
+    rays_step = args.rays * world
+    value = rays_step * args.steps / (ms / 1e3)
+    e2e = rays_step * args.steps / (ms_e2e / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in batch)
+
+    # per-kernel device time of the dominant kernels (CUDA events on the launching stream), 3 extra steps
+    roof = None
+    if rank == 0:
+        L = lib()
+        L.profile_begin()
+        for _ in range(3):
+            step(dev_batch, False)
+        prof = L.profile_end()
+        from mc_nerf_b200 import render
+        n_fine = int(render.LAST["n_rows_dev"].item()) if render.LAST.get("n_rows_dev") is not None else render.LAST["n_rows"]
+        evals = args.rays * SC + n_fine
+        mlp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_mlp_")) / 3
+        comp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_composite") or k.startswith("mcnerf_sigma2w")) / 3
+        peaks = load_peaks()
+        flops = 6.0 * MACS_PER_EVAL * evals          # fwd + dgrad + wgrad
+        ach = flops / (mlp_ms / 1e3) / 1e12
+        roof = dict(bound="tensor", achieved=round(ach, 2), peak=peaks["tensor"], unit="TFLOP/s",
+                    frac=round(ach / peaks["tensor"], 4), traffic=None, peak_source=peaks["src"],
+                    kernel="mcnerf_mlp_* (fwd+bwd, coarse+fine)", kernel_ms_per_step=round(mlp_ms, 3),
+                    mlp_evals_per_step=evals, fine_selected_frac=round(n_fine / (args.rays * SC * SCALE), 4),
+                    kernel_ms_by_name={k: round(v / 3, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:12]})
+        # compositing kernels against the HBM roofline (SURVEY §8d algorithmic bytes: 3348 B fwd + 6156 B bwd per ray)
+        if comp_ms > 0:
+            gbs = 9504.0 * args.rays / (comp_ms / 1e3) / 1e9
+            roof["compositing"] = dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s",
+                                       frac=round(gbs / peaks["hbm"], 4), kernel_ms_per_step=round(comp_ms, 4))
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference(steps=2, warmup=1, rays=1024)
+    if rank == 0:
+        line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="bf16" if args.precision == "bf16" else "f32",
+                    data="synthetic",
+                    config=dict(workload="BASELINE configs[1]: 110 cameras, 800x800, 4096 rays/batch/GPU, 64 coarse + 128 "
+                                         "fine samples, coarse+fine 8x256 MLPs, GLOBAL_OPTIM stage (fwd+loss+bwd+RAdam)",
+                                rays_per_step_per_gpu=args.rays, img=args.img, parallelism=f"dp{world} (rays sharded by image, "
+                                "NCCL allreduce of MLP+camera grads)" if world > 1 else "single GPU",
+                                l2="per-step working set (activation stash > 3 GB) exceeds the 126 MB L2; no flush needed",
+                                precision=args.precision),
+                    e2e=dict(value=round(e2e, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                             ms_per_step=round(ms_e2e / args.steps, 3)),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
+                    loss=float(last.item()) if torch.is_tensor(last) else float(last))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def cpu_reference(steps, warmup, rays):
+    """The reference's CPU implementation of the path (oracle port), all host threads, bounded sample."""
+    from mc_nerf_b200 import synthetic as syn
+    from oracle import mcnerf_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sp = syn.make_sys_param(n_cam=N_CAM, img_h=IMG, img_w=IMG, batch=rays, samples=SC, scale=SCALE, with_images=False)
+    cfg = orc.cfg_from_sys_param(sp)
+    cam = {k: v.clone().requires_grad_(True) for k, v in syn.init_camera_weights(sp).items()}
+    pc = {k: v.clone().requires_grad_(True) for k, v in orc.init_mlp_params(*cfg["coarse"], seed=42).items()}
+    pf = {k: v.clone().requires_grad_(True) for k, v in orc.init_mlp_params(*cfg["fine"], seed=43).items()}
+    batch = syn.make_train_batch(sp, img_id=3)
+    times = []
+    for i in range(warmup + steps):
+        rng = syn.draw_step_rng(sp, rays, seed=100 + i)
+        for d in (cam, pc, pf):
+            for v in d.values():
+                v.grad = None
+        t0 = time.perf_counter()
+        orc.train_step(cam, pc, pf, cfg, batch, rng, step_r=RATIO, stage=STAGE)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return dict(value=round(rays / sec, 2), unit=UNIT, cores=cores, kind="port",
+                sample=f"{steps} train steps (fwd+loss+bwd, no optimiser) of {rays} rays of the same workload "
+                       f"(110 cameras, 800x800, 64+128 samples, 8x256 MLPs), torch CPU fp32 oracle, {cores} threads",
+                sec_per_step=round(sec, 3))
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    rays = 1024
+    cpu = cpu_reference(steps=max(1, min(args.steps, 5)), warmup=max(1, min(args.warmup, 1)), rays=rays)
+    line = dict(metric=METRIC, value=cpu["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=round(cpu["sec_per_step"] * 1e3, 1), higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="BASELINE configs[1] (bounded sample: 1024 rays/step of the 4096-ray batch)"),
+                cpu_baseline=cpu, e2e=dict(value=cpu["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("MCNERF_PRECISION", "fp32"), choices=["bf16", "fp32"])
+    ap.add_argument("--rays", type=int, default=RAYS)
+    ap.add_argument("--img", type=int, default=IMG)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

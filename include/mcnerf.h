@@ -196,6 +196,12 @@ int mcnerf_radam_step(float* p, const float* g, float* exp_avg, float* exp_avg_s
                       float lr, float beta1, float beta2, float eps, float weight_decay,
                       float step_size, int mode, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ tensor-core self test
+ * One 128xN tcgen05 tile: D = A B^T (mn_major = 0: A [128,K], B [N,K] bf16, K-major operands) or
+ * D = A^T B (mn_major = 1: A [K,128], B [K,N], MN-major operands).  Used by tests/ to pin the UMMA
+ * shared-memory / instruction descriptor conventions the fused MLP kernels rely on. */
+int mcnerf_tc_selftest(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int mn_major, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

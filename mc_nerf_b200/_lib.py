@@ -98,9 +98,32 @@ class _Lib:
         if self.cdll.mcnerf_abi_version() != 1:
             raise McnerfError("libmcnerf.so ABI version mismatch")
 
+    def profile_begin(self):
+        """Record a CUDA-event pair around every subsequent call (on the launching stream); bench.py uses this
+        for the per-kernel device times behind the roofline numbers."""
+        self._prof = []
+
+    def profile_end(self):
+        """-> {entry name: total milliseconds} and stop recording."""
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self._prof:
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        self._prof = None
+        return out
+
     def call(self, name, *args):
         """Call an int-returning entry; raise McnerfError(mcnerf_last_error()) on failure."""
-        rc = getattr(self.cdll, name)(*args)
+        if getattr(self, "_prof", None) is not None:
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = getattr(self.cdll, name)(*args)
+            e1.record()
+            self._prof.append((name, e0, e1))
+        else:
+            rc = getattr(self.cdll, name)(*args)
         if rc != 0:
             msg = self.cdll.mcnerf_last_error()
             raise McnerfError(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -19,6 +19,9 @@ from ._lib import MlpGrads, lib
 _p, _stream = ops._p, ops._stream
 
 
+LAST = {}      # debug/bench: row counts of the most recent fine pass (device tensor: no sync is forced here)
+
+
 class RenderCfg:
     """Static renderer configuration (the sys_param keys NeRF_Model reads, ref: model/mc_nerf.py:547-571)."""
 
@@ -116,6 +119,7 @@ class RenderFn(torch.autograd.Function):
                    ctypes.byref(cc), _p(rgb_c), None, None, None, _stream())
         # selection
         sel_idx, n_rows, n_rows_dev, _ = select_and_cap(cfg, out_c, noise_sel, jitter, B, train, cap_perm)
+        LAST["n_rows"], LAST["n_rows_dev"] = n_rows, n_rows_dev
         # fine
         if n_rows > 0:
             out_sel, saved_f = _branch_fwd(cfg, cfg.fine, tf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx,
