@@ -196,6 +196,35 @@ int mcnerf_radam_step(float* p, const float* g, float* exp_avg, float* exp_avg_s
                       float lr, float beta1, float beta2, float eps, float weight_decay,
                       float step_size, int mode, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------ NeRF MLP, bf16 tcgen05 path (a8-a12 fused)
+ * Throughput path for width-256 networks (depth 2..12, at most one input skip, L = 10, deg 2): sampling +
+ * encoding + MLP + SH head fused in one persistent kernel; bf16 operands, fp32 accumulation in TMEM.
+ * ref: model/mc_nerf.py:599-602,633-635 ; model/net_block.py:20-35,67-78 ; model/net_utils.py:154-169.
+ * Weights are first packed (once per optimiser step) into UMMA-ready bf16 images. */
+typedef struct {
+  /* rays mode (x_enc == NULL): row m is sample sample_idx[m] (or m) = ray*S + k of the grid `smp` */
+  const float *rays_o, *rays_d, *jitter;
+  int n_rays;
+  mcnerf_sampling smp;
+  const int32_t* sample_idx;
+  int n_rows;                    /* capacity / row count */
+  const int32_t* n_rows_dev;     /* optional device-side row count (<= n_rows) */
+  /* explicit mode: encodings x_enc [n_rows, ld_enc] (63 valid columns) and per-row view directions [n_rows,3] */
+  const float* x_enc;
+  int ld_enc;
+  const float* dirs_rows;
+} mcnerf_tc_input;
+
+int mcnerf_mlp_tc_supported(const mcnerf_mlp_params* p);   /* 1 if this network shape can use the tcgen05 path */
+int mcnerf_mlp_tc_pack_sizes(const mcnerf_mlp_params* p, size_t* wf_bytes, size_t* wb_bytes, size_t* bias_bytes);
+/* wf: forward image, wb: transposed image for the backward pass (may be NULL), bias: fp32 bias block */
+int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb, float* bias, void* stream);
+/* bytes of the activation stash the training forward writes for n_rows rows */
+size_t mcnerf_mlp_tc_stash_bytes(const mcnerf_mlp_params* p, int n_rows);
+/* out4 [n_rows,4] = (sigma_raw, r, g, b).  stash == NULL: inference (activations never leave the SM). */
+int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, const float* bias, const mcnerf_tc_input* in,
+                      float* out4, void* stash, void* stream);
+
 /* ------------------------------------------------------------------ tensor-core self test
  * One 128xN tcgen05 tile: D = A B^T (mn_major = 0: A [128,K], B [N,K] bf16, K-major operands) or
  * D = A^T B (mn_major = 1: A [K,128], B [K,N], MN-major operands).  Used by tests/ to pin the UMMA

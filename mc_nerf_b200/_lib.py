@@ -45,7 +45,13 @@ class CompositeCfg(ctypes.Structure):
                 ("white_back", ctypes.c_int)]
 
 
-_STRUCTS = {"mcnerf_sampling": Sampling, "mcnerf_mlp_params": MlpParams, "mcnerf_mlp_grads": MlpGrads,
+class TcInput(ctypes.Structure):
+    _fields_ = [("rays_o", _fp), ("rays_d", _fp), ("jitter", _fp), ("n_rays", ctypes.c_int), ("smp", Sampling),
+                ("sample_idx", _fp), ("n_rows", ctypes.c_int), ("n_rows_dev", _fp),
+                ("x_enc", _fp), ("ld_enc", ctypes.c_int), ("dirs_rows", _fp)]
+
+
+_STRUCTS = {"mcnerf_tc_input": TcInput, "mcnerf_sampling": Sampling, "mcnerf_mlp_params": MlpParams, "mcnerf_mlp_grads": MlpGrads,
             "mcnerf_dirs": Dirs, "mcnerf_composite_cfg": CompositeCfg}
 _SCALARS = {"int": ctypes.c_int, "float": ctypes.c_float, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
             "uint64_t": ctypes.c_uint64, "uint32_t": ctypes.c_uint32, "void": None}

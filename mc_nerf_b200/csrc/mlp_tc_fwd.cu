@@ -1,0 +1,457 @@
+// bf16 tcgen05 NeRF MLP, forward: ONE persistent kernel per network evaluation that fuses
+//   ray sampling + sin/cos (BARF-weighted) encoding  ->  8x256 trunk with input skip  ->  sigma head
+//   -> SH-27 colour head -> eval_sh + sigmoid,
+// keeping every activation on-chip (shared memory as the UMMA A operand, fp32 accumulators in TMEM).
+// ref: model/mc_nerf.py:599-602/633-635 (sampling), model/net_block.py:20-35 (encoding), :67-78 (MLP),
+//      model/net_utils.py:154-169 (eval_sh).
+//
+// CTA = 10 warps on one SM, two 128-row tiles in flight (TMEM: 2 x 256 fp32 columns):
+//   warps 0-3 / 4-7 : input stage + epilogues of tile slot 0 / 1 (thread = row = TMEM lane)
+//   warp 8          : weight producer - 1-D bulk async copies (TMA engine) of pre-packed 16 KB UMMA-ready
+//                     chunks into a 4-deep ring, mbarrier full/empty
+//   warp 9          : MMA issuer - one thread issues tcgen05.mma (M=128, N<=256, K=16) for both slots,
+//                     alternating slots per layer so one slot's epilogue overlaps the other slot's MMAs
+// Weights are re-streamed from L2 per tile (1.26 MB per net: L2 resident); activations never touch HBM in
+// inference; in training each layer's bf16 activation tile is also written to the stash for the backward pass.
+#include "mlp_tc.cuh"
+
+namespace mlptc {
+
+// ----------------------------------------------------------------------------------------- packing
+// dst chunk image for a [N x K] K-major B operand: chunk c (32 k), plane kg (8 k), row n: ((c*4+kg)*N + n)*16 B.
+// value(n,k) = src[n*sn + kk*sk] with the 63->64 pad remap applied to k (pad_k) or n (pad_n).
+__global__ void pack_k(const float* __restrict__ src, int64_t sn, int64_t sk, int N, int K, int pad_k, int pad_n,
+                       int n_valid, int k_valid, __nv_bfloat16* __restrict__ dst) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * K) return;
+  int j = i & 7;
+  int64_t t = i >> 3;
+  int n = (int)(t % N);
+  int kgg = (int)(t / N);          // global k-group index (chunk*4 + kg)
+  int k = kgg * 8 + j;
+  int ks = k, ns = n;
+  bool ok = true;
+  if (pad_k) { if (k == 63) ok = false; else if (k > 63) ks = k - 1; }
+  if (pad_n) { if (n == 63) ok = false; else if (n > 63) ns = n - 1; }
+  if (ns >= n_valid || ks >= k_valid) ok = false;
+  dst[i] = __float2bfloat16(ok ? src[ns * sn + ks * sk] : 0.f);
+}
+
+__global__ void pack_bias_k(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) dst[i] = i < n ? src[i] : 0.f;
+}
+
+// ----------------------------------------------------------------------------------------- plan
+int build_layout(const mcnerf_mlp_params* p, PackLayout* L) {
+  MC_ARG(p && p->width == WID && p->in_ch == 63 && p->sh_dim == 27 && p->depth >= 2 && p->depth <= 12);
+  int n_skip = __builtin_popcount(p->skip_mask);
+  MC_ARG(n_skip <= 1 && (p->skip_mask & 1u) == 0 && (p->skip_mask >> p->depth) == 0);
+  L->depth = p->depth;
+  L->skip_mask = p->skip_mask;
+  Plan& P = L->fwd;
+  uint32_t off = 0, boff = 0;
+  int ns = 0;
+  int bias = 0;
+  auto add = [&](int a_src, int K, int N, int epi, int slot) {
+    Step& s = P.s[ns];
+    s.a_src = a_src; s.n_chunks = K / KC; s.N = N; s.epi = epi; s.w_off = off; s.bias_off = bias; s.stash_slot = slot;
+    L->wb_off[ns] = boff;
+    off += (uint32_t)N * K * 2;
+    boff += (uint32_t)N * K * 2;
+    bias += 256;
+    ++ns;
+  };
+  for (int i = 0; i < p->depth; ++i) {
+    if (i == 0) add(A_ENC, ENCW, WID, EPI_RELU, i);
+    else if (p->skip_mask >> i & 1u) add(A_ENC_ACT, ENCW + WID, WID, EPI_RELU, i);
+    else add(A_ACT, WID, WID, EPI_RELU, i);
+  }
+  add(A_ACT, WID, WID, EPI_SIGMA, p->depth);         // sigma.0 (sigma.2 is a dot product in its epilogue)
+  add(A_ACT, WID, WID, EPI_RELU, p->depth + 1);      // sh.0
+  add(A_ACT, WID, 32, EPI_OUT, -1);                  // sh.2 (27 -> 32 columns) + eval_sh + sigmoid
+  P.n_steps = ns;
+  L->wf_bytes = off;
+  L->wb_bytes = boff;
+  L->sig2_off = bias;
+  L->bias_floats = bias + 256 + 8;
+  return 0;
+}
+
+static int pack_matrix(const float* src, int64_t sn, int64_t sk, int N, int K, int pad_k, int pad_n, int n_valid,
+                       int k_valid, void* dst, cudaStream_t st) {
+  int64_t tot = (int64_t)N * K;
+  pack_k<<<cdiv(tot, 256), 256, 0, st>>>(src, sn, sk, N, K, pad_k, pad_n, n_valid, k_valid, (__nv_bfloat16*)dst);
+  MC_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------- forward kernel
+struct FwdArgs {
+  Plan plan;
+  const uint8_t* wpack;
+  const float* bias;
+  int sig2_off;
+  const float *rays_o, *rays_d, *jitter;
+  mcnerf_sampling smp;
+  const int32_t* sel_idx;
+  int n_rows;
+  const int32_t* n_rows_dev;
+  const float* x_enc;
+  int ld_enc;
+  const float* dirs_rows;
+  float* out4;
+  uint8_t* stash;        // [tile][n_slots][ACT_BYTES] or null
+  uint8_t* stash_enc;    // [tile][ENC_BYTES]
+  float* stash_sh;       // [row][SH_LD]
+  int n_slots;
+};
+
+struct __align__(16) SmemBars {
+  uint64_t w_full[NSTAGE], w_empty[NSTAGE], a_ready[2], acc_full[2];
+  uint32_t tmem_base;
+};
+
+constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + NSTAGE * STAGE_BYTES + 256;
+
+__constant__ float cC0 = 0.28209479177387814f;
+__constant__ float cC1 = 0.4886025119029199f;
+__constant__ float cC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                             -1.0925484305920792f, 0.5462742152960396f};
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Encode one row (sample) into 64 bf16 features and store them as 8 planes of the enc tile image
+// (and optionally to the global stash image).  L = 10 frequencies.
+__device__ __forceinline__ void encode_row(const FwdArgs& a, int row_g, bool valid, uint32_t enc_smem, int q,
+                                           uint8_t* stash_enc_tile) {
+  float f[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) f[i] = 0.f;
+  if (valid) {
+    if (a.x_enc) {
+      const float* src = a.x_enc + (size_t)row_g * a.ld_enc;
+#pragma unroll
+      for (int i = 0; i < 63; ++i) f[i] = src[i];
+    } else {
+      int flat = a.sel_idx ? a.sel_idx[row_g] : row_g;
+      int ray = flat / a.smp.S, k = flat - ray * a.smp.S;
+      float z = linspace_f(a.smp.near_, a.smp.far_, a.smp.S, k) + (a.jitter ? a.jitter[ray] : 0.f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float xc = a.rays_o[3 * ray + c] + a.rays_d[3 * ray + c] * z;
+        f[c] = xc;
+        float sn, cs;
+        sincosf(xc, &sn, &cs);
+#pragma unroll
+        for (int kf = 0; kf < 10; ++kf) {
+          f[3 + c * 20 + kf] = sn * a.smp.band_w[kf];
+          f[3 + c * 20 + 10 + kf] = cs * a.smp.band_w[kf];
+          float s2 = 2.f * sn * cs;            // angle doubling: error grows 2x per octave (<= 5e-5 at 2^9),
+          float c2 = 1.f - 2.f * sn * sn;      // far below the bf16 rounding of the feature
+          sn = s2;
+          cs = c2;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int kg = 0; kg < 8; ++kg) {
+    uint32_t w0 = tc::pack_bf16(f[kg * 8 + 0], f[kg * 8 + 1]), w1 = tc::pack_bf16(f[kg * 8 + 2], f[kg * 8 + 3]);
+    uint32_t w2 = tc::pack_bf16(f[kg * 8 + 4], f[kg * 8 + 5]), w3 = tc::pack_bf16(f[kg * 8 + 6], f[kg * 8 + 7]);
+    st_shared_v4(enc_smem + kg * PLANE + q * 16, w0, w1, w2, w3);
+    if (stash_enc_tile) *reinterpret_cast<uint4*>(stash_enc_tile + kg * PLANE + q * 16) = make_uint4(w0, w1, w2, w3);
+  }
+}
+
+__global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ FwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* act = smem;                                   // [2][ACT_BYTES]
+  uint8_t* enc = smem + 2 * ACT_BYTES;                   // [2][ENC_BYTES]
+  uint8_t* wst = enc + 2 * ENC_BYTES;                    // [NSTAGE][STAGE_BYTES]
+  SmemBars* bars = reinterpret_cast<SmemBars*>(wst + NSTAGE * STAGE_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
+  const int n_tiles = (rows + TM - 1) / TM;
+  const int n_pairs = (n_tiles + 1) / 2;
+  const int n_steps = a.plan.n_steps;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 128); tc::mbar_init(&bars->acc_full[i], 1); }
+    tc::mbar_init_fence();
+  }
+  if (warp == 9) tc::tmem_alloc(&bars->tmem_base, 512);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t par = 0;
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (int s = 0; s < n_steps; ++s) {
+          const Step& st = a.plan.s[s];
+          const uint32_t bytes = (uint32_t)st.N * KC * 2;
+          for (int t = 0; t < 2; ++t)
+            for (int c = 0; c < st.n_chunks; ++c) {
+              tc::mbar_wait(&bars->w_empty[stage], par ^ 1);
+              tc::mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
+              tc::bulk_g2s(wst + stage * STAGE_BYTES, a.wpack + st.w_off + (size_t)c * bytes, bytes, &bars->w_full[stage]);
+              if (++stage == NSTAGE) { stage = 0; par ^= 1; }
+            }
+        }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t par = 0, apar[2] = {0, 0};
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (int s = 0; s < n_steps; ++s) {
+          const Step& st = a.plan.s[s];
+          const uint32_t idesc = tc::umma_idesc_bf16(TM, st.N);
+          for (int t = 0; t < 2; ++t) {
+            tc::mbar_wait(&bars->a_ready[t], apar[t]);
+            apar[t] ^= 1;
+            tc::tcgen05_fence_after();
+            const uint32_t act_t = tc::smem_u32(act + t * ACT_BYTES), enc_t = tc::smem_u32(enc + t * ENC_BYTES);
+            for (int c = 0; c < st.n_chunks; ++c) {
+              tc::mbar_wait(&bars->w_full[stage], par);
+              tc::tcgen05_fence_after();
+              uint32_t a_base;
+              if (st.a_src == A_ENC) a_base = enc_t + c * (KC / 8) * PLANE;
+              else if (st.a_src == A_ACT) a_base = act_t + c * (KC / 8) * PLANE;
+              else a_base = (c < ENCW / KC) ? enc_t + c * (KC / 8) * PLANE : act_t + (c - ENCW / KC) * (KC / 8) * PLANE;
+              const uint32_t b_base = tc::smem_u32(wst + stage * STAGE_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < KC / 16; ++kk) {
+                uint64_t da = tc::umma_desc(a_base + kk * 2 * PLANE, PLANE, 128);
+                uint64_t db = tc::umma_desc(b_base + kk * 2 * st.N * 16, st.N * 16, 128);
+                tc::umma_bf16(tmem + t * 256, da, db, idesc, (c | kk) != 0);
+              }
+              tc::umma_commit(&bars->w_empty[stage]);
+              if (++stage == NSTAGE) { stage = 0; par ^= 1; }
+            }
+            tc::umma_commit(&bars->acc_full[t]);
+          }
+        }
+    }
+  } else {
+    // ------------------------------------------------------------------ input stage + epilogues (slot t)
+    const int t = warp >> 2;
+    const int q = tid - t * 128;                      // row in tile == TMEM lane
+    const uint32_t act_t = tc::smem_u32(act + t * ACT_BYTES), enc_t = tc::smem_u32(enc + t * ENC_BYTES);
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * 256;
+    uint32_t par = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int tile = 2 * pair + t;
+      const int row_g = tile * TM + q;
+      const bool valid = row_g < rows;
+      uint8_t* st_enc = (a.stash_enc && tile < n_tiles) ? a.stash_enc + (size_t)tile * ENC_BYTES : nullptr;
+      encode_row(a, row_g, valid, enc_t, q, st_enc);
+      tc::fence_proxy_async();
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(&bars->a_ready[t]);
+      float sigma_raw = 0.f;
+      for (int s = 0; s < n_steps; ++s) {
+        const Step& st = a.plan.s[s];
+        tc::mbar_wait(&bars->acc_full[t], par);
+        par ^= 1;
+        tc::tcgen05_fence_after();
+        const float* bias = a.bias + st.bias_off;
+        if (st.epi == EPI_OUT) {
+          uint32_t v[32];
+          tc::tmem_ld32(taddr, v);
+          tc::tmem_ld_wait();
+          if (valid) {
+            float sh[27];
+#pragma unroll
+            for (int i = 0; i < 27; ++i) sh[i] = __uint_as_float(v[i]) + __ldg(bias + i);
+            const float* dp;
+            if (a.x_enc) dp = a.dirs_rows + (size_t)row_g * 3;
+            else {
+              int flat = a.sel_idx ? a.sel_idx[row_g] : row_g;
+              dp = a.rays_d + 3 * (size_t)(flat / a.smp.S);
+            }
+            float x = dp[0], y = dp[1], z = dp[2];
+            float Y[9] = {cC0, -cC1 * y, cC1 * z, -cC1 * x, cC2[0] * x * y, cC2[1] * y * z,
+                          cC2[2] * (2.f * z * z - x * x - y * y), cC2[3] * x * z, cC2[4] * (x * x - y * y)};
+            float c[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              float acc = 0.f;
+#pragma unroll
+              for (int b = 0; b < 9; ++b) acc += Y[b] * sh[9 * ch + b];
+              c[ch] = sigmoid_f(acc);
+            }
+            reinterpret_cast<float4*>(a.out4)[row_g] = make_float4(sigma_raw, c[0], c[1], c[2]);
+            if (a.stash_sh) {
+              float4* dst = reinterpret_cast<float4*>(a.stash_sh + (size_t)row_g * SH_LD);
+#pragma unroll
+              for (int i = 0; i < 7; ++i)
+                dst[i] = make_float4(sh[4 * i], sh[4 * i + 1], sh[4 * i + 2], i < 6 ? sh[4 * i + 3] : 0.f);
+            }
+          }
+        } else {
+          uint8_t* st_tile = (a.stash && st.stash_slot >= 0 && tile < n_tiles)
+                                 ? a.stash + ((size_t)tile * a.n_slots + st.stash_slot) * ACT_BYTES
+                                 : nullptr;
+          const bool to_smem = st.epi == EPI_RELU;
+          const float* w2 = a.bias + a.sig2_off;
+          float dot = 0.f;
+#pragma unroll 1
+          for (int cg = 0; cg < WID / 32; ++cg) {
+            uint32_t v[32];
+            tc::tmem_ld32(taddr + cg * 32, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x[8];
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cg * 32 + j * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cg * 32 + j * 8 + 4));
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(v[j * 8 + i]) + bb[i], 0.f);
+              if (!to_smem) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8 + 4));
+                dot += x[0] * s0.x + x[1] * s0.y + x[2] * s0.z + x[3] * s0.w + x[4] * s1.x + x[5] * s1.y + x[6] * s1.z +
+                       x[7] * s1.w;
+              }
+              const uint32_t w0 = tc::pack_bf16(x[0], x[1]), w1 = tc::pack_bf16(x[2], x[3]);
+              const uint32_t w2p = tc::pack_bf16(x[4], x[5]), w3 = tc::pack_bf16(x[6], x[7]);
+              const int kg = cg * 4 + j;
+              if (to_smem) st_shared_v4(act_t + kg * PLANE + q * 16, w0, w1, w2p, w3);
+              if (st_tile) *reinterpret_cast<uint4*>(st_tile + kg * PLANE + q * 16) = make_uint4(w0, w1, w2p, w3);
+            }
+          }
+          if (!to_smem) sigma_raw = dot + __ldg(w2 + 256);
+        }
+        if (s + 1 < n_steps) {
+          tc::fence_proxy_async();
+          tc::tcgen05_fence_before();
+          tc::mbar_arrive(&bars->a_ready[t]);
+        }
+      }
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 9) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace mlptc
+
+using namespace mlptc;
+
+extern "C" int mcnerf_mlp_tc_supported(const mcnerf_mlp_params* p) {
+  if (!p) return 0;
+  if (p->width != WID || p->in_ch != 63 || p->sh_dim != 27 || p->depth < 2 || p->depth > 12) return 0;
+  if (__builtin_popcount(p->skip_mask) > 1 || (p->skip_mask & 1u) || (p->skip_mask >> p->depth)) return 0;
+  return 1;
+}
+
+extern "C" int mcnerf_mlp_tc_pack_sizes(const mcnerf_mlp_params* p, size_t* wf_bytes, size_t* wb_bytes,
+                                        size_t* bias_bytes) {
+  PackLayout L;
+  if (int e = build_layout(p, &L)) return e;
+  if (wf_bytes) *wf_bytes = L.wf_bytes;
+  if (wb_bytes) *wb_bytes = L.wb_bytes;
+  if (bias_bytes) *bias_bytes = (size_t)L.bias_floats * sizeof(float);
+  return 0;
+}
+
+// fp32 reference parameters -> bf16 UMMA-ready images (forward: B(n=out,k=in); dgrad: B(n=in,k=out)) + fp32 bias block
+extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb, float* bias, void* stream) {
+  PackLayout L;
+  if (int e = build_layout(p, &L)) return e;
+  MC_ARG(wf && bias);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* f = (uint8_t*)wf;
+  uint8_t* b = (uint8_t*)wb;
+  const int D = p->depth;
+  for (int s = 0; s < L.fwd.n_steps; ++s) {
+    const Step& sp = L.fwd.s[s];
+    const float* W;
+    const float* bs;
+    int n_out = WID, k_in, ld, pad = 0;
+    if (s < D) {
+      W = p->W[s]; bs = p->b[s];
+      if (s == 0) { k_in = 63; ld = 63; pad = 1; }
+      else if (p->skip_mask >> s & 1u) { k_in = 63 + WID; ld = 63 + WID; pad = 1; }
+      else { k_in = WID; ld = WID; }
+    } else if (s == D) { W = p->W_sigma0; bs = p->b_sigma0; k_in = WID; ld = WID; }
+    else if (s == D + 1) { W = p->W_sh0; bs = p->b_sh0; k_in = WID; ld = WID; }
+    else { W = p->W_sh2; bs = p->b_sh2; k_in = WID; ld = WID; n_out = 27; }
+    const int K = sp.n_chunks * KC;
+    // forward image: rows n = output feature, reduction k = input feature (padded)
+    if (int e = pack_matrix(W, ld, 1, sp.N, K, pad, 0, n_out, k_in, f + sp.w_off, st)) return e;
+    // dgrad image: rows n = input feature (padded), reduction k = output feature
+    if (b) {
+      const int Nb = K, Kb = sp.N;
+      if (int e = pack_matrix(W, 1, ld, Nb, Kb, 0, pad, k_in, n_out, b + L.wb_off[s], st)) return e;
+    }
+    pack_bias_k<<<1, 256, 0, st>>>(bs, n_out, bias + sp.bias_off, 256);
+    MC_LAUNCHED();
+  }
+  pack_bias_k<<<1, 256, 0, st>>>(p->W_sigma2, WID, bias + L.sig2_off, 256);
+  MC_LAUNCHED();
+  pack_bias_k<<<1, 32, 0, st>>>(p->b_sigma2, 1, bias + L.sig2_off + 256, 8);
+  MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t mcnerf_mlp_tc_stash_bytes(const mcnerf_mlp_params* p, int n_rows) {
+  if (!mcnerf_mlp_tc_supported(p) || n_rows <= 0) return 0;
+  size_t tiles = (size_t)(n_rows + TM - 1) / TM;
+  tiles += tiles & 1;   // tiles are processed in pairs
+  return tiles * ((size_t)(p->depth + 2) * ACT_BYTES + ENC_BYTES + (size_t)TM * SH_LD * sizeof(float));
+}
+
+extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, const float* bias,
+                                 const mcnerf_tc_input* in, float* out4, void* stash, void* stream) {
+  PackLayout L;
+  if (int e = build_layout(p, &L)) return e;
+  MC_ARG(wf && bias && in && out4 && in->n_rows >= 0 && ((uintptr_t)out4 & 15) == 0);
+  if (in->n_rows == 0) return 0;
+  MC_ARG((in->x_enc && in->dirs_rows && in->ld_enc >= 63) ||
+         (in->rays_o && in->rays_d && in->smp.S >= 2 && in->smp.n_freqs == 10));
+  FwdArgs a;
+  a.plan = L.fwd;
+  a.wpack = (const uint8_t*)wf;
+  a.bias = bias;
+  a.sig2_off = L.sig2_off;
+  a.rays_o = in->rays_o; a.rays_d = in->rays_d; a.jitter = in->jitter; a.smp = in->smp;
+  a.sel_idx = in->sample_idx; a.n_rows = in->n_rows; a.n_rows_dev = in->n_rows_dev;
+  a.x_enc = in->x_enc; a.ld_enc = in->ld_enc; a.dirs_rows = in->dirs_rows;
+  a.out4 = out4;
+  a.n_slots = p->depth + 2;
+  if (stash) {
+    size_t tiles = (size_t)(in->n_rows + TM - 1) / TM;
+    tiles += tiles & 1;
+    a.stash = (uint8_t*)stash;
+    a.stash_enc = a.stash + tiles * (size_t)a.n_slots * ACT_BYTES;
+    a.stash_sh = (float*)(a.stash_enc + tiles * ENC_BYTES);
+  } else {
+    a.stash = nullptr; a.stash_enc = nullptr; a.stash_sh = nullptr;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+    attr_set = true;
+  }
+  int n_pairs = ((in->n_rows + TM - 1) / TM + 1) / 2;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = n_pairs < sms ? n_pairs : sms;
+  mlp_tc_fwd_k<<<grid, 320, SMEM_FWD, (cudaStream_t)stream>>>(a);
+  MC_LAUNCHED();
+  return 0;
+}

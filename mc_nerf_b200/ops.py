@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import CompositeCfg, Dirs, MlpGrads, MlpParams, Sampling, lib
+from ._lib import CompositeCfg, Dirs, MlpGrads, MlpParams, Sampling, TcInput, lib
 
 
 def _stream():
@@ -355,3 +355,68 @@ class ScatterFineFn(torch.autograd.Function):
         g_sel = torch.empty(ctx.n, 4, device=g_dense.device)
         lib().call("mcnerf_gather_fine", _p(_f32(g_dense)), _p(idx, torch.int32), ctx.n, None, _p(g_sel), _stream())
         return g_sel, None, None, None
+
+
+# --------------------------------------------------------------------------- bf16 tcgen05 MLP path
+
+
+def tc_supported(ps):
+    return bool(lib().cdll.mcnerf_mlp_tc_supported(ctypes.byref(ps)))
+
+
+class TcWeights:
+    """UMMA-ready bf16 weight images + fp32 bias block of one network (derived cache of the fp32 parameters;
+    re-packed when any parameter's version counter changes, i.e. after optimizer.step())."""
+
+    def __init__(self):
+        self.key = None
+        self.wf = self.wb = self.bias = None
+
+    def get(self, ps, tensors, need_bwd=True):
+        key = tuple((t.data_ptr(), t._version) for t in tensors.values())
+        if key != self.key or (need_bwd and self.wb is None):
+            dev = next(iter(tensors.values())).device
+            sz = [ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()]
+            lib().call("mcnerf_mlp_tc_pack_sizes", ctypes.byref(ps), *[ctypes.byref(x) for x in sz])
+            if self.wf is None:
+                self.wf = torch.empty(sz[0].value, dtype=torch.uint8, device=dev)
+                self.bias = torch.empty(sz[2].value // 4, dtype=torch.float32, device=dev)
+            if need_bwd and self.wb is None:
+                self.wb = torch.empty(sz[1].value, dtype=torch.uint8, device=dev)
+            lib().call("mcnerf_mlp_tc_pack", ctypes.byref(ps), _p(self.wf, torch.uint8),
+                       _p(self.wb, torch.uint8) if self.wb is not None else None, _p(self.bias), _stream())
+            self.key = key
+        return self
+
+
+def make_tc_input_rays(rays_o, rays_d, jitter, smp, sel_idx, n_rows, n_rows_dev):
+    t = TcInput()
+    t.rays_o, t.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
+    t.jitter = jitter.data_ptr() if jitter is not None else None
+    t.n_rays = rays_o.shape[0]
+    t.smp = smp
+    t.sample_idx = sel_idx.data_ptr() if sel_idx is not None else None
+    t.n_rows = int(n_rows)
+    t.n_rows_dev = n_rows_dev.data_ptr() if n_rows_dev is not None else None
+    t.x_enc, t.ld_enc, t.dirs_rows = None, 0, None
+    return t
+
+
+def make_tc_input_enc(x_enc, dirs):
+    t = TcInput()
+    t.rays_o = t.rays_d = t.jitter = t.sample_idx = t.n_rows_dev = None
+    t.n_rays = 0
+    t.smp = make_sampling(0.0, 1.0, 2, 10)
+    t.n_rows = x_enc.shape[0]
+    t.x_enc, t.ld_enc, t.dirs_rows = x_enc.data_ptr(), x_enc.shape[1], dirs.data_ptr()
+    return t
+
+
+def tc_stash(ps, n_rows, device):
+    n = lib().cdll.mcnerf_mlp_tc_stash_bytes(ctypes.byref(ps), int(n_rows))
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def mlp_tc_fwd(ps, tcw, tcin, out4, stash=None):
+    lib().call("mcnerf_mlp_tc_fwd", ctypes.byref(ps), _p(tcw.wf, torch.uint8), _p(tcw.bias), ctypes.byref(tcin),
+               _p(out4), _p(stash, torch.uint8) if stash is not None else None, _stream())

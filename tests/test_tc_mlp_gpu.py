@@ -1,0 +1,97 @@
+"""bf16 tcgen05 MLP path against the oracle.  Two comparisons per case:
+  * against the oracle with the SAME rounding points emulated (bf16 weights / inputs / per-layer activations,
+    fp32 accumulation): tight - proves the kernel computes what it claims;
+  * against the plain fp32 oracle: the stated bf16 tolerance of the path."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mcnerf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def mlp_forward_bf16emu(p, x_enc, dirs, depth, skips):
+    """oracle.mlp_forward with the kernel's rounding points."""
+    x = bf(x_enc)
+    h = x
+    for i in range(depth):
+        if i in skips:
+            h = torch.cat([x, h], -1)
+        h = bf(F.relu(F.linear(h, bf(p[f"xyz_encoding_{i+1}.0.weight"]), p[f"xyz_encoding_{i+1}.0.bias"])))
+    s = F.relu(F.linear(h, bf(p["sigma.0.weight"]), p["sigma.0.bias"]))           # kept fp32 in the epilogue
+    sigma = F.linear(s, p["sigma.2.weight"], p["sigma.2.bias"])
+    c = bf(F.relu(F.linear(h, bf(p["sh.0.weight"]), p["sh.0.bias"])))
+    sh = F.linear(c, bf(p["sh.2.weight"]), p["sh.2.bias"])
+    rgb = torch.sigmoid(orc.eval_sh_deg2(sh.reshape(-1, 3, 9), dirs))
+    return torch.cat([sigma, rgb], -1)
+
+
+def setup(depth, skips, seed=3):
+    from mc_nerf_b200 import ops
+    p = orc.init_mlp_params(depth, 256, skips, seed=seed)
+    tensors = {k: p[k].to(DEV).contiguous() for k in ops.param_names(depth)}
+    ps = ops.make_mlp_params(tensors, depth, 256, skips)
+    assert ops.tc_supported(ps)
+    tcw = ops.TcWeights().get(ps, tensors)
+    return ops, p, tensors, ps, tcw
+
+
+@pytest.mark.parametrize("depth,skips,M", [(8, (4,), 1000), (8, (4,), 128 * 5), (4, (2,), 77), (3, (), 300)])
+def test_tc_forward_explicit_encodings(depth, skips, M):
+    ops, p, tensors, ps, tcw = setup(depth, skips)
+    g = torch.Generator().manual_seed(M)
+    xyz = (torch.rand(M, 3, generator=g) - 0.5) * 6
+    x_enc = orc.sincos_encode(xyz, 10)
+    dirs = F.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    out = torch.full((M, 4), float("nan"), device=DEV)
+    ops.mlp_tc_fwd(ps, tcw, ops.make_tc_input_enc(x_enc.to(DEV).contiguous(), dirs.to(DEV).contiguous()), out)
+    torch.cuda.synchronize()
+    emu = mlp_forward_bf16emu(p, x_enc, dirs, depth, skips)
+    ref = orc.mlp_forward(p, x_enc, dirs, depth, skips)
+    err_emu = (out.cpu() - emu).abs().max().item()
+    err_ref = (out.cpu() - ref).abs().max().item()
+    print(f"depth {depth}: max|tc - bf16emu| = {err_emu:.3e}, max|tc - fp32| = {err_ref:.3e}")
+    assert err_emu < 3e-3, err_emu          # accumulation-order noise amplified through rounding flips
+    assert err_ref < 3e-2, err_ref          # bf16 operands through 10 chained layers
+
+
+def test_tc_forward_rays_mode_and_stash():
+    """fused sampling + encoding (dense coarse grid and a compacted fine list with a device-side count)."""
+    ops, p, tensors, ps, tcw = setup(8, (4,))
+    g = torch.Generator().manual_seed(11)
+    B, S = 37, 16
+    ro = torch.randn(B, 3, generator=g) * 0.5
+    rd = F.normalize(torch.randn(B, 3, generator=g), dim=-1)
+    jit = torch.rand(B, generator=g) * 0.1
+    bw = [0.0, 0.1, 0.5, 0.9, 1.0, 1.0, 1.0, 0.7, 0.2, 0.0]
+    smp = ops.make_sampling(1.0, 8.0, S, 10, bw)
+    z = torch.linspace(1.0, 8.0, S).expand(B, -1) + jit[:, None]
+    xyz = (ro[:, None] + rd[:, None] * z[..., None]).reshape(-1, 3)
+    x_enc = orc.sincos_encode(xyz, 10, torch.tensor(bw))
+    dirs = rd[:, None].expand(-1, S, -1).reshape(-1, 3)
+    emu = mlp_forward_bf16emu(p, x_enc, dirs, 8, (4,))
+    d = lambda t: t.to(DEV).contiguous()
+    ro_d, rd_d, jit_d = d(ro), d(rd), d(jit)
+    out = torch.full((B * S, 4), float("nan"), device=DEV)
+    stash = ops.tc_stash(ps, B * S, DEV)
+    ops.mlp_tc_fwd(ps, tcw, ops.make_tc_input_rays(ro_d, rd_d, jit_d, smp, None, B * S, None), out, stash)
+    torch.cuda.synchronize()
+    assert (out.cpu() - emu).abs().max().item() < 3e-3
+    # compacted list: every third sample, count given on the device, capacity larger than the count
+    sel = torch.arange(0, B * S, 3, dtype=torch.int32)
+    n = sel.shape[0]
+    sel_pad = torch.cat([sel, torch.zeros(50, dtype=torch.int32)]).to(DEV)
+    out2 = torch.full((n + 50, 4), float("nan"), device=DEV)
+    ops.mlp_tc_fwd(ps, tcw, ops.make_tc_input_rays(ro_d, rd_d, jit_d, smp, sel_pad, n + 50,
+                                                   torch.tensor([n], dtype=torch.int32, device=DEV)), out2)
+    torch.cuda.synchronize()
+    assert (out2[:n].cpu() - emu[sel.long()]).abs().max().item() < 3e-3
+    assert torch.isnan(out2[n:]).all()       # rows beyond the device-side count are untouched
