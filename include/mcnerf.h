@@ -225,6 +225,16 @@ size_t mcnerf_mlp_tc_stash_bytes(const mcnerf_mlp_params* p, int n_rows);
 int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, const float* bias, const mcnerf_tc_input* in,
                       float* out4, void* stash, void* stream);
 
+/* bytes of scratch the backward pass needs (dY stash + weight-gradient partials) */
+size_t mcnerf_mlp_tc_bwd_workspace(const mcnerf_mlp_params* p, int n_rows);
+/* Backward of mcnerf_mlp_tc_fwd (training forward with `stash`).  wb: transposed weight image from
+ * mcnerf_mlp_tc_pack.  Parameter gradients are accumulated into `g`.  rays mode: accumulates dL/d(rays_o),
+ * dL/d(rays_d) [n_rays,3]; explicit mode: overwrites g_x_enc [n_rows, ld_enc] and g_dirs_rows [n_rows,3]. */
+int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, const float* bias, const mcnerf_tc_input* in,
+                      const float* out4, const float* g_out4, const void* stash, void* workspace,
+                      const mcnerf_mlp_grads* g, float* g_rays_o, float* g_rays_d, float* g_x_enc,
+                      float* g_dirs_rows, void* stream);
+
 /* ------------------------------------------------------------------ tensor-core self test
  * One 128xN tcgen05 tile: D = A B^T (mn_major = 0: A [128,K], B [N,K] bf16, K-major operands) or
  * D = A^T B (mn_major = 1: A [K,128], B [K,N], MN-major operands).  Used by tests/ to pin the UMMA

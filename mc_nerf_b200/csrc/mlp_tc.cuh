@@ -40,16 +40,62 @@ struct Plan {
   Step s[MAX_STEPS];
 };
 
+// ---- backward chain (dgrad) jobs: dX = dY * W, chained from the heads down to the encoding
+enum { BK_MASK_STORE = 0, BK_SIGMA_INJECT = 1, BK_RELOAD_SKIP = 2, BK_ENC_OUT = 3 };
+struct BJob {
+  int a_small;        // 1: A operand is the 128x32 head-gradient tile, 0: the 128x256 dY tile
+  int n_chunks;       // K / KC (K = number of output features of the layer being back-propagated through)
+  int N;              // width of dX (256, or 64 for the encoding part)
+  int accumulate;     // 1: add onto the accumulator left by the previous job
+  int kind;           // epilogue kind
+  uint32_t w_off;     // byte offset in the transposed weight image
+  int mask_slot;      // forward-stash slot whose ">0" pattern gates dX (ReLU backward)
+  int dy_slot;        // dY-stash slot the epilogue writes (-1: none)
+};
+struct BPlan {
+  int n_jobs;
+  int skip_dy_slot;   // dY slot of the skip layer (reloaded for the encoding part), -1 if no skip
+  BJob j[MAX_STEPS];
+};
+
+// ---- weight-gradient jobs: dW = dY^T X over all rows
+struct WJob {
+  int dy_slot;        // dY-stash slot (A operand, M = output features, two halves of 128) ; -1: head tile
+  int x_slot;         // forward-stash slot of X (B operand, N = input features); -1: encoding stash
+  int N;              // input features of this job (256, or 64 for the encoding)
+  int transposed;     // 1: roles swapped (A = X^T, B = head dY tile): computes dW^T (sh.2 / sigma.2)
+  int head_col0;      // transposed jobs: first column of the head tile used as B, and N columns from there
+  int which;          // parameter id: 0..depth-1 trunk, depth sigma.0, depth+1 sh.0, depth+2 sh.2, depth+3 sigma.2
+  int col_off;        // column offset inside the parameter's [out,in] matrix (63 for the h part of a skip layer)
+  int n_valid;        // valid input columns (63 for encoding parts, else 256)
+};
+struct WPlan {
+  int n_jobs;
+  WJob j[MAX_STEPS];
+};
+
 // host-side description of one packed network (built by mcnerf_mlp_tc_pack)
 struct PackLayout {
   int depth;
   uint32_t skip_mask;
   Plan fwd;
+  BPlan bwd;
+  WPlan wg;
   size_t wf_bytes;          // forward weight image
   size_t wb_bytes;          // transposed (dgrad) weight image
   int bias_floats;          // bias block incl. w_sigma2 / b_sigma2
   int sig2_off;             // float offset of w_sigma2[256] (b_sigma2 follows)
-  uint32_t wb_off[MAX_STEPS];   // dgrad image offsets, indexed like fwd steps
+  uint32_t wb_main[MAX_STEPS];  // dgrad image of fwd step s: rows = hidden inputs (256) [or enc inputs for step 0]
+  uint32_t wb_enc[MAX_STEPS];   // skip step: rows = encoding inputs (64)
 };
+
+// stash geometry (per tile; tiles are processed in pairs so the tile count is rounded up to even)
+__host__ __device__ inline size_t stash_tiles(int n_rows) {
+  size_t t = (size_t)(n_rows + TM - 1) / TM;
+  return t + (t & 1);
+}
+constexpr int HEAD_BYTES = TM * 32 * 2;      // 8 KB: head-gradient tile [128 x 32] bf16 (g_sh 0..26, g_sigma at 31)
+
+int build_layout(const mcnerf_mlp_params* p, PackLayout* L);
 
 }  // namespace mlptc

@@ -1,0 +1,404 @@
+// bf16 tcgen05 NeRF MLP, backward chain (data gradients): ONE persistent kernel that walks a 128-row tile from
+// d(out4) back to the ray, entirely on-chip:
+//   SH/sigmoid head backward (CUDA cores) -> dgrad GEMMs through sh.2, sh.0 + sigma.0, trunk layers D-1..1,
+//   layer 0 + the skip layer's encoding part (tcgen05, transposed weight images streamed by bulk copies)
+//   -> sin/cos encoding backward -> per-ray (dL/do, dL/dd) with a segmented warp reduction + atomics.
+// ReLU masks come from the forward activation stash; every layer's dY tile is written (bf16, UMMA tile image)
+// to the dY stash that the weight-gradient kernel (mlp_tc_wgrad.cu) consumes.
+// ref: autograd of model/net_block.py:67-78, model/net_utils.py:154-169, model/net_block.py:20-35.
+#include "mlp_tc.cuh"
+
+namespace mlptc {
+
+struct BwdArgs {
+  BPlan plan;
+  const uint8_t* wb;        // transposed weight images
+  const float* bias;        // bias block (w_sigma2 at sig2_off)
+  int sig2_off;
+  int n_slots;              // D + 2
+  const uint8_t* stash;     // forward activations [tile][n_slots][ACT_BYTES]
+  const float* stash_sh;    // [row][SH_LD]
+  uint8_t* dy;              // [tile][n_slots][ACT_BYTES]
+  uint8_t* dy_head;         // [tile][HEAD_BYTES]
+  const float* g_out4;      // [rows,4]
+  const float* out4;        // [rows,4]
+  const float *rays_o, *rays_d, *jitter;
+  mcnerf_sampling smp;
+  const int32_t* sel_idx;
+  int n_rows;
+  const int32_t* n_rows_dev;
+  const float* x_enc;       // explicit mode (module API)
+  int ld_enc;
+  const float* dirs_rows;
+  float *g_rays_o, *g_rays_d;     // rays mode: accumulated [n_rays,3]
+  float* g_x_enc;                 // explicit mode: [rows, ld_enc] overwritten
+  float* g_dirs_rows;             // explicit mode: [rows,3] overwritten
+};
+
+struct __align__(16) BwdBars {
+  uint64_t w_full[NSTAGE], w_empty[NSTAGE], a_ready[2], acc_full[2];
+  uint32_t tmem_base;
+};
+constexpr int SMEM_BWD = 2 * ACT_BYTES + 2 * HEAD_BYTES + NSTAGE * STAGE_BYTES + 256;
+
+__constant__ float bC0 = 0.28209479177387814f;
+__constant__ float bC1 = 0.4886025119029199f;
+__constant__ float bC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                             -1.0925484305920792f, 0.5462742152960396f};
+
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// sum `v` over lanes that share `key` (keys sorted within the warp); true on the first lane of each run
+template <int NV>
+__device__ __forceinline__ bool seg_reduce(int key, float (&v)[NV], int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int k2 = __shfl_down_sync(0xffffffffu, key, o);
+    bool take = (lane + o < 32) && (k2 == key);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float x2 = __shfl_down_sync(0xffffffffu, v[i], o);
+      if (take) v[i] += x2;
+    }
+  }
+  int kp = __shfl_up_sync(0xffffffffu, key, 1);
+  return lane == 0 || kp != key;
+}
+
+__device__ __forceinline__ uint32_t relu_gate2(uint32_t act_pair, float lo, float hi) {
+  // act_pair: two bf16 forward activations (post-ReLU, so >= +0): gate = activation != 0
+  float a = (act_pair & 0x00007FFFu) ? lo : 0.f;
+  float b = (act_pair & 0x7FFF0000u) ? hi : 0.f;
+  return tc::pack_bf16(a, b);
+}
+
+__global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ BwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* bufX = smem;                                    // [2][ACT_BYTES]  dY tile (A operand)
+  uint8_t* small = smem + 2 * ACT_BYTES;                   // [2][HEAD_BYTES] head-gradient tile
+  uint8_t* wst = small + 2 * HEAD_BYTES;                   // [NSTAGE][STAGE_BYTES]
+  BwdBars* bars = reinterpret_cast<BwdBars*>(wst + NSTAGE * STAGE_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
+  const int n_tiles = (rows + TM - 1) / TM;
+  const int n_pairs = (n_tiles + 1) / 2;
+  const int n_jobs = a.plan.n_jobs;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 128); tc::mbar_init(&bars->acc_full[i], 1); }
+    tc::mbar_init_fence();
+  }
+  if (warp == 9) tc::tmem_alloc(&bars->tmem_base, 512);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t par = 0;
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (int jn = 0; jn < n_jobs; ++jn) {
+          const BJob& jb = a.plan.j[jn];
+          const uint32_t bytes = (uint32_t)jb.N * KC * 2;
+          for (int t = 0; t < 2; ++t)
+            for (int c = 0; c < jb.n_chunks; ++c) {
+              tc::mbar_wait(&bars->w_empty[stage], par ^ 1);
+              tc::mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
+              tc::bulk_g2s(wst + stage * STAGE_BYTES, a.wb + jb.w_off + (size_t)c * bytes, bytes, &bars->w_full[stage]);
+              if (++stage == NSTAGE) { stage = 0; par ^= 1; }
+            }
+        }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t par = 0, apar[2] = {0, 0};
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (int jn = 0; jn < n_jobs; ++jn) {
+          const BJob& jb = a.plan.j[jn];
+          const uint32_t idesc = tc::umma_idesc_bf16(TM, jb.N);
+          for (int t = 0; t < 2; ++t) {
+            tc::mbar_wait(&bars->a_ready[t], apar[t]);
+            apar[t] ^= 1;
+            tc::tcgen05_fence_after();
+            const uint32_t a_tile = jb.a_small ? tc::smem_u32(small + t * HEAD_BYTES) : tc::smem_u32(bufX + t * ACT_BYTES);
+            for (int c = 0; c < jb.n_chunks; ++c) {
+              tc::mbar_wait(&bars->w_full[stage], par);
+              tc::tcgen05_fence_after();
+              const uint32_t a_base = a_tile + c * (KC / 8) * PLANE;
+              const uint32_t b_base = tc::smem_u32(wst + stage * STAGE_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < KC / 16; ++kk) {
+                uint64_t da = tc::umma_desc(a_base + kk * 2 * PLANE, PLANE, 128);
+                uint64_t db = tc::umma_desc(b_base + kk * 2 * jb.N * 16, jb.N * 16, 128);
+                tc::umma_bf16(tmem + t * 256, da, db, idesc, (jb.accumulate | c | kk) != 0);
+              }
+              tc::umma_commit(&bars->w_empty[stage]);
+              if (++stage == NSTAGE) { stage = 0; par ^= 1; }
+            }
+            tc::umma_commit(&bars->acc_full[t]);
+          }
+        }
+    }
+  } else {
+    const int t = warp >> 2;
+    const int q = tid - t * 128;
+    const uint32_t bufX_t = tc::smem_u32(bufX + t * ACT_BYTES), small_t = tc::smem_u32(small + t * HEAD_BYTES);
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * 256;
+    const float* w2 = a.bias + a.sig2_off;
+    uint32_t par = 0;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const int tile = 2 * pair + t;
+      const int row_g = tile * TM + q;
+      const bool valid = row_g < rows;
+      const bool tile_ok = tile < n_tiles;
+      const uint8_t* st_tile = a.stash + (size_t)tile * a.n_slots * ACT_BYTES;
+      uint8_t* dy_tile = a.dy + (size_t)tile * a.n_slots * ACT_BYTES;
+      int ray = -1 - lane;
+      float z = 0.f;
+      if (valid && !a.x_enc) {
+        int flat = a.sel_idx ? a.sel_idx[row_g] : row_g;
+        ray = flat / a.smp.S;
+        z = linspace_f(a.smp.near_, a.smp.far_, a.smp.S, flat - ray * a.smp.S) + (a.jitter ? a.jitter[ray] : 0.f);
+      }
+      // ---------------- head backward: eval_sh + sigmoid, builds the [128 x 32] head-gradient tile
+      float g_sigma = 0.f;
+      {
+        float hv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) hv[i] = 0.f;
+        float gd[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          const float4 g = reinterpret_cast<const float4*>(a.g_out4)[row_g];
+          const float4 o = reinterpret_cast<const float4*>(a.out4)[row_g];
+          const float* dp = a.x_enc ? a.dirs_rows + (size_t)row_g * 3 : a.rays_d + 3 * (size_t)ray;
+          const float x = dp[0], y = dp[1], zz = dp[2];
+          const float Y[9] = {bC0, -bC1 * y, bC1 * zz, -bC1 * x, bC2[0] * x * y, bC2[1] * y * zz,
+                              bC2[2] * (2.f * zz * zz - x * x - y * y), bC2[3] * x * zz, bC2[4] * (x * x - y * y)};
+          const float gc[3] = {g.y * o.y * (1.f - o.y), g.z * o.z * (1.f - o.z), g.w * o.w * (1.f - o.w)};
+          const float4* shp = reinterpret_cast<const float4*>(a.stash_sh + (size_t)row_g * SH_LD);
+          float sh[28];
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            float4 v = shp[i];
+            sh[4 * i] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
+          }
+          float comb[9];
+#pragma unroll
+          for (int b = 0; b < 9; ++b) comb[b] = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+            for (int b = 0; b < 9; ++b) {
+              hv[9 * ch + b] = gc[ch] * Y[b];
+              comb[b] += gc[ch] * sh[9 * ch + b];
+            }
+          gd[0] = -bC1 * comb[3] + bC2[0] * y * comb[4] - 2.f * bC2[2] * x * comb[6] + bC2[3] * zz * comb[7] +
+                  2.f * bC2[4] * x * comb[8];
+          gd[1] = -bC1 * comb[1] + bC2[0] * x * comb[4] + bC2[1] * zz * comb[5] - 2.f * bC2[2] * y * comb[6] -
+                  2.f * bC2[4] * y * comb[8];
+          gd[2] = bC1 * comb[2] + bC2[1] * y * comb[5] + 4.f * bC2[2] * zz * comb[6] + bC2[3] * x * comb[7];
+          g_sigma = g.x;
+          hv[31] = g_sigma;
+        }
+#pragma unroll
+        for (int kg = 0; kg < 4; ++kg) {
+          uint4 v = make_uint4(tc::pack_bf16(hv[kg * 8], hv[kg * 8 + 1]), tc::pack_bf16(hv[kg * 8 + 2], hv[kg * 8 + 3]),
+                               tc::pack_bf16(hv[kg * 8 + 4], hv[kg * 8 + 5]), tc::pack_bf16(hv[kg * 8 + 6], hv[kg * 8 + 7]));
+          sts_v4(small_t + kg * PLANE + q * 16, v);
+          if (tile_ok) *reinterpret_cast<uint4*>(a.dy_head + (size_t)tile * HEAD_BYTES + kg * PLANE + q * 16) = v;
+        }
+        if (a.x_enc) {
+          if (valid) { a.g_dirs_rows[3 * (size_t)row_g] = gd[0]; a.g_dirs_rows[3 * (size_t)row_g + 1] = gd[1]; a.g_dirs_rows[3 * (size_t)row_g + 2] = gd[2]; }
+        } else {
+          bool head = seg_reduce<3>(ray, gd, lane);
+          if (valid && head) { atomicAdd(a.g_rays_d + 3 * ray, gd[0]); atomicAdd(a.g_rays_d + 3 * ray + 1, gd[1]); atomicAdd(a.g_rays_d + 3 * ray + 2, gd[2]); }
+        }
+      }
+      tc::fence_proxy_async();
+      tc::tcgen05_fence_before();
+      tc::mbar_arrive(&bars->a_ready[t]);
+
+      for (int jn = 0; jn < n_jobs; ++jn) {
+        const BJob& jb = a.plan.j[jn];
+        tc::mbar_wait(&bars->acc_full[t], par);
+        par ^= 1;
+        tc::tcgen05_fence_after();
+        if (jb.kind == BK_MASK_STORE) {
+          const uint8_t* mk = st_tile + (size_t)jb.mask_slot * ACT_BYTES + q * 16;
+          uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES + q * 16;
+#pragma unroll 1
+          for (int cg = 0; cg < WID / 32; ++cg) {
+            uint4 m[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              m[j] = tile_ok ? *reinterpret_cast<const uint4*>(mk + (cg * 4 + j) * PLANE) : make_uint4(0, 0, 0, 0);
+            uint32_t v[32];
+            tc::tmem_ld32(taddr + cg * 32, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = relu_gate2(m[j].x, __uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+              o.y = relu_gate2(m[j].y, __uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+              o.z = relu_gate2(m[j].z, __uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+              o.w = relu_gate2(m[j].w, __uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+              sts_v4(bufX_t + (cg * 4 + j) * PLANE + q * 16, o);
+              if (tile_ok) *reinterpret_cast<uint4*>(dyo + (cg * 4 + j) * PLANE) = o;
+            }
+          }
+        } else if (jb.kind == BK_SIGMA_INJECT) {
+          // d relu(sigma.0) pre-activation = g_sigma * w_sigma2 gated by the stashed activation; the accumulator
+          // (gradient that arrived through sh.0) stays in TMEM and the next job accumulates onto it.
+          const uint8_t* mk = st_tile + (size_t)jb.mask_slot * ACT_BYTES + q * 16;
+          uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES + q * 16;
+#pragma unroll 4
+          for (int kg = 0; kg < WID / 8; ++kg) {
+            const uint4 m = tile_ok ? *reinterpret_cast<const uint4*>(mk + kg * PLANE) : make_uint4(0, 0, 0, 0);
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(w2 + kg * 8));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(w2 + kg * 8 + 4));
+            uint4 o;
+            o.x = relu_gate2(m.x, g_sigma * s0.x, g_sigma * s0.y);
+            o.y = relu_gate2(m.y, g_sigma * s0.z, g_sigma * s0.w);
+            o.z = relu_gate2(m.z, g_sigma * s1.x, g_sigma * s1.y);
+            o.w = relu_gate2(m.w, g_sigma * s1.z, g_sigma * s1.w);
+            sts_v4(bufX_t + kg * PLANE + q * 16, o);
+            if (tile_ok) *reinterpret_cast<uint4*>(dyo + kg * PLANE) = o;
+          }
+        } else if (jb.kind == BK_RELOAD_SKIP) {
+          // bring the skip layer's dY tile (this thread's own row, written a few jobs ago) back as the A operand
+          const uint8_t* src = dy_tile + (size_t)a.plan.skip_dy_slot * ACT_BYTES + q * 16;
+#pragma unroll 4
+          for (int kg = 0; kg < WID / 8; ++kg) {
+            const uint4 v = tile_ok ? *reinterpret_cast<const uint4*>(src + kg * PLANE) : make_uint4(0, 0, 0, 0);
+            sts_v4(bufX_t + kg * PLANE + q * 16, v);
+          }
+        } else {   // BK_ENC_OUT
+          float d[64];
+          {
+            uint32_t v[32];
+            tc::tmem_ld32(taddr, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]);
+            tc::tmem_ld32(taddr + 32, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) d[32 + i] = __uint_as_float(v[i]);
+          }
+          if (a.x_enc) {
+            if (valid) {
+              float* dst = a.g_x_enc + (size_t)row_g * a.ld_enc;
+#pragma unroll
+              for (int i = 0; i < 63; ++i) dst[i] = d[i];
+            }
+          } else {
+            float gv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const float xc = a.rays_o[3 * ray + c] + a.rays_d[3 * ray + c] * z;
+                float sn, cs;
+                sincosf(xc, &sn, &cs);
+                float g = d[c], f = 1.f;
+#pragma unroll
+                for (int kf = 0; kf < 10; ++kf) {
+                  g += a.smp.band_w[kf] * f * (d[3 + c * 20 + kf] * cs - d[3 + c * 20 + 10 + kf] * sn);
+                  const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
+                  sn = s2; cs = c2; f *= 2.f;
+                }
+                gv[c] = g;
+                gv[3 + c] = g * z;
+              }
+            }
+            bool head = seg_reduce<6>(ray, gv, lane);
+            if (valid && head) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                atomicAdd(a.g_rays_o + 3 * ray + c, gv[c]);
+                atomicAdd(a.g_rays_d + 3 * ray + c, gv[3 + c]);
+              }
+            }
+          }
+        }
+        if (jn + 1 < n_jobs) {
+          tc::fence_proxy_async();
+          tc::tcgen05_fence_before();
+          tc::mbar_arrive(&bars->a_ready[t]);
+        }
+      }
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 9) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace mlptc
+
+using namespace mlptc;
+
+size_t mlp_tc_wgrad_scratch_bytes(int n_ctas);
+int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const uint8_t* stash, const uint8_t* stash_enc,
+                        const uint8_t* dy, const uint8_t* dy_head, float* scratch, int n_rows,
+                        const int32_t* n_rows_dev, const mcnerf_mlp_grads* g, cudaStream_t st);
+constexpr int WG_MAX_CTAS = 160;
+
+extern "C" size_t mcnerf_mlp_tc_bwd_workspace(const mcnerf_mlp_params* p, int n_rows) {
+  if (!mcnerf_mlp_tc_supported(p) || n_rows <= 0) return 0;
+  return stash_tiles(n_rows) * ((size_t)(p->depth + 2) * ACT_BYTES + HEAD_BYTES) + mlp_tc_wgrad_scratch_bytes(WG_MAX_CTAS);
+}
+
+extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, const float* bias,
+                                 const mcnerf_tc_input* in, const float* out4, const float* g_out4, const void* stash,
+                                 void* workspace, const mcnerf_mlp_grads* g, float* g_rays_o, float* g_rays_d,
+                                 float* g_x_enc, float* g_dirs_rows, void* stream) {
+  PackLayout L;
+  if (int e = build_layout(p, &L)) return e;
+  MC_ARG(in && in->n_rows >= 0);
+  if (in->n_rows == 0) return 0;
+  MC_ARG(wb && bias && out4 && g_out4 && stash && workspace && g);
+  const bool explicit_mode = in->x_enc != nullptr;
+  MC_ARG(explicit_mode ? (in->dirs_rows && g_x_enc && g_dirs_rows && in->ld_enc >= 63)
+                       : (in->rays_o && in->rays_d && g_rays_o && g_rays_d && in->smp.n_freqs == 10));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t tiles = stash_tiles(in->n_rows);
+  const int n_slots = p->depth + 2;
+  BwdArgs a;
+  a.plan = L.bwd;
+  a.wb = (const uint8_t*)wb;
+  a.bias = bias;
+  a.sig2_off = L.sig2_off;
+  a.n_slots = n_slots;
+  a.stash = (const uint8_t*)stash;
+  const uint8_t* stash_enc = a.stash + tiles * (size_t)n_slots * ACT_BYTES;
+  a.stash_sh = (const float*)(stash_enc + tiles * ENC_BYTES);
+  a.dy = (uint8_t*)workspace;
+  a.dy_head = a.dy + tiles * (size_t)n_slots * ACT_BYTES;
+  a.g_out4 = g_out4; a.out4 = out4;
+  a.rays_o = in->rays_o; a.rays_d = in->rays_d; a.jitter = in->jitter; a.smp = in->smp;
+  a.sel_idx = in->sample_idx; a.n_rows = in->n_rows; a.n_rows_dev = in->n_rows_dev;
+  a.x_enc = in->x_enc; a.ld_enc = in->ld_enc; a.dirs_rows = in->dirs_rows;
+  a.g_rays_o = g_rays_o; a.g_rays_d = g_rays_d; a.g_x_enc = g_x_enc; a.g_dirs_rows = g_dirs_rows;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
+    attr_set = true;
+  }
+  const int n_tiles = (in->n_rows + TM - 1) / TM;
+  const int n_pairs = (n_tiles + 1) / 2;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  mlp_tc_bwd_k<<<n_pairs < sms ? n_pairs : sms, 320, SMEM_BWD, st>>>(a);
+  MC_LAUNCHED();
+  // weight gradients (tcgen05, reduction over all rows) and bias gradients (column sums of the dY stash)
+  MC_ARG(sms <= WG_MAX_CTAS);
+  float* scratch = (float*)(a.dy_head + tiles * HEAD_BYTES);
+  return mlp_tc_wgrad_launch(p, L, a.stash, stash_enc, a.dy, a.dy_head, scratch, in->n_rows, in->n_rows_dev, g, st);
+}

@@ -47,34 +47,81 @@ int build_layout(const mcnerf_mlp_params* p, PackLayout* L) {
   MC_ARG(p && p->width == WID && p->in_ch == 63 && p->sh_dim == 27 && p->depth >= 2 && p->depth <= 12);
   int n_skip = __builtin_popcount(p->skip_mask);
   MC_ARG(n_skip <= 1 && (p->skip_mask & 1u) == 0 && (p->skip_mask >> p->depth) == 0);
-  L->depth = p->depth;
+  const int D = p->depth;
+  L->depth = D;
   L->skip_mask = p->skip_mask;
   Plan& P = L->fwd;
   uint32_t off = 0, boff = 0;
-  int ns = 0;
-  int bias = 0;
+  int ns = 0, bias = 0;
   auto add = [&](int a_src, int K, int N, int epi, int slot) {
     Step& s = P.s[ns];
     s.a_src = a_src; s.n_chunks = K / KC; s.N = N; s.epi = epi; s.w_off = off; s.bias_off = bias; s.stash_slot = slot;
-    L->wb_off[ns] = boff;
     off += (uint32_t)N * K * 2;
-    boff += (uint32_t)N * K * 2;
+    // transposed images: rows = inputs, reduction = outputs (N).  Encoding inputs get their own 64-row image.
+    L->wb_enc[ns] = L->wb_main[ns] = 0;
+    if (a_src == A_ENC) { L->wb_main[ns] = boff; boff += (uint32_t)ENCW * N * 2; }
+    else if (a_src == A_ENC_ACT) {
+      L->wb_enc[ns] = boff; boff += (uint32_t)ENCW * N * 2;
+      L->wb_main[ns] = boff; boff += (uint32_t)WID * N * 2;
+    } else { L->wb_main[ns] = boff; boff += (uint32_t)WID * N * 2; }
     bias += 256;
     ++ns;
   };
-  for (int i = 0; i < p->depth; ++i) {
+  int skip_layer = -1;
+  for (int i = 0; i < D; ++i) {
     if (i == 0) add(A_ENC, ENCW, WID, EPI_RELU, i);
-    else if (p->skip_mask >> i & 1u) add(A_ENC_ACT, ENCW + WID, WID, EPI_RELU, i);
+    else if (p->skip_mask >> i & 1u) { add(A_ENC_ACT, ENCW + WID, WID, EPI_RELU, i); skip_layer = i; }
     else add(A_ACT, WID, WID, EPI_RELU, i);
   }
-  add(A_ACT, WID, WID, EPI_SIGMA, p->depth);         // sigma.0 (sigma.2 is a dot product in its epilogue)
-  add(A_ACT, WID, WID, EPI_RELU, p->depth + 1);      // sh.0
-  add(A_ACT, WID, 32, EPI_OUT, -1);                  // sh.2 (27 -> 32 columns) + eval_sh + sigmoid
+  add(A_ACT, WID, WID, EPI_SIGMA, D);           // sigma.0 (sigma.2 is a dot product in its epilogue)
+  add(A_ACT, WID, WID, EPI_RELU, D + 1);        // sh.0
+  add(A_ACT, WID, 32, EPI_OUT, -1);             // sh.2 (27 -> 32 columns) + eval_sh + sigmoid
   P.n_steps = ns;
   L->wf_bytes = off;
   L->wb_bytes = boff;
   L->sig2_off = bias;
   L->bias_floats = bias + 256 + 8;
+
+  // backward chain.  Forward-stash slots: l -> output of trunk layer l (h_{l+1}), D -> relu(sigma.0), D+1 -> relu(sh.0).
+  // dY-stash slots:  l -> grad wrt pre-activation of trunk layer l, D -> sigma.0, D+1 -> sh.0.
+  BPlan& B = L->bwd;
+  int nb = 0;
+  auto badd = [&](int a_small, int K, int N, int acc, int kind, uint32_t w_off, int mask_slot, int dy_slot) {
+    BJob& j = B.j[nb++];
+    j.a_small = a_small; j.n_chunks = K / KC; j.N = N; j.accumulate = acc; j.kind = kind; j.w_off = w_off;
+    j.mask_slot = mask_slot; j.dy_slot = dy_slot;
+  };
+  badd(1, 32, WID, 0, BK_MASK_STORE, L->wb_main[D + 2], D + 1, D + 1);     // through sh.2 -> d relu(sh.0) pre-act
+  badd(0, WID, WID, 0, BK_SIGMA_INJECT, L->wb_main[D + 1], D, D);          // through sh.0 (acc kept) ; inject sigma
+  badd(0, WID, WID, 1, BK_MASK_STORE, L->wb_main[D], D - 1, D - 1);        // + through sigma.0 -> dY of layer D-1
+  for (int l = D - 1; l >= 1; --l) badd(0, WID, WID, 0, BK_MASK_STORE, L->wb_main[l], l - 1, l - 1);
+  if (skip_layer >= 0) {
+    badd(0, WID, ENCW, 0, BK_RELOAD_SKIP, L->wb_main[0], -1, -1);          // layer 0 -> d enc (partial)
+    badd(0, WID, ENCW, 1, BK_ENC_OUT, L->wb_enc[skip_layer], -1, -1);      // + skip layer's encoding part
+  } else {
+    badd(0, WID, ENCW, 0, BK_ENC_OUT, L->wb_main[0], -1, -1);
+  }
+  B.n_jobs = nb;
+  B.skip_dy_slot = skip_layer;
+
+  // weight-gradient jobs
+  WPlan& Wp = L->wg;
+  int nw = 0;
+  auto wadd = [&](int dy, int x, int N, int tr, int hc, int which, int col_off, int n_valid) {
+    WJob& j = Wp.j[nw++];
+    j.dy_slot = dy; j.x_slot = x; j.N = N; j.transposed = tr; j.head_col0 = hc; j.which = which; j.col_off = col_off;
+    j.n_valid = n_valid;
+  };
+  for (int l = 0; l < D; ++l) {
+    if (l == 0) wadd(0, -1, ENCW, 0, 0, 0, 0, 63);
+    else if (l == skip_layer) { wadd(l, -1, ENCW, 0, 0, l, 0, 63); wadd(l, l - 1, WID, 0, 0, l, 63, WID); }
+    else wadd(l, l - 1, WID, 0, 0, l, 0, WID);
+  }
+  wadd(D, D - 1, WID, 0, 0, D, 0, WID);          // sigma.0
+  wadd(D + 1, D - 1, WID, 0, 0, D + 1, 0, WID);  // sh.0
+  wadd(-1, D + 1, 32, 1, 0, D + 2, 0, WID);      // sh.2 (transposed: A = relu(sh.0)^T, B = head tile cols 0..31)
+  wadd(-1, D, 16, 1, 16, D + 3, 0, WID);         // sigma.2 (transposed: B = head tile cols 16..31, g_sigma at col 31)
+  Wp.n_jobs = nw;
   return 0;
 }
 
@@ -392,10 +439,16 @@ extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb
     const int K = sp.n_chunks * KC;
     // forward image: rows n = output feature, reduction k = input feature (padded)
     if (int e = pack_matrix(W, ld, 1, sp.N, K, pad, 0, n_out, k_in, f + sp.w_off, st)) return e;
-    // dgrad image: rows n = input feature (padded), reduction k = output feature
+    // dgrad images: rows n = input feature, reduction k = output feature (sp.N, zero beyond n_out)
     if (b) {
-      const int Nb = K, Kb = sp.N;
-      if (int e = pack_matrix(W, 1, ld, Nb, Kb, 0, pad, k_in, n_out, b + L.wb_off[s], st)) return e;
+      if (sp.a_src == A_ENC) {
+        if (int e = pack_matrix(W, 1, ld, ENCW, sp.N, 0, 1, 63, n_out, b + L.wb_main[s], st)) return e;
+      } else if (sp.a_src == A_ENC_ACT) {
+        if (int e = pack_matrix(W, 1, ld, ENCW, sp.N, 0, 1, 63, n_out, b + L.wb_enc[s], st)) return e;
+        if (int e = pack_matrix(W + 63, 1, ld, WID, sp.N, 0, 0, WID, n_out, b + L.wb_main[s], st)) return e;
+      } else {
+        if (int e = pack_matrix(W, 1, ld, WID, sp.N, 0, 0, WID, n_out, b + L.wb_main[s], st)) return e;
+      }
     }
     pack_bias_k<<<1, 256, 0, st>>>(bs, n_out, bias + sp.bias_off, 256);
     MC_LAUNCHED();

@@ -1,0 +1,286 @@
+// bf16 tcgen05 NeRF MLP, weight gradients: dW_l = dY_l^T X_l with the reduction running over ALL sample rows.
+// Both operands are the UMMA tile images the forward / backward-chain kernels left in HBM (activation stash and
+// dY stash); read as MN-major operands (reduction index = row) they need no transposition.
+// Grid = one CTA per SM, partitioned over the (layer, tile-range) jobs in proportion to their HBM traffic:
+//   warp 0   : producer - every lane issues 1 KB bulk copies (one k-group plane of 64 rows each) into a 3-stage ring
+//   warp 1   : MMA issuer - M = 256 output features as two 128-lane halves, N = input features (<= 256), K = 64 rows
+//              per stage; fp32 accumulators fill TMEM (2 x 256 columns)
+//   warps 2-5: epilogue - TMEM -> per-CTA partial in a scratch buffer; a second small kernel sums the partials into
+//              the fp32 parameter gradients (deterministic, no fp32 atomics) and column-sums dY for the biases.
+// HBM-bound by construction (64 KB of operands per 2 x 4 MMAs): see DESIGN.md for the roofline.
+#include "mlp_tc.cuh"
+
+namespace mlptc {
+
+constexpr int WG_ROWS = 64;                          // rows per stage
+constexpr int WG_PLANE = WG_ROWS * 16;               // 1 KB: one k-group plane of a 64-row half tile
+constexpr int WG_STAGE = 2 * 32 * WG_PLANE;          // 64 KB: A region (32 planes) + B region (<= 32 planes)
+constexpr int WG_NSTAGE = 3;
+constexpr int SMEM_WG = WG_NSTAGE * WG_STAGE + 256;
+constexpr int WG_THREADS = 192;
+
+struct WArgs {
+  WPlan plan;
+  int n_slots;
+  const uint8_t *stash, *stash_enc, *dy, *dy_head;
+  int n_rows;
+  const int32_t* n_rows_dev;
+  float* scratch;                    // [gridDim.x][2][128][256] fp32 partials
+  int cta_begin[MAX_STEPS + 1];
+};
+
+struct __align__(16) WBars {
+  uint64_t full[WG_NSTAGE], empty[WG_NSTAGE], acc_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) mlp_tc_wgrad_k(const __grid_constant__ WArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  WBars* bars = reinterpret_cast<WBars*>(smem + WG_NSTAGE * WG_STAGE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
+  const int n_tiles = (rows + TM - 1) / TM;
+  int job = 0;
+  while (job + 1 < a.plan.n_jobs && (int)blockIdx.x >= a.cta_begin[job + 1]) ++job;
+  const WJob& wj = a.plan.j[job];
+  const int part = blockIdx.x - a.cta_begin[job], nparts = a.cta_begin[job + 1] - a.cta_begin[job];
+  const int t_begin = (int)((long long)n_tiles * part / nparts), t_end = (int)((long long)n_tiles * (part + 1) / nparts);
+  const int n_stages_total = (t_end - t_begin) * 2;
+  const int N = wj.N;
+
+  if (tid == 0) {
+    for (int i = 0; i < WG_NSTAGE; ++i) { tc::mbar_init(&bars->full[i], 1); tc::mbar_init(&bars->empty[i], 1); }
+    tc::mbar_init(&bars->acc_full, 1);
+    tc::mbar_init_fence();
+  }
+  if (warp == 1) tc::tmem_alloc(&bars->tmem_base, 512);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  // operand sources.  A: 32 planes (256 features); B: N/8 planes.
+  const size_t tile_stride = (size_t)a.n_slots * ACT_BYTES;
+  const uint8_t *a_base, *b_base;
+  size_t a_stride, b_stride;
+  if (!wj.transposed) {
+    a_base = a.dy + (size_t)wj.dy_slot * ACT_BYTES; a_stride = tile_stride;
+    if (wj.x_slot < 0) { b_base = a.stash_enc; b_stride = ENC_BYTES; }
+    else { b_base = a.stash + (size_t)wj.x_slot * ACT_BYTES; b_stride = tile_stride; }
+  } else {
+    a_base = a.stash + (size_t)wj.x_slot * ACT_BYTES; a_stride = tile_stride;
+    b_base = a.dy_head + (size_t)(wj.head_col0 / 8) * PLANE; b_stride = HEAD_BYTES;
+  }
+  const int nb_planes = N / 8;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t par = 0;
+    for (int i = 0; i < n_stages_total; ++i) {
+      const int tile = t_begin + (i >> 1), half = i & 1;
+      if (lane == 0) {
+        tc::mbar_wait(&bars->empty[stage], par ^ 1);
+        tc::mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)(32 + nb_planes) * WG_PLANE);
+      }
+      __syncwarp();
+      uint8_t* sdst = smem + stage * WG_STAGE;
+      tc::bulk_g2s(sdst + lane * WG_PLANE, a_base + (size_t)tile * a_stride + (size_t)lane * PLANE + half * WG_PLANE,
+                   WG_PLANE, &bars->full[stage]);
+      if (lane < nb_planes)
+        tc::bulk_g2s(sdst + 32 * WG_PLANE + lane * WG_PLANE,
+                     b_base + (size_t)tile * b_stride + (size_t)lane * PLANE + half * WG_PLANE, WG_PLANE,
+                     &bars->full[stage]);
+      if (++stage == WG_NSTAGE) { stage = 0; par ^= 1; }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_stages_total > 0) {
+      const uint32_t idesc = tc::umma_idesc_bf16(128, N, 1, 1);
+      int stage = 0;
+      uint32_t par = 0;
+      for (int i = 0; i < n_stages_total; ++i) {
+        tc::mbar_wait(&bars->full[stage], par);
+        tc::tcgen05_fence_after();
+        const uint32_t sA = tc::smem_u32(smem + stage * WG_STAGE), sB = sA + 32 * WG_PLANE;
+#pragma unroll
+        for (int k16 = 0; k16 < WG_ROWS / 16; ++k16) {
+          const uint64_t db = tc::umma_desc(sB + k16 * 256, 128, WG_PLANE);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t da = tc::umma_desc(sA + h * 16 * WG_PLANE + k16 * 256, 128, WG_PLANE);
+            tc::umma_bf16(tmem + h * 256, da, db, idesc, (i | k16) != 0);
+          }
+        }
+        tc::umma_commit(&bars->empty[stage]);
+        if (++stage == WG_NSTAGE) { stage = 0; par ^= 1; }
+      }
+      tc::umma_commit(&bars->acc_full);
+    }
+  } else {
+    // epilogue: lane quarter (warp % 4), both halves
+    float* out = a.scratch + (size_t)blockIdx.x * 2 * 128 * 256;
+    const int m = (warp & 3) * 32 + lane;
+    if (n_stages_total > 0) {
+      tc::mbar_wait(&bars->acc_full, 0);
+      tc::tcgen05_fence_after();
+    }
+    for (int h = 0; h < 2; ++h) {
+      float* row = out + ((size_t)h * 128 + m) * 256;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        if (n_stages_total > 0) {
+          tc::tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + h * 256 + c0, v);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        // N is a multiple of 16: the last block of a 16-wide job only owns 16 valid columns
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (c0 + 4 * i < N)
+            *reinterpret_cast<float4*>(row + c0 + 4 * i) = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                       __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+      }
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+// Sum the per-CTA partials of every job into the parameter gradients (+=), mapping the padded / transposed
+// accumulator coordinates back to the reference's [out,in] layout.
+struct RArgs {
+  WPlan plan;
+  const float* scratch;
+  int cta_begin[MAX_STEPS + 1];
+  float* dst[MAX_STEPS];
+  int ld[MAX_STEPS];
+};
+
+__global__ void __launch_bounds__(256) wgrad_reduce_k(const __grid_constant__ RArgs a) {
+  const int job = blockIdx.y;
+  const WJob& wj = a.plan.j[job];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // (m, n) of the 256 x N accumulator
+  const int N = wj.N;
+  if (idx >= 256 * N) return;
+  const int m = idx / N, n = idx - m * N;
+  float s = 0.f;
+  for (int p = a.cta_begin[job]; p < a.cta_begin[job + 1]; ++p)
+    s += a.scratch[((size_t)p * 2 + (m >> 7)) * 128 * 256 + (size_t)(m & 127) * 256 + n];
+  if (!wj.transposed) {
+    if (n < wj.n_valid) a.dst[job][(size_t)m * a.ld[job] + wj.col_off + n] += s;     // m = out feature, n = in feature
+  } else if (wj.N == 16) {
+    if (n == 15) a.dst[job][m] += s;                                                 // head column 31 = g_sigma
+  } else {
+    if (n < 27) a.dst[job][(size_t)n * a.ld[job] + m] += s;                          // m = in feature, n = out feature
+  }
+}
+
+// bias gradients: column sums of a dY-stash slot (or of the head tile) over all tiles.
+__global__ void __launch_bounds__(128) dy_colsum_k(const uint8_t* __restrict__ base, size_t tile_stride, int n_rows,
+                                                   const int32_t* __restrict__ n_rows_dev, float* __restrict__ db,
+                                                   int col0, int n_cols_valid) {
+  const int rows = n_rows_dev ? min(*n_rows_dev, n_rows) : n_rows;
+  const int n_tiles = (rows + TM - 1) / TM;
+  const int p = blockIdx.x;     // k-group plane: columns p*8 .. p*8+7
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
+    const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)tile * tile_stride + (size_t)p * PLANE + threadIdx.x * 16);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] += __uint_as_float(w[i] << 16);
+      acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  __shared__ float sm[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[i][wid] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const float s = sm[threadIdx.x][0] + sm[threadIdx.x][1] + sm[threadIdx.x][2] + sm[threadIdx.x][3];
+    const int col = p * 8 + threadIdx.x - col0;
+    if (col >= 0 && col < n_cols_valid) atomicAdd(db + col, s);
+  }
+}
+
+}  // namespace mlptc
+
+using namespace mlptc;
+
+size_t mlp_tc_wgrad_scratch_bytes(int n_ctas) { return (size_t)n_ctas * 2 * 128 * 256 * sizeof(float); }
+
+int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const uint8_t* stash, const uint8_t* stash_enc,
+                        const uint8_t* dy, const uint8_t* dy_head, float* scratch, int n_rows,
+                        const int32_t* n_rows_dev, const mcnerf_mlp_grads* g, cudaStream_t st) {
+  const int D = p->depth;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  WArgs a;
+  a.plan = L.wg;
+  a.n_slots = D + 2;
+  a.stash = stash; a.stash_enc = stash_enc; a.dy = dy; a.dy_head = dy_head;
+  a.n_rows = n_rows; a.n_rows_dev = n_rows_dev;
+  a.scratch = scratch;
+  // CTAs per job in proportion to the bytes each stage streams (A: 32 planes, B: N/8 planes)
+  const int nj = L.wg.n_jobs;
+  double tot = 0;
+  for (int j = 0; j < nj; ++j) tot += 32 + L.wg.j[j].N / 8;
+  int used = 0, cnt[MAX_STEPS];
+  for (int j = 0; j < nj; ++j) {
+    cnt[j] = (int)((32 + L.wg.j[j].N / 8) / tot * sms);
+    if (cnt[j] < 1) cnt[j] = 1;
+    used += cnt[j];
+  }
+  for (int j = 0; used < sms; j = (j + 1) % nj) if (L.wg.j[j].N == WID) { ++cnt[j]; ++used; }
+  while (used > sms) for (int j = 0; j < nj && used > sms; ++j) if (cnt[j] > 1) { --cnt[j]; --used; }
+  a.cta_begin[0] = 0;
+  for (int j = 0; j < nj; ++j) a.cta_begin[j + 1] = a.cta_begin[j] + cnt[j];
+  static bool attr_set = false;
+  if (!attr_set) {
+    MC_CUDA(cudaFuncSetAttribute(mlp_tc_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG));
+    attr_set = true;
+  }
+  mlp_tc_wgrad_k<<<used, WG_THREADS, SMEM_WG, st>>>(a);
+  MC_LAUNCHED();
+
+  RArgs r;
+  r.plan = L.wg;
+  r.scratch = scratch;
+  for (int j = 0; j <= nj; ++j) r.cta_begin[j] = a.cta_begin[j];
+  auto wptr = [&](int which, int* ld) -> float* {
+    if (which < D) {
+      *ld = which == 0 ? 63 : ((p->skip_mask >> which & 1u) ? 63 + WID : WID);
+      return g->W[which];
+    }
+    *ld = WID;
+    if (which == D) return g->W_sigma0;
+    if (which == D + 1) return g->W_sh0;
+    if (which == D + 2) return g->W_sh2;
+    return g->W_sigma2;
+  };
+  for (int j = 0; j < nj; ++j) r.dst[j] = wptr(L.wg.j[j].which, &r.ld[j]);
+  wgrad_reduce_k<<<dim3(256, nj), 256, 0, st>>>(r);
+  MC_LAUNCHED();
+
+  // biases
+  const size_t tile_stride = (size_t)(D + 2) * ACT_BYTES;
+  auto colsum = [&](const uint8_t* base, size_t stride, int planes, float* db, int col0, int n_valid) -> int {
+    dy_colsum_k<<<dim3(planes, 64), 128, 0, st>>>(base, stride, n_rows, n_rows_dev, db, col0, n_valid);
+    MC_LAUNCHED();
+    return 0;
+  };
+  for (int l = 0; l < D; ++l)
+    if (int e = colsum(dy + (size_t)l * ACT_BYTES, tile_stride, 32, g->b[l], 0, WID)) return e;
+  if (int e = colsum(dy + (size_t)D * ACT_BYTES, tile_stride, 32, g->b_sigma0, 0, WID)) return e;
+  if (int e = colsum(dy + (size_t)(D + 1) * ACT_BYTES, tile_stride, 32, g->b_sh0, 0, WID)) return e;
+  if (int e = colsum(dy_head, HEAD_BYTES, 4, g->b_sh2, 0, 27)) return e;
+  if (int e = colsum(dy_head, HEAD_BYTES, 4, g->b_sigma2, 31, 1)) return e;
+  return 0;
+}

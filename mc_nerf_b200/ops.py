@@ -399,6 +399,7 @@ def make_tc_input_rays(rays_o, rays_d, jitter, smp, sel_idx, n_rows, n_rows_dev)
     t.n_rows = int(n_rows)
     t.n_rows_dev = n_rows_dev.data_ptr() if n_rows_dev is not None else None
     t.x_enc, t.ld_enc, t.dirs_rows = None, 0, None
+    t._keep = (rays_o, rays_d, jitter, sel_idx, n_rows_dev)      # the struct only holds raw pointers
     return t
 
 
@@ -409,6 +410,7 @@ def make_tc_input_enc(x_enc, dirs):
     t.smp = make_sampling(0.0, 1.0, 2, 10)
     t.n_rows = x_enc.shape[0]
     t.x_enc, t.ld_enc, t.dirs_rows = x_enc.data_ptr(), x_enc.shape[1], dirs.data_ptr()
+    t._keep = (x_enc, dirs)
     return t
 
 
@@ -420,3 +422,15 @@ def tc_stash(ps, n_rows, device):
 def mlp_tc_fwd(ps, tcw, tcin, out4, stash=None):
     lib().call("mcnerf_mlp_tc_fwd", ctypes.byref(ps), _p(tcw.wf, torch.uint8), _p(tcw.bias), ctypes.byref(tcin),
                _p(out4), _p(stash, torch.uint8) if stash is not None else None, _stream())
+
+
+def tc_bwd_workspace(ps, n_rows, device):
+    n = lib().cdll.mcnerf_mlp_tc_bwd_workspace(ctypes.byref(ps), int(n_rows))
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def mlp_tc_bwd(ps, tcw, tcin, out4, g_out4, stash, workspace, grads_struct, g_rays_o=None, g_rays_d=None,
+               g_x_enc=None, g_dirs_rows=None):
+    lib().call("mcnerf_mlp_tc_bwd", ctypes.byref(ps), _p(tcw.wb, torch.uint8), _p(tcw.bias), ctypes.byref(tcin),
+               _p(out4), _p(g_out4), _p(stash, torch.uint8), _p(workspace, torch.uint8), ctypes.byref(grads_struct),
+               _p(g_rays_o), _p(g_rays_d), _p(g_x_enc), _p(g_dirs_rows), _stream())

@@ -34,6 +34,48 @@ def mlp_forward_bf16emu(p, x_enc, dirs, depth, skips):
     return torch.cat([sigma, rgb], -1)
 
 
+class _RoundGrad(torch.autograd.Function):
+    """identity whose backward rounds the gradient to bf16 (the kernels store every dY tile as bf16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return bf(g)
+
+
+class _BfSTE(torch.autograd.Function):
+    """bf16 rounding with a straight-through gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return bf(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def mlp_forward_bf16emu_trainable(p, x_enc, dirs, depth, skips):
+    """same rounding points as the tcgen05 path in forward AND backward: bf16 weights/activations/dY tiles,
+    fp32 accumulation; weight gradients are formed from the bf16 activations and bf16 dY."""
+    rg, q = _RoundGrad.apply, _BfSTE.apply
+    x = q(x_enc)
+    h = x
+    for i in range(depth):
+        if i in skips:
+            h = torch.cat([x, h], -1)
+        h = q(F.relu(rg(F.linear(h, q(p[f"xyz_encoding_{i+1}.0.weight"]), p[f"xyz_encoding_{i+1}.0.bias"]))))
+    s = F.relu(rg(F.linear(h, q(p["sigma.0.weight"]), p["sigma.0.bias"])))
+    sigma = F.linear(s, p["sigma.2.weight"], p["sigma.2.bias"])
+    c = q(F.relu(rg(F.linear(h, q(p["sh.0.weight"]), p["sh.0.bias"]))))
+    sh = rg(F.linear(c, q(p["sh.2.weight"]), p["sh.2.bias"]))
+    rgb = torch.sigmoid(orc.eval_sh_deg2(sh.reshape(-1, 3, 9), dirs))
+    return torch.cat([sigma, rgb], -1)
+
+
 def setup(depth, skips, seed=3):
     from mc_nerf_b200 import ops
     p = orc.init_mlp_params(depth, 256, skips, seed=seed)
@@ -95,3 +137,99 @@ def test_tc_forward_rays_mode_and_stash():
     torch.cuda.synchronize()
     assert (out2[:n].cpu() - emu[sel.long()]).abs().max().item() < 3e-3
     assert torch.isnan(out2[n:]).all()       # rows beyond the device-side count are untouched
+
+
+def rel_err(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("depth,skips,M", [(8, (4,), 1000), (4, (2,), 333), (3, (), 256)])
+def test_tc_backward_explicit_encodings(depth, skips, M):
+    """gradients wrt encodings, view directions and every parameter vs fp32 autograd of the oracle.
+    bf16 operands (activations, dY, weights) with fp32 accumulation: relative Frobenius error per tensor."""
+    ops, p, tensors, ps, tcw = setup(depth, skips)
+    g = torch.Generator().manual_seed(M + 1)
+    xyz = (torch.rand(M, 3, generator=g) - 0.5) * 6
+    x_enc = orc.sincos_encode(xyz, 10)
+    dirs = F.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    gout = torch.randn(M, 4, generator=g)
+    # oracle
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    xr, dr = x_enc.clone().requires_grad_(True), dirs.clone().requires_grad_(True)
+    orc.mlp_forward(pr, xr, dr, depth, skips).backward(gout)
+    # kernels
+    xd, dd = x_enc.to(DEV).contiguous(), dirs.to(DEV).contiguous()
+    tin = ops.make_tc_input_enc(xd, dd)
+    out = torch.empty(M, 4, device=DEV)
+    stash = ops.tc_stash(ps, M, DEV)
+    ops.mlp_tc_fwd(ps, tcw, tin, out, stash)
+    grads = {k: torch.zeros_like(v) for k, v in tensors.items()}
+    gs = ops.fill_mlp_struct(ops.MlpGrads(), grads, depth)
+    ws = ops.tc_bwd_workspace(ps, M, DEV)
+    g_x = torch.zeros(M, 63, device=DEV)
+    g_d = torch.zeros(M, 3, device=DEV)
+    ops.mlp_tc_bwd(ps, tcw, tin, out, gout.to(DEV).contiguous(), stash, ws, gs, g_x_enc=g_x, g_dirs_rows=g_d)
+    torch.cuda.synchronize()
+    # same rounding points emulated (tight) ...
+    pe = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    xe, de = x_enc.clone().requires_grad_(True), dirs.clone().requires_grad_(True)
+    mlp_forward_bf16emu_trainable(pe, xe, de, depth, skips).backward(gout)
+    emu = {"g_x_enc": rel_err(g_x.cpu(), xe.grad), "g_dirs": rel_err(g_d.cpu(), de.grad)}
+    for k in tensors:
+        emu[k] = rel_err(grads[k].cpu(), pe[k].grad)
+    # ... and the plain fp32 oracle (reported: ReLU gates that flip under bf16 rounding dominate)
+    errs = {"g_x_enc": rel_err(g_x.cpu(), xr.grad), "g_dirs": rel_err(g_d.cpu(), dr.grad)}
+    for k in tensors:
+        errs[k] = rel_err(grads[k].cpu(), pr[k].grad)
+    print("vs bf16-emulated:", {k: f"{v:.1e}" for k, v in emu.items()})
+    print("vs fp32 oracle  :", {k: f"{v:.1e}" for k, v in errs.items()})
+    bad = {k: v for k, v in emu.items() if not v < 1.5e-2}
+    assert not bad, bad
+    bad = {k: v for k, v in errs.items() if not v < 0.2}
+    assert not bad, bad
+
+
+def test_tc_backward_rays_mode():
+    """fused path: gradients reach the rays (dL/do, dL/dd incl. the view-direction term) and the parameters;
+    compacted sample list with a device-side count."""
+    ops, p, tensors, ps, tcw = setup(8, (4,))
+    g = torch.Generator().manual_seed(21)
+    B, S = 41, 16
+    ro = torch.randn(B, 3, generator=g) * 0.5
+    rd = F.normalize(torch.randn(B, 3, generator=g), dim=-1)
+    jit = torch.rand(B, generator=g) * 0.1
+    bw = [1.0, 1.0, 1.0, 0.9, 0.6, 0.3, 0.1, 0.0, 0.0, 0.0]
+    sel = torch.arange(0, B * S, 2, dtype=torch.int32)          # every other sample
+    n = sel.shape[0]
+    gout = torch.randn(n, 4, generator=g)
+    # oracle
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ror, rdr = ro.clone().requires_grad_(True), rd.clone().requires_grad_(True)
+    z = torch.linspace(1.0, 8.0, S).expand(B, -1) + jit[:, None]
+    xyz = (ror[:, None] + rdr[:, None] * z[..., None]).reshape(-1, 3)[sel.long()]
+    dirs = rdr[:, None].expand(-1, S, -1).reshape(-1, 3)[sel.long()]
+    orc.mlp_forward(pr, orc.sincos_encode(xyz, 10, torch.tensor(bw)), dirs, 8, (4,)).backward(gout)
+    # kernels
+    d = lambda t: t.to(DEV).contiguous()
+    cap = n + 37
+    sel_pad = torch.cat([sel, torch.zeros(cap - n, dtype=torch.int32)]).to(DEV)
+    n_dev = torch.tensor([n], dtype=torch.int32, device=DEV)
+    smp = ops.make_sampling(1.0, 8.0, S, 10, bw)
+    ro_d, rd_d, jit_d = d(ro), d(rd), d(jit)
+    tin = ops.make_tc_input_rays(ro_d, rd_d, jit_d, smp, sel_pad, cap, n_dev)
+    out = torch.zeros(cap, 4, device=DEV)
+    stash = ops.tc_stash(ps, cap, DEV)
+    ops.mlp_tc_fwd(ps, tcw, tin, out, stash)
+    grads = {k: torch.zeros_like(v) for k, v in tensors.items()}
+    gs = ops.fill_mlp_struct(ops.MlpGrads(), grads, 8)
+    ws = ops.tc_bwd_workspace(ps, cap, DEV)
+    g_o, g_d = torch.zeros(B, 3, device=DEV), torch.zeros(B, 3, device=DEV)
+    gpad = torch.cat([gout, torch.full((cap - n, 4), float("nan"))]).to(DEV).contiguous()   # rows beyond n must be ignored
+    ops.mlp_tc_bwd(ps, tcw, tin, out, gpad, stash, ws, gs, g_rays_o=g_o, g_rays_d=g_d)
+    torch.cuda.synchronize()
+    errs = {"g_rays_o": rel_err(g_o.cpu(), ror.grad), "g_rays_d": rel_err(g_d.cpu(), rdr.grad)}
+    for k in tensors:
+        errs[k] = rel_err(grads[k].cpu(), pr[k].grad)
+    print("vs fp32 oracle  :", {k: f"{v:.1e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < 0.2}
+    assert not bad, bad
