@@ -45,42 +45,45 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML in a
+    background thread (an `nvidia-smi -lms` subprocess stalls kernel launches for ~100 ms per query)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period=0.05):
+        self.index, self.period, self.rows, self.stop_flag, self.t = index, period, [], False, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.t = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                why = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((mhz, why))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
+        if self.t is None:
             return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        rows = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
-        if not rows:
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        if not self.rows:
             return None
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in rows for n, v in zip(names, r[2:]) if v.lower().startswith("active")})
-        return dict(sm_mhz=statistics.median(int(r[0]) for r in rows), sm_max_mhz=int(rows[0][1]), reasons=reasons,
-                    samples=len(rows))
+        reasons = sorted({name for _, why in self.rows for bit, name in self.REASONS.items() if why & bit})
+        return dict(sm_mhz=statistics.median(r[0] for r in self.rows), sm_max_mhz=self.max_mhz, reasons=reasons,
+                    samples=len(self.rows))
 
 
 def dist_env():
@@ -271,7 +274,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("MCNERF_PRECISION", "fp32"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("MCNERF_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--rays", type=int, default=RAYS)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

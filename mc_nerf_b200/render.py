@@ -36,19 +36,53 @@ class RenderCfg:
         self.precision = precision
 
     @staticmethod
-    def from_sys_param(sp, precision="fp32"):
+    def from_sys_param(sp, precision=None):
+        """`mlp_precision` (sys_param key, or env MCNERF_PRECISION): "bf16" = tcgen05 tensor-core path (default),
+        "fp32" = CUDA-core exact-parity path.  Shapes the tensor-core kernels do not implement use fp32."""
+        import os
+        if precision is None:
+            precision = sp.get("mlp_precision", os.environ.get("MCNERF_PRECISION", "bf16"))
         return RenderCfg(sp["near"], sp["far"], sp["samples"], sp["scale"], sp["emb_freqs_xyz"], sp["white_back"],
                          sp["sigma_default"], sp["sample_weight_thresh"],
                          (sp["coarse_MLP_depth"], sp["coarse_MLP_width"], tuple(sp["coarse_MLP_skip"])),
                          (sp["fine_MLP_depth"], sp["fine_MLP_width"], tuple(sp["fine_MLP_skip"])), precision)
 
 
-def _branch_fwd(cfg, net, tensors, rays_o, rays_d, jitter, S, band_w, sel_idx, n_rows, n_rows_dev):
+_TC_CACHE = {}     # (data_ptr of the first weight) -> ops.TcWeights (packed bf16 images, refreshed on version change)
+
+
+def _tc_weights(ps, tensors, need_bwd):
+    key = next(iter(tensors.values())).data_ptr()
+    tcw = _TC_CACHE.get(key)
+    if tcw is None:
+        if len(_TC_CACHE) > 16:
+            _TC_CACHE.clear()
+        tcw = _TC_CACHE[key] = ops.TcWeights()
+    return tcw.get(ps, tensors, need_bwd)
+
+
+def use_tc(cfg, net):
+    """bf16 tcgen05 path when asked for and the network shape is one the tensor-core kernels implement."""
+    depth, width, skips = net
+    return (cfg.precision == "bf16" and width == 256 and cfg.n_freqs == 10 and 2 <= depth <= 12
+            and len([s for s in skips if 0 < s < depth]) <= 1)
+
+
+def _branch_fwd(cfg, net, tensors, rays_o, rays_d, jitter, S, band_w, sel_idx, n_rows, n_rows_dev, train=True):
     """encode + MLP for one branch.  Returns (out4 [n_rows,4], saved-for-backward tuple)."""
     depth, width, skips = net
     dev = rays_o.device
     B = rays_o.shape[0]
     smp = ops.make_sampling(cfg.near, cfg.far, S, cfg.n_freqs, band_w)
+    if use_tc(cfg, net):
+        # fused sampling + encoding + MLP + SH head, bf16 tcgen05 (mlp_tc_fwd.cu)
+        ps = ops.make_mlp_params(tensors, depth, width, skips, in_ch=cfg.in_ch)
+        tcw = _tc_weights(ps, tensors, train)
+        tin = ops.make_tc_input_rays(rays_o, rays_d, jitter, smp, sel_idx, n_rows, n_rows_dev)
+        out4 = torch.empty(n_rows, 4, device=dev)
+        stash = ops.tc_stash(ps, n_rows, dev) if train else None
+        ops.mlp_tc_fwd(ps, tcw, tin, out4, stash)
+        return out4, ("tc", tcw, tin, stash)
     enc = torch.empty(n_rows, cfg.in_ch, device=dev)
     lib().call("mcnerf_encode_rays_fwd", _p(rays_o), _p(rays_d), _p(jitter), B, ctypes.byref(smp),
                _p(sel_idx, torch.int32), n_rows, _p(n_rows_dev, torch.int32), _p(enc), cfg.in_ch, _stream())
@@ -62,12 +96,17 @@ def _branch_fwd(cfg, net, tensors, rays_o, rays_d, jitter, S, band_w, sel_idx, n
 
 
 def _branch_bwd(cfg, net, tensors, grads, rays_o, rays_d, jitter, S, band_w, sel_idx, n_rows, n_rows_dev,
-                saved, g_out4, g_rays_o, g_rays_d):
+                saved, out4, g_out4, g_rays_o, g_rays_d):
     depth, width, skips = net
-    enc, ws = saved
     B = rays_o.shape[0]
     ps = ops.make_mlp_params(tensors, depth, width, skips, in_ch=cfg.in_ch)
     gs = ops.fill_mlp_struct(MlpGrads(), grads, depth)
+    if saved[0] == "tc":
+        _, tcw, tin, stash = saved
+        ws = ops.tc_bwd_workspace(ps, n_rows, rays_o.device)
+        ops.mlp_tc_bwd(ps, tcw, tin, out4, g_out4, stash, ws, gs, g_rays_o=g_rays_o, g_rays_d=g_rays_d)
+        return
+    enc, ws = saved
     d = ops.make_dirs(rays_d, sel_idx, S)
     g_enc = torch.empty_like(enc)
     lib().call("mcnerf_mlp_f32_bwd", ctypes.byref(ps), _p(enc), cfg.in_ch, ctypes.byref(d), n_rows,
@@ -112,7 +151,9 @@ class RenderFn(torch.autograd.Function):
         jitter = ops._f32(rng["jitter"]).reshape(-1) if (train and rng.get("jitter") is not None) else None
         noise_c, noise_sel, noise_f = (ops._f32(rng[k]) for k in ("noise_c", "noise_sel", "noise_f"))
         # coarse
-        out_c, saved_c = _branch_fwd(cfg, cfg.coarse, tc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None)
+        need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
+        out_c, saved_c = _branch_fwd(cfg, cfg.coarse, tc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
+                                     need_grad)
         cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
         rgb_c = torch.empty(B, 3, device=dev)
         lib().call("mcnerf_composite_fwd", _p(out_c), _p(noise_c), _p(rays_d), _p(jitter), None, B,
@@ -123,7 +164,7 @@ class RenderFn(torch.autograd.Function):
         # fine
         if n_rows > 0:
             out_sel, saved_f = _branch_fwd(cfg, cfg.fine, tf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx,
-                                           n_rows, n_rows_dev)
+                                           n_rows, n_rows_dev, need_grad)
         else:
             out_sel, saved_f = torch.empty(0, 4, device=dev), None
         dense = torch.empty(B * cfg.Sf, 4, device=dev)
@@ -137,14 +178,15 @@ class RenderFn(torch.autograd.Function):
                    ctypes.byref(cf), _p(rgb_f), _p(depth_f), _p(opa_f), None, _stream())
         ctx.cfg, ctx.band_w, ctx.n_rows = cfg, band_w, n_rows
         ctx.tc, ctx.tf = tc, tf
-        ctx.saved = (rays_d, rays_o, jitter, noise_c, noise_f, out_c, saved_c, sel_idx, n_rows_dev, dense, saved_f)
+        ctx.saved = (rays_d, rays_o, jitter, noise_c, noise_f, out_c, saved_c, sel_idx, n_rows_dev, dense, saved_f,
+                     out_sel)
         ctx.mark_non_differentiable(depth_f, opa_f)
         return rgb_c, rgb_f, depth_f, opa_f
 
     @staticmethod
     def backward(ctx, g_rgb_c, g_rgb_f, _gd, _go):
         cfg, band_w, n_rows = ctx.cfg, ctx.band_w, ctx.n_rows
-        rays_d, rays_o, jitter, noise_c, noise_f, out_c, saved_c, sel_idx, n_rows_dev, dense, saved_f = ctx.saved
+        rays_d, rays_o, jitter, noise_c, noise_f, out_c, saved_c, sel_idx, n_rows_dev, dense, saved_f, out_sel = ctx.saved
         B, dev = rays_d.shape[0], rays_d.device
         tc, tf = ctx.tc, ctx.tf
         gc = {k: torch.zeros_like(v) for k, v in tc.items()}
@@ -160,14 +202,14 @@ class RenderFn(torch.autograd.Function):
             lib().call("mcnerf_gather_fine", _p(g_dense), _p(sel_idx, torch.int32), n_rows,
                        _p(n_rows_dev, torch.int32), _p(g_sel), _stream())
             _branch_bwd(cfg, cfg.fine, tf, gf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx, n_rows, n_rows_dev,
-                        saved_f, g_sel, g_o, g_d)
+                        saved_f, out_sel, g_sel, g_o, g_d)
         if g_rgb_c is not None:
             cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
             g_out_c = torch.empty_like(out_c)
             lib().call("mcnerf_composite_bwd", _p(out_c), _p(noise_c), _p(jitter), None, B, ctypes.byref(cc),
                        _p(ops._f32(g_rgb_c)), _p(g_out_c), _stream())
             _branch_bwd(cfg, cfg.coarse, tc, gc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
-                        saved_c, g_out_c, g_o, g_d)
+                        saved_c, out_c, g_out_c, g_o, g_d)
         pg = [gc[k] for k in ops.param_names(cfg.coarse[0])] + [gf[k] for k in ops.param_names(cfg.fine[0])]
         return (None, None, None, None, None, g_d, g_o) + tuple(pg)
 
