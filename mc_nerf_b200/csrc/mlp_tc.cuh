@@ -68,6 +68,8 @@ struct WJob {
   int which;          // parameter id: 0..depth-1 trunk, depth sigma.0, depth+1 sh.0, depth+2 sh.2, depth+3 sigma.2
   int col_off;        // column offset inside the parameter's [out,in] matrix (63 for the h part of a skip layer)
   int n_valid;        // valid input columns (63 for encoding parts, else 256)
+  int bias_mode;      // 0: none; 1: column sums of the A operand (dY) -> bias grad of `which`;
+                      // 2: B operand = head tile cols 0..26 -> sh.2 bias; 3: head tile col 31 -> sigma.2 bias
 };
 struct WPlan {
   int n_jobs;
@@ -95,6 +97,14 @@ __host__ __device__ inline size_t stash_tiles(int n_rows) {
   return t + (t & 1);
 }
 constexpr int HEAD_BYTES = TM * 32 * 2;      // 8 KB: head-gradient tile [128 x 32] bf16 (g_sh 0..26, g_sigma at 31)
+constexpr int BITS_BYTES = TM * 32;          // 4 KB: ReLU gate bits of one tile-layer [128 rows][8 x u32]
+
+// Tile images in HBM (activation stash, dY stash, head tile) are stored as two 64-row halves, each a contiguous
+// [k-group plane][64 rows][16 B] block, so that the weight-gradient kernel fetches one half of ALL planes with a
+// single large bulk copy.  (In shared memory the forward / backward-chain kernels keep whole 128-row planes.)
+__host__ __device__ inline uint32_t stash_off(int row, int kg, int n_planes) {
+  return (uint32_t)(row >> 6) * (uint32_t)(n_planes * 1024) + (uint32_t)kg * 1024u + (uint32_t)(row & 63) * 16u;
+}
 
 int build_layout(const mcnerf_mlp_params* p, PackLayout* L);
 

@@ -16,7 +16,7 @@ struct BwdArgs {
   const float* bias;        // bias block (w_sigma2 at sig2_off)
   int sig2_off;
   int n_slots;              // D + 2
-  const uint8_t* stash;     // forward activations [tile][n_slots][ACT_BYTES]
+  const uint8_t* stash_bits;  // forward ReLU gate bits [tile][n_slots][BITS_BYTES]
   const float* stash_sh;    // [row][SH_LD]
   uint8_t* dy;              // [tile][n_slots][ACT_BYTES]
   uint8_t* dy_head;         // [tile][HEAD_BYTES]
@@ -67,10 +67,10 @@ __device__ __forceinline__ bool seg_reduce(int key, float (&v)[NV], int lane) {
   return lane == 0 || kp != key;
 }
 
-__device__ __forceinline__ uint32_t relu_gate2(uint32_t act_pair, float lo, float hi) {
-  // act_pair: two bf16 forward activations (post-ReLU, so >= +0): gate = activation != 0
-  float a = (act_pair & 0x00007FFFu) ? lo : 0.f;
-  float b = (act_pair & 0x7FFF0000u) ? hi : 0.f;
+__device__ __forceinline__ uint32_t relu_gate2(uint32_t bits, int pos, float lo, float hi) {
+  // bits: forward ReLU gate word (bit c set <=> activation c of this 32-column block was > 0)
+  float a = (bits >> pos & 1u) ? lo : 0.f;
+  float b = (bits >> (pos + 1) & 1u) ? hi : 0.f;
   return tc::pack_bf16(a, b);
 }
 
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
       const int row_g = tile * TM + q;
       const bool valid = row_g < rows;
       const bool tile_ok = tile < n_tiles;
-      const uint8_t* st_tile = a.stash + (size_t)tile * a.n_slots * ACT_BYTES;
+      const uint8_t* bits_tile = a.stash_bits + (size_t)tile * a.n_slots * BITS_BYTES + q * 32;
       uint8_t* dy_tile = a.dy + (size_t)tile * a.n_slots * ACT_BYTES;
       int ray = -1 - lane;
       float z = 0.f;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
           uint4 v = make_uint4(tc::pack_bf16(hv[kg * 8], hv[kg * 8 + 1]), tc::pack_bf16(hv[kg * 8 + 2], hv[kg * 8 + 3]),
                                tc::pack_bf16(hv[kg * 8 + 4], hv[kg * 8 + 5]), tc::pack_bf16(hv[kg * 8 + 6], hv[kg * 8 + 7]));
           sts_v4(small_t + kg * PLANE + q * 16, v);
-          if (tile_ok) *reinterpret_cast<uint4*>(a.dy_head + (size_t)tile * HEAD_BYTES + kg * PLANE + q * 16) = v;
+          if (tile_ok) *reinterpret_cast<uint4*>(a.dy_head + (size_t)tile * HEAD_BYTES + stash_off(q, kg, 4)) = v;
         }
         if (a.x_enc) {
           if (valid) { a.g_dirs_rows[3 * (size_t)row_g] = gd[0]; a.g_dirs_rows[3 * (size_t)row_g + 1] = gd[1]; a.g_dirs_rows[3 * (size_t)row_g + 2] = gd[2]; }
@@ -226,56 +226,60 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
 
       for (int jn = 0; jn < n_jobs; ++jn) {
         const BJob& jb = a.plan.j[jn];
+        // forward ReLU gate bits of this row (32 B), fetched BEFORE waiting for the accumulator
+        uint32_t gate[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (tile_ok && jb.mask_slot >= 0) {
+          const uint4* gp = reinterpret_cast<const uint4*>(bits_tile + (size_t)jb.mask_slot * BITS_BYTES);
+          const uint4 g0 = gp[0], g1 = gp[1];
+          gate[0] = g0.x; gate[1] = g0.y; gate[2] = g0.z; gate[3] = g0.w;
+          gate[4] = g1.x; gate[5] = g1.y; gate[6] = g1.z; gate[7] = g1.w;
+        }
         tc::mbar_wait(&bars->acc_full[t], par);
         par ^= 1;
         tc::tcgen05_fence_after();
         if (jb.kind == BK_MASK_STORE) {
-          const uint8_t* mk = st_tile + (size_t)jb.mask_slot * ACT_BYTES + q * 16;
-          uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES + q * 16;
-#pragma unroll 1
-          for (int cg = 0; cg < WID / 32; ++cg) {
-            uint4 m[4];
+          uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              m[j] = tile_ok ? *reinterpret_cast<const uint4*>(mk + (cg * 4 + j) * PLANE) : make_uint4(0, 0, 0, 0);
+          for (int cg = 0; cg < WID / 32; ++cg) {
             uint32_t v[32];
             tc::tmem_ld32(taddr + cg * 32, v);
             tc::tmem_ld_wait();
+            const uint32_t gb = gate[cg];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
-              o.x = relu_gate2(m[j].x, __uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
-              o.y = relu_gate2(m[j].y, __uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
-              o.z = relu_gate2(m[j].z, __uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
-              o.w = relu_gate2(m[j].w, __uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+              o.x = relu_gate2(gb, j * 8 + 0, __uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+              o.y = relu_gate2(gb, j * 8 + 2, __uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+              o.z = relu_gate2(gb, j * 8 + 4, __uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+              o.w = relu_gate2(gb, j * 8 + 6, __uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
               sts_v4(bufX_t + (cg * 4 + j) * PLANE + q * 16, o);
-              if (tile_ok) *reinterpret_cast<uint4*>(dyo + (cg * 4 + j) * PLANE) = o;
+              if (tile_ok) *reinterpret_cast<uint4*>(dyo + stash_off(q, cg * 4 + j, 32)) = o;
             }
           }
         } else if (jb.kind == BK_SIGMA_INJECT) {
-          // d relu(sigma.0) pre-activation = g_sigma * w_sigma2 gated by the stashed activation; the accumulator
+          // d relu(sigma.0) pre-activation = g_sigma * w_sigma2 gated by the forward gate bits; the accumulator
           // (gradient that arrived through sh.0) stays in TMEM and the next job accumulates onto it.
-          const uint8_t* mk = st_tile + (size_t)jb.mask_slot * ACT_BYTES + q * 16;
-          uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES + q * 16;
-#pragma unroll 4
+          uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES;
+#pragma unroll
           for (int kg = 0; kg < WID / 8; ++kg) {
-            const uint4 m = tile_ok ? *reinterpret_cast<const uint4*>(mk + kg * PLANE) : make_uint4(0, 0, 0, 0);
             const float4 s0 = __ldg(reinterpret_cast<const float4*>(w2 + kg * 8));
             const float4 s1 = __ldg(reinterpret_cast<const float4*>(w2 + kg * 8 + 4));
+            const uint32_t gb = gate[kg >> 2];
+            const int pos = (kg & 3) * 8;
             uint4 o;
-            o.x = relu_gate2(m.x, g_sigma * s0.x, g_sigma * s0.y);
-            o.y = relu_gate2(m.y, g_sigma * s0.z, g_sigma * s0.w);
-            o.z = relu_gate2(m.z, g_sigma * s1.x, g_sigma * s1.y);
-            o.w = relu_gate2(m.w, g_sigma * s1.z, g_sigma * s1.w);
+            o.x = relu_gate2(gb, pos + 0, g_sigma * s0.x, g_sigma * s0.y);
+            o.y = relu_gate2(gb, pos + 2, g_sigma * s0.z, g_sigma * s0.w);
+            o.z = relu_gate2(gb, pos + 4, g_sigma * s1.x, g_sigma * s1.y);
+            o.w = relu_gate2(gb, pos + 6, g_sigma * s1.z, g_sigma * s1.w);
             sts_v4(bufX_t + kg * PLANE + q * 16, o);
-            if (tile_ok) *reinterpret_cast<uint4*>(dyo + kg * PLANE) = o;
+            if (tile_ok) *reinterpret_cast<uint4*>(dyo + stash_off(q, kg, 32)) = o;
           }
         } else if (jb.kind == BK_RELOAD_SKIP) {
           // bring the skip layer's dY tile (this thread's own row, written a few jobs ago) back as the A operand
-          const uint8_t* src = dy_tile + (size_t)a.plan.skip_dy_slot * ACT_BYTES + q * 16;
-#pragma unroll 4
+          const uint8_t* src = dy_tile + (size_t)a.plan.skip_dy_slot * ACT_BYTES;
+#pragma unroll 8
           for (int kg = 0; kg < WID / 8; ++kg) {
-            const uint4 v = tile_ok ? *reinterpret_cast<const uint4*>(src + kg * PLANE) : make_uint4(0, 0, 0, 0);
+            const uint4 v = tile_ok ? *reinterpret_cast<const uint4*>(src + stash_off(q, kg, 32)) : make_uint4(0, 0, 0, 0);
             sts_v4(bufX_t + kg * PLANE + q * 16, v);
           }
         } else {   // BK_ENC_OUT
@@ -375,9 +379,10 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
   a.bias = bias;
   a.sig2_off = L.sig2_off;
   a.n_slots = n_slots;
-  a.stash = (const uint8_t*)stash;
-  const uint8_t* stash_enc = a.stash + tiles * (size_t)n_slots * ACT_BYTES;
+  const uint8_t* stash_act = (const uint8_t*)stash;
+  const uint8_t* stash_enc = stash_act + tiles * (size_t)n_slots * ACT_BYTES;
   a.stash_sh = (const float*)(stash_enc + tiles * ENC_BYTES);
+  a.stash_bits = (const uint8_t*)(a.stash_sh + tiles * (size_t)TM * SH_LD);
   a.dy = (uint8_t*)workspace;
   a.dy_head = a.dy + tiles * (size_t)n_slots * ACT_BYTES;
   a.g_out4 = g_out4; a.out4 = out4;
@@ -400,5 +405,5 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
   // weight gradients (tcgen05, reduction over all rows) and bias gradients (column sums of the dY stash)
   MC_ARG(sms <= WG_MAX_CTAS);
   float* scratch = (float*)(a.dy_head + tiles * HEAD_BYTES);
-  return mlp_tc_wgrad_launch(p, L, a.stash, stash_enc, a.dy, a.dy_head, scratch, in->n_rows, in->n_rows_dev, g, st);
+  return mlp_tc_wgrad_launch(p, L, stash_act, stash_enc, a.dy, a.dy_head, scratch, in->n_rows, in->n_rows_dev, g, st);
 }

@@ -107,20 +107,20 @@ int build_layout(const mcnerf_mlp_params* p, PackLayout* L) {
   // weight-gradient jobs
   WPlan& Wp = L->wg;
   int nw = 0;
-  auto wadd = [&](int dy, int x, int N, int tr, int hc, int which, int col_off, int n_valid) {
+  auto wadd = [&](int dy, int x, int N, int tr, int hc, int which, int col_off, int n_valid, int bias_mode) {
     WJob& j = Wp.j[nw++];
     j.dy_slot = dy; j.x_slot = x; j.N = N; j.transposed = tr; j.head_col0 = hc; j.which = which; j.col_off = col_off;
-    j.n_valid = n_valid;
+    j.n_valid = n_valid; j.bias_mode = bias_mode;
   };
   for (int l = 0; l < D; ++l) {
-    if (l == 0) wadd(0, -1, ENCW, 0, 0, 0, 0, 63);
-    else if (l == skip_layer) { wadd(l, -1, ENCW, 0, 0, l, 0, 63); wadd(l, l - 1, WID, 0, 0, l, 63, WID); }
-    else wadd(l, l - 1, WID, 0, 0, l, 0, WID);
+    if (l == 0) wadd(0, -1, ENCW, 0, 0, 0, 0, 63, 1);
+    else if (l == skip_layer) { wadd(l, -1, ENCW, 0, 0, l, 0, 63, 0); wadd(l, l - 1, WID, 0, 0, l, 63, WID, 1); }
+    else wadd(l, l - 1, WID, 0, 0, l, 0, WID, 1);
   }
-  wadd(D, D - 1, WID, 0, 0, D, 0, WID);          // sigma.0
-  wadd(D + 1, D - 1, WID, 0, 0, D + 1, 0, WID);  // sh.0
-  wadd(-1, D + 1, 32, 1, 0, D + 2, 0, WID);      // sh.2 (transposed: A = relu(sh.0)^T, B = head tile cols 0..31)
-  wadd(-1, D, 16, 1, 16, D + 3, 0, WID);         // sigma.2 (transposed: B = head tile cols 16..31, g_sigma at col 31)
+  wadd(D, D - 1, WID, 0, 0, D, 0, WID, 1);          // sigma.0
+  wadd(D + 1, D - 1, WID, 0, 0, D + 1, 0, WID, 1);  // sh.0
+  wadd(-1, D + 1, 32, 1, 0, D + 2, 0, WID, 2);      // sh.2 (transposed: A = relu(sh.0)^T, B = head tile cols 0..31)
+  wadd(-1, D, 16, 1, 16, D + 3, 0, WID, 3);         // sigma.2 (transposed: B = head tile cols 16..31, g_sigma at col 31)
   Wp.n_jobs = nw;
   return 0;
 }
@@ -151,6 +151,7 @@ struct FwdArgs {
   uint8_t* stash;        // [tile][n_slots][ACT_BYTES] or null
   uint8_t* stash_enc;    // [tile][ENC_BYTES]
   float* stash_sh;       // [row][SH_LD]
+  uint8_t* stash_bits;   // [tile][n_slots][BITS_BYTES] ReLU gate bits
   int n_slots;
 };
 
@@ -209,10 +210,11 @@ __device__ __forceinline__ void encode_row(const FwdArgs& a, int row_g, bool val
     uint32_t w0 = tc::pack_bf16(f[kg * 8 + 0], f[kg * 8 + 1]), w1 = tc::pack_bf16(f[kg * 8 + 2], f[kg * 8 + 3]);
     uint32_t w2 = tc::pack_bf16(f[kg * 8 + 4], f[kg * 8 + 5]), w3 = tc::pack_bf16(f[kg * 8 + 6], f[kg * 8 + 7]);
     st_shared_v4(enc_smem + kg * PLANE + q * 16, w0, w1, w2, w3);
-    if (stash_enc_tile) *reinterpret_cast<uint4*>(stash_enc_tile + kg * PLANE + q * 16) = make_uint4(w0, w1, w2, w3);
+    if (stash_enc_tile) *reinterpret_cast<uint4*>(stash_enc_tile + stash_off(q, kg, 8)) = make_uint4(w0, w1, w2, w3);
   }
 }
 
+template <bool TRAIN>
 __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;                                   // [2][ACT_BYTES]
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
       const int tile = 2 * pair + t;
       const int row_g = tile * TM + q;
       const bool valid = row_g < rows;
-      uint8_t* st_enc = (a.stash_enc && tile < n_tiles) ? a.stash_enc + (size_t)tile * ENC_BYTES : nullptr;
+      uint8_t* st_enc = (TRAIN && tile < n_tiles) ? a.stash_enc + (size_t)tile * ENC_BYTES : nullptr;
       encode_row(a, row_g, valid, enc_t, q, st_enc);
       tc::fence_proxy_async();
       tc::tcgen05_fence_before();
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
               c[ch] = sigmoid_f(acc);
             }
             reinterpret_cast<float4*>(a.out4)[row_g] = make_float4(sigma_raw, c[0], c[1], c[2]);
-            if (a.stash_sh) {
+            if (TRAIN) {
               float4* dst = reinterpret_cast<float4*>(a.stash_sh + (size_t)row_g * SH_LD);
 #pragma unroll
               for (int i = 0; i < 7; ++i)
@@ -346,17 +348,19 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
             }
           }
         } else {
-          uint8_t* st_tile = (a.stash && st.stash_slot >= 0 && tile < n_tiles)
+          uint8_t* st_tile = (TRAIN && st.stash_slot >= 0 && tile < n_tiles)
                                  ? a.stash + ((size_t)tile * a.n_slots + st.stash_slot) * ACT_BYTES
                                  : nullptr;
           const bool to_smem = st.epi == EPI_RELU;
           const float* w2 = a.bias + a.sig2_off;
           float dot = 0.f;
+          uint32_t gate[8];
 #pragma unroll 1
           for (int cg = 0; cg < WID / 32; ++cg) {
             uint32_t v[32];
             tc::tmem_ld32(taddr + cg * 32, v);
             tc::tmem_ld_wait();
+            uint32_t gbits = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float x[8];
@@ -364,7 +368,10 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cg * 32 + j * 8 + 4));
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(v[j * 8 + i]) + bb[i], 0.f);
+              for (int i = 0; i < 8; ++i) {
+                x[i] = fmaxf(__uint_as_float(v[j * 8 + i]) + bb[i], 0.f);
+                if (TRAIN) gbits |= (x[i] > 0.f ? 1u : 0u) << (j * 8 + i);
+              }
               if (!to_smem) {
                 const float4 s0 = __ldg(reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8));
                 const float4 s1 = __ldg(reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8 + 4));
@@ -375,8 +382,15 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
               const uint32_t w2p = tc::pack_bf16(x[4], x[5]), w3 = tc::pack_bf16(x[6], x[7]);
               const int kg = cg * 4 + j;
               if (to_smem) st_shared_v4(act_t + kg * PLANE + q * 16, w0, w1, w2p, w3);
-              if (st_tile) *reinterpret_cast<uint4*>(st_tile + kg * PLANE + q * 16) = make_uint4(w0, w1, w2p, w3);
+              if (st_tile) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w0, w1, w2p, w3);
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (TRAIN && i == cg) gate[i] = gbits;
+          }
+          if (st_tile) {
+            uint4* gp = reinterpret_cast<uint4*>(a.stash_bits + ((size_t)tile * a.n_slots + st.stash_slot) * BITS_BYTES + q * 32);
+            gp[0] = make_uint4(gate[0], gate[1], gate[2], gate[3]);
+            gp[1] = make_uint4(gate[4], gate[5], gate[6], gate[7]);
           }
           if (!to_smem) sigma_raw = dot + __ldg(w2 + 256);
         }
@@ -464,7 +478,7 @@ extern "C" size_t mcnerf_mlp_tc_stash_bytes(const mcnerf_mlp_params* p, int n_ro
   if (!mcnerf_mlp_tc_supported(p) || n_rows <= 0) return 0;
   size_t tiles = (size_t)(n_rows + TM - 1) / TM;
   tiles += tiles & 1;   // tiles are processed in pairs
-  return tiles * ((size_t)(p->depth + 2) * ACT_BYTES + ENC_BYTES + (size_t)TM * SH_LD * sizeof(float));
+  return tiles * ((size_t)(p->depth + 2) * (ACT_BYTES + BITS_BYTES) + ENC_BYTES + (size_t)TM * SH_LD * sizeof(float));
 }
 
 extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, const float* bias,
@@ -491,12 +505,14 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
     a.stash = (uint8_t*)stash;
     a.stash_enc = a.stash + tiles * (size_t)a.n_slots * ACT_BYTES;
     a.stash_sh = (float*)(a.stash_enc + tiles * ENC_BYTES);
+    a.stash_bits = (uint8_t*)(a.stash_sh + tiles * (size_t)TM * SH_LD);
   } else {
-    a.stash = nullptr; a.stash_enc = nullptr; a.stash_sh = nullptr;
+    a.stash = nullptr; a.stash_enc = nullptr; a.stash_sh = nullptr; a.stash_bits = nullptr;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+    MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+    MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
     attr_set = true;
   }
   int n_pairs = ((in->n_rows + TM - 1) / TM + 1) / 2;
@@ -504,7 +520,8 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = n_pairs < sms ? n_pairs : sms;
-  mlp_tc_fwd_k<<<grid, 320, SMEM_FWD, (cudaStream_t)stream>>>(a);
+  if (stash) mlp_tc_fwd_k<true><<<grid, 320, SMEM_FWD, (cudaStream_t)stream>>>(a);
+  else mlp_tc_fwd_k<false><<<grid, 320, SMEM_FWD, (cudaStream_t)stream>>>(a);
   MC_LAUNCHED();
   return 0;
 }

@@ -27,6 +27,7 @@ struct WArgs {
   const int32_t* n_rows_dev;
   float* scratch;                    // [gridDim.x][2][128][256] fp32 partials
   int cta_begin[MAX_STEPS + 1];
+  float* db[MAX_STEPS];              // bias gradient of each job (bias_mode != 0), accumulated with atomics
 };
 
 struct __align__(16) WBars {
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_tc_wgrad_k(const __grid_con
   const int N = wj.N;
 
   if (tid == 0) {
-    for (int i = 0; i < WG_NSTAGE; ++i) { tc::mbar_init(&bars->full[i], 1); tc::mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < WG_NSTAGE; ++i) { tc::mbar_init(&bars->full[i], 1); tc::mbar_init(&bars->empty[i], 5); }
     tc::mbar_init(&bars->acc_full, 1);
     tc::mbar_init_fence();
   }
@@ -59,38 +60,38 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_tc_wgrad_k(const __grid_con
   tc::tcgen05_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  // operand sources.  A: 32 planes (256 features); B: N/8 planes.
+  // operand sources: each 64-row half of a tile image is one contiguous [plane][64 rows][16 B] block.
+  // A: all 32 planes (256 features) = 32 KB; B: N/8 planes starting at plane b_plane0 of a b_planes-plane image.
   const size_t tile_stride = (size_t)a.n_slots * ACT_BYTES;
   const uint8_t *a_base, *b_base;
   size_t a_stride, b_stride;
+  int b_planes, b_plane0 = 0;
   if (!wj.transposed) {
     a_base = a.dy + (size_t)wj.dy_slot * ACT_BYTES; a_stride = tile_stride;
-    if (wj.x_slot < 0) { b_base = a.stash_enc; b_stride = ENC_BYTES; }
-    else { b_base = a.stash + (size_t)wj.x_slot * ACT_BYTES; b_stride = tile_stride; }
+    if (wj.x_slot < 0) { b_base = a.stash_enc; b_stride = ENC_BYTES; b_planes = 8; }
+    else { b_base = a.stash + (size_t)wj.x_slot * ACT_BYTES; b_stride = tile_stride; b_planes = 32; }
   } else {
     a_base = a.stash + (size_t)wj.x_slot * ACT_BYTES; a_stride = tile_stride;
-    b_base = a.dy_head + (size_t)(wj.head_col0 / 8) * PLANE; b_stride = HEAD_BYTES;
+    b_base = a.dy_head; b_stride = HEAD_BYTES; b_planes = 4; b_plane0 = wj.head_col0 / 8;
   }
   const int nb_planes = N / 8;
+  const uint32_t a_bytes = 32 * WG_PLANE, b_bytes = (uint32_t)nb_planes * WG_PLANE;
 
   if (warp == 0) {
-    int stage = 0;
-    uint32_t par = 0;
-    for (int i = 0; i < n_stages_total; ++i) {
-      const int tile = t_begin + (i >> 1), half = i & 1;
-      if (lane == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t par = 0;
+      for (int i = 0; i < n_stages_total; ++i) {
+        const int tile = t_begin + (i >> 1), half = i & 1;
         tc::mbar_wait(&bars->empty[stage], par ^ 1);
-        tc::mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)(32 + nb_planes) * WG_PLANE);
+        tc::mbar_arrive_expect_tx(&bars->full[stage], a_bytes + b_bytes);
+        uint8_t* sdst = smem + stage * WG_STAGE;
+        tc::bulk_g2s(sdst, a_base + (size_t)tile * a_stride + (size_t)half * a_bytes, a_bytes, &bars->full[stage]);
+        tc::bulk_g2s(sdst + 32 * WG_PLANE,
+                     b_base + (size_t)tile * b_stride + (size_t)half * b_planes * WG_PLANE + (size_t)b_plane0 * WG_PLANE,
+                     b_bytes, &bars->full[stage]);
+        if (++stage == WG_NSTAGE) { stage = 0; par ^= 1; }
       }
-      __syncwarp();
-      uint8_t* sdst = smem + stage * WG_STAGE;
-      tc::bulk_g2s(sdst + lane * WG_PLANE, a_base + (size_t)tile * a_stride + (size_t)lane * PLANE + half * WG_PLANE,
-                   WG_PLANE, &bars->full[stage]);
-      if (lane < nb_planes)
-        tc::bulk_g2s(sdst + 32 * WG_PLANE + lane * WG_PLANE,
-                     b_base + (size_t)tile * b_stride + (size_t)lane * PLANE + half * WG_PLANE, WG_PLANE,
-                     &bars->full[stage]);
-      if (++stage == WG_NSTAGE) { stage = 0; par ^= 1; }
     }
   } else if (warp == 1) {
     if (lane == 0 && n_stages_total > 0) {
@@ -116,7 +117,72 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_tc_wgrad_k(const __grid_con
       tc::umma_commit(&bars->acc_full);
     }
   } else {
-    // epilogue: lane quarter (warp % 4), both halves
+    // ---- warps 2-5.  While the MMAs run: bias gradients = column sums of the dY operand sitting in the ring
+    // (warp w owns 8 of the 32 planes; lane l owns rows l and l+32).  Afterwards: TMEM -> scratch partials.
+    const int w4 = warp - 2;
+    const int bm = wj.bias_mode;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    {
+      int stage = 0;
+      uint32_t par = 0;
+      for (int i = 0; i < n_stages_total; ++i) {
+        tc::mbar_wait(&bars->full[stage], par);
+        const uint8_t* sA = smem + stage * WG_STAGE;
+        if (bm == 1) {
+#pragma unroll
+          for (int pl = 0; pl < 8; ++pl)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const uint4 v = *reinterpret_cast<const uint4*>(sA + (w4 * 8 + pl) * WG_PLANE + (lane + 32 * rr) * 16);
+              const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                acc[pl][2 * e] += __uint_as_float(w[e] << 16);
+                acc[pl][2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+              }
+            }
+        } else if (bm >= 2 && w4 < nb_planes) {
+          const uint8_t* sB = sA + 32 * WG_PLANE;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sB + w4 * WG_PLANE + (lane + 32 * rr) * 16);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[0][2 * e] += __uint_as_float(w[e] << 16);
+              acc[0][2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars->empty[stage]);
+        if (++stage == WG_NSTAGE) { stage = 0; par ^= 1; }
+      }
+    }
+    if (bm == 1) {
+#pragma unroll
+      for (int pl = 0; pl < 8; ++pl)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float s = warp_sum(acc[pl][j]);
+          if (lane == 0) atomicAdd(a.db[job] + (w4 * 8 + pl) * 8 + j, s);
+        }
+    } else if (bm >= 2 && w4 < nb_planes) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float s = warp_sum(acc[0][j]);
+        const int col = (b_plane0 + w4) * 8 + j;          // head-tile column
+        if (lane == 0) {
+          if (bm == 2 && col < 27) atomicAdd(a.db[job] + col, s);
+          if (bm == 3 && col == 31) atomicAdd(a.db[job], s);
+        }
+      }
+    }
+    // ---- epilogue proper: lane quarter (warp % 4), both halves
     float* out = a.scratch + (size_t)blockIdx.x * 2 * 128 * 256;
     const int m = (warp & 3) * 32 + lane;
     if (n_stages_total > 0) {
@@ -177,38 +243,6 @@ __global__ void __launch_bounds__(256) wgrad_reduce_k(const __grid_constant__ RA
   }
 }
 
-// bias gradients: column sums of a dY-stash slot (or of the head tile) over all tiles.
-__global__ void __launch_bounds__(128) dy_colsum_k(const uint8_t* __restrict__ base, size_t tile_stride, int n_rows,
-                                                   const int32_t* __restrict__ n_rows_dev, float* __restrict__ db,
-                                                   int col0, int n_cols_valid) {
-  const int rows = n_rows_dev ? min(*n_rows_dev, n_rows) : n_rows;
-  const int n_tiles = (rows + TM - 1) / TM;
-  const int p = blockIdx.x;     // k-group plane: columns p*8 .. p*8+7
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
-    const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)tile * tile_stride + (size_t)p * PLANE + threadIdx.x * 16);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc[2 * i] += __uint_as_float(w[i] << 16);
-      acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
-    }
-  }
-  __shared__ float sm[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sm[i][wid] = acc[i];
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    const float s = sm[threadIdx.x][0] + sm[threadIdx.x][1] + sm[threadIdx.x][2] + sm[threadIdx.x][3];
-    const int col = p * 8 + threadIdx.x - col0;
-    if (col >= 0 && col < n_cols_valid) atomicAdd(db + col, s);
-  }
-}
-
 }  // namespace mlptc
 
 using namespace mlptc;
@@ -242,6 +276,14 @@ int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const u
   while (used > sms) for (int j = 0; j < nj && used > sms; ++j) if (cnt[j] > 1) { --cnt[j]; --used; }
   a.cta_begin[0] = 0;
   for (int j = 0; j < nj; ++j) a.cta_begin[j + 1] = a.cta_begin[j] + cnt[j];
+  for (int j = 0; j < nj; ++j) {
+    const int which = L.wg.j[j].which;
+    float* db = nullptr;
+    if (L.wg.j[j].bias_mode == 1) db = which < D ? g->b[which] : (which == D ? g->b_sigma0 : g->b_sh0);
+    else if (L.wg.j[j].bias_mode == 2) db = g->b_sh2;
+    else if (L.wg.j[j].bias_mode == 3) db = g->b_sigma2;
+    a.db[j] = db;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     MC_CUDA(cudaFuncSetAttribute(mlp_tc_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG));
@@ -269,18 +311,5 @@ int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const u
   wgrad_reduce_k<<<dim3(256, nj), 256, 0, st>>>(r);
   MC_LAUNCHED();
 
-  // biases
-  const size_t tile_stride = (size_t)(D + 2) * ACT_BYTES;
-  auto colsum = [&](const uint8_t* base, size_t stride, int planes, float* db, int col0, int n_valid) -> int {
-    dy_colsum_k<<<dim3(planes, 64), 128, 0, st>>>(base, stride, n_rows, n_rows_dev, db, col0, n_valid);
-    MC_LAUNCHED();
-    return 0;
-  };
-  for (int l = 0; l < D; ++l)
-    if (int e = colsum(dy + (size_t)l * ACT_BYTES, tile_stride, 32, g->b[l], 0, WID)) return e;
-  if (int e = colsum(dy + (size_t)D * ACT_BYTES, tile_stride, 32, g->b_sigma0, 0, WID)) return e;
-  if (int e = colsum(dy + (size_t)(D + 1) * ACT_BYTES, tile_stride, 32, g->b_sh0, 0, WID)) return e;
-  if (int e = colsum(dy_head, HEAD_BYTES, 4, g->b_sh2, 0, 27)) return e;
-  if (int e = colsum(dy_head, HEAD_BYTES, 4, g->b_sigma2, 31, 1)) return e;
   return 0;
 }
