@@ -123,9 +123,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(device))
     from mc_nerf_b200._lib import lib
     sp, model, loss_fn, opt, batch = build_workload(device, rank, args.precision, args.rays, args.img)
-    net = model
+    net, sync_grads = model, (lambda: None)
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+        if args.allreduce == "ddp":     # exactly the reference's wrapper (main.py:61)
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+        else:                           # one flat-buffer NCCL all-reduce of MLP + camera gradients per step
+            from mc_nerf_b200.parallel import FlatGradAllReduce
+            sync_grads = FlatGradAllReduce(list(model.parameters()))
     dev_batch = tuple(t.to(device) for t in batch)
     host_batch = tuple(t.pin_memory() for t in batch)
 
@@ -134,6 +138,7 @@ def run_ours(args):
         loss_dict, _, _, _ = net(data, 25, STAGE, RATIO)
         loss = loss_fn(loss_dict, STAGE)
         loss.backward()
+        sync_grads()
         opt.step()
         return loss.item() if read_loss else loss
 
@@ -210,8 +215,9 @@ def run_ours(args):
                     data="synthetic",
                     config=dict(workload="BASELINE configs[1]: 110 cameras, 800x800, 4096 rays/batch/GPU, 64 coarse + 128 "
                                          "fine samples, coarse+fine 8x256 MLPs, GLOBAL_OPTIM stage (fwd+loss+bwd+RAdam)",
-                                rays_per_step_per_gpu=args.rays, img=args.img, parallelism=f"dp{world} (rays sharded by image, "
-                                "NCCL allreduce of MLP+camera grads)" if world > 1 else "single GPU",
+                                rays_per_step_per_gpu=args.rays, img=args.img,
+                                parallelism=(f"dp{world}: one camera's {args.rays}-ray batch per rank, {args.allreduce} NCCL "
+                                             "all-reduce of MLP+camera grads") if world > 1 else "single GPU",
                                 l2="per-step working set (activation stash > 3 GB) exceeds the 126 MB L2; no flush needed",
                                 precision=args.precision),
                     e2e=dict(value=round(e2e, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
@@ -278,6 +284,7 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--allreduce", default="flat", choices=["flat", "ddp"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
