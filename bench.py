@@ -151,8 +151,10 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             last = step(data, read_loss)
+        timed.host_ms = (time.perf_counter() - t0) * 1e3 / steps      # CPU time to ISSUE a step (no sync inside)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -169,6 +171,7 @@ def run_ours(args):
         sampler.start()
     n0 = lib().launch_count()
     ms, last = timed(dev_batch, False, args.steps)
+    host_issue_ms = timed.host_ms
     launches = lib().launch_count() - n0
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
@@ -181,11 +184,13 @@ def run_ours(args):
 
     # per-kernel device time of the dominant kernels (CUDA events on the launching stream), 3 extra steps
     roof = None
+    L = lib()
     if rank == 0:
-        L = lib()
         L.profile_begin()
-        for _ in range(3):
-            step(dev_batch, False)
+    for _ in range(3):                 # every rank steps (the step contains the gradient all-reduce)
+        step(dev_batch, False)
+    barrier()
+    if rank == 0:
         prof = L.profile_end()
         from mc_nerf_b200 import render
         n_fine = int(render.LAST["n_rows_dev"].item()) if render.LAST.get("n_rows_dev") is not None else render.LAST["n_rows"]
@@ -222,7 +227,7 @@ def run_ours(args):
                                 precision=args.precision),
                     e2e=dict(value=round(e2e, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                              ms_per_step=round(ms_e2e / args.steps, 3)),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
+                    gpu_launches=int(launches), host_issue_ms_per_step=round(host_issue_ms, 3), clocks=clocks, roofline=roof, cpu_baseline=cpu,
                     loss=float(last.item()) if torch.is_tensor(last) else float(last))
         print(json.dumps(line), flush=True)
     if world > 1:

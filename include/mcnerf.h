@@ -196,6 +196,12 @@ int mcnerf_radam_step(float* p, const float* g, float* exp_avg, float* exp_avg_s
                       float lr, float beta1, float beta2, float eps, float weight_decay,
                       float step_size, int mode, float grad_scale, void* stream);
 
+/* The same update applied to n_tensors tensors sharing all scalars, in one launch per 64 tensors.
+ * p, g, exp_avg, exp_avg_sq, numel are HOST arrays (of device pointers / element counts). */
+int mcnerf_radam_multi(int n_tensors, float* const* p, const float* const* g, float* const* exp_avg,
+                       float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, float step_size, int mode, float grad_scale, void* stream);
+
 /* ------------------------------------------------------------------ NeRF MLP, bf16 tcgen05 path (a8-a12 fused)
  * Throughput path for width-256 networks (depth 2..12, at most one input skip, L = 10, deg 2): sampling +
  * encoding + MLP + SH head fused in one persistent kernel; bf16 operands, fp32 accumulation in TMEM.

@@ -51,6 +51,40 @@ __global__ void radam_k(float* __restrict__ p, const float* __restrict__ g, floa
   }
 }
 
+constexpr int RADAM_MAX_TENSORS = 64;
+struct RadamMulti {
+  int n;
+  float* p[RADAM_MAX_TENSORS];
+  const float* g[RADAM_MAX_TENSORS];
+  float* m[RADAM_MAX_TENSORS];
+  float* v[RADAM_MAX_TENSORS];
+  int64_t numel[RADAM_MAX_TENSORS];
+  int blk_prefix[RADAM_MAX_TENSORS + 1];     // prefix of 256-element blocks per tensor
+};
+
+// One launch for a whole parameter group: block b serves 256 consecutive elements of one tensor.
+__global__ void __launch_bounds__(256) radam_multi_k(const __grid_constant__ RadamMulti a, float lr, float b1, float b2,
+                                                     float eps, float wd, float step_size, int mode, float gscale) {
+  int t = 0;
+  while ((int)blockIdx.x >= a.blk_prefix[t + 1]) ++t;
+  const int64_t i = (int64_t)((int)blockIdx.x - a.blk_prefix[t]) * 256 + threadIdx.x;
+  if (i >= a.numel[t]) return;
+  float* p = a.p[t];
+  float* m = a.m[t];
+  float* v = a.v[t];
+  const float gi = a.g[t][i] * gscale;
+  const float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+  const float mi = m[i] * b1 + (1.f - b1) * gi;
+  v[i] = vi;
+  m[i] = mi;
+  if (mode == 0) return;
+  float pi = p[i];
+  if (wd != 0.f) pi += pi * (-wd * lr);
+  if (mode == 1) pi += (-step_size * lr) * (mi / (sqrtf(vi) + eps));
+  else pi += (-step_size * lr) * mi;
+  p[i] = pi;
+}
+
 }  // namespace
 
 extern "C" int mcnerf_rgb_loss(const float* rgb_c, const float* rgb_f, const float* gt, const int32_t* gt_idx,
@@ -71,5 +105,33 @@ extern "C" int mcnerf_radam_step(float* p, const float* g, float* exp_avg, float
   radam_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                                      step_size, mode, grad_scale);
   MC_LAUNCHED();
+  return 0;
+}
+
+// Same update for up to 64 tensors that share (lr, betas, eps, weight decay, step) in ONE launch; longer lists
+// are processed in slices.  p/g/m/v are HOST arrays of device pointers.
+extern "C" int mcnerf_radam_multi(int n_tensors, float* const* p, const float* const* g, float* const* exp_avg,
+                                  float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2,
+                                  float eps, float weight_decay, float step_size, int mode, float grad_scale,
+                                  void* stream) {
+  MC_ARG(n_tensors >= 0 && mode >= 0 && mode <= 2);
+  if (n_tensors == 0) return 0;
+  MC_ARG(p && g && exp_avg && exp_avg_sq && numel);
+  for (int base = 0; base < n_tensors; base += RADAM_MAX_TENSORS) {
+    RadamMulti a;
+    a.n = n_tensors - base < RADAM_MAX_TENSORS ? n_tensors - base : RADAM_MAX_TENSORS;
+    int blocks = 0;
+    for (int t = 0; t < a.n; ++t) {
+      MC_ARG(p[base + t] && g[base + t] && exp_avg[base + t] && exp_avg_sq[base + t] && numel[base + t] > 0);
+      a.p[t] = p[base + t]; a.g[t] = g[base + t]; a.m[t] = exp_avg[base + t]; a.v[t] = exp_avg_sq[base + t];
+      a.numel[t] = numel[base + t];
+      a.blk_prefix[t] = blocks;
+      blocks += (int)((numel[base + t] + 255) / 256);
+    }
+    for (int t = a.n; t <= RADAM_MAX_TENSORS; ++t) a.blk_prefix[t] = blocks;
+    radam_multi_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, lr, beta1, beta2, eps, weight_decay, step_size, mode,
+                                                             grad_scale);
+    MC_LAUNCHED();
+  }
   return 0;
 }

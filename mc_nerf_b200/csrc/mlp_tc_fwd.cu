@@ -19,28 +19,7 @@ namespace mlptc {
 
 // ----------------------------------------------------------------------------------------- packing
 // dst chunk image for a [N x K] K-major B operand: chunk c (32 k), plane kg (8 k), row n: ((c*4+kg)*N + n)*16 B.
-// value(n,k) = src[n*sn + kk*sk] with the 63->64 pad remap applied to k (pad_k) or n (pad_n).
-__global__ void pack_k(const float* __restrict__ src, int64_t sn, int64_t sk, int N, int K, int pad_k, int pad_n,
-                       int n_valid, int k_valid, __nv_bfloat16* __restrict__ dst) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)N * K) return;
-  int j = i & 7;
-  int64_t t = i >> 3;
-  int n = (int)(t % N);
-  int kgg = (int)(t / N);          // global k-group index (chunk*4 + kg)
-  int k = kgg * 8 + j;
-  int ks = k, ns = n;
-  bool ok = true;
-  if (pad_k) { if (k == 63) ok = false; else if (k > 63) ks = k - 1; }
-  if (pad_n) { if (n == 63) ok = false; else if (n > 63) ns = n - 1; }
-  if (ns >= n_valid || ks >= k_valid) ok = false;
-  dst[i] = __float2bfloat16(ok ? src[ns * sn + ks * sk] : 0.f);
-}
-
-__global__ void pack_bias_k(const float* __restrict__ src, int n, float* __restrict__ dst, int n_pad) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_pad) dst[i] = i < n ? src[i] : 0.f;
-}
+// value(n,k) = src[n*sn + kk*sk] with the 63->64 pad remap applied to k (pad_k) or n (pad_n): see pack_all_k.
 
 // ----------------------------------------------------------------------------------------- plan
 int build_layout(const mcnerf_mlp_params* p, PackLayout* L) {
@@ -125,12 +104,49 @@ int build_layout(const mcnerf_mlp_params* p, PackLayout* L) {
   return 0;
 }
 
-static int pack_matrix(const float* src, int64_t sn, int64_t sk, int N, int K, int pad_k, int pad_n, int n_valid,
-                       int k_valid, void* dst, cudaStream_t st) {
-  int64_t tot = (int64_t)N * K;
-  pack_k<<<cdiv(tot, 256), 256, 0, st>>>(src, sn, sk, N, K, pad_k, pad_n, n_valid, k_valid, (__nv_bfloat16*)dst);
-  MC_LAUNCHED();
-  return 0;
+// One launch packs every matrix of a network: a table of jobs, each thread resolves its job by a linear scan
+// over the (<= 48) element-count prefixes.
+constexpr int MAX_PACK_JOBS = 48;
+struct PackJob {
+  const float* src;
+  int64_t sn, sk;          // source strides of the (n, k) indices (floats); bias jobs: unused
+  int N, K;                // packed extents (bias jobs: N = padded length, K = 1)
+  int pad_k, pad_n, n_valid, k_valid;
+  int is_bias;             // 1: fp32 copy of n_valid floats padded with zeros to N
+  size_t dst_off;          // byte offset in wf / wb (is_bias: float offset in the bias block)
+  int dst_sel;             // 0: wf, 1: wb, 2: bias block
+};
+struct PackArgs {
+  int n_jobs;
+  int64_t prefix[MAX_PACK_JOBS + 1];
+  PackJob j[MAX_PACK_JOBS];
+  uint8_t *wf, *wb;
+  float* bias;
+};
+
+__global__ void __launch_bounds__(256) pack_all_k(const __grid_constant__ PackArgs a) {
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= a.prefix[a.n_jobs]) return;
+  int job = 0;
+  while (gi >= a.prefix[job + 1]) ++job;
+  const PackJob& pj = a.j[job];
+  const int64_t i = gi - a.prefix[job];
+  if (pj.is_bias) {
+    a.bias[pj.dst_off + i] = i < pj.n_valid ? pj.src[i] : 0.f;
+    return;
+  }
+  const int N = pj.N;
+  const int j = (int)(i & 7);
+  const int64_t t = i >> 3;
+  const int n = (int)(t % N);
+  const int k = (int)(t / N) * 8 + j;
+  int ks = k, ns = n;
+  bool ok = true;
+  if (pj.pad_k) { if (k == 63) ok = false; else if (k > 63) ks = k - 1; }
+  if (pj.pad_n) { if (n == 63) ok = false; else if (n > 63) ns = n - 1; }
+  if (ns >= pj.n_valid || ks >= pj.k_valid) ok = false;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>((pj.dst_sel == 0 ? a.wf : a.wb) + pj.dst_off);
+  dst[i] = __float2bfloat16(ok ? pj.src[ns * pj.sn + ks * pj.sk] : 0.f);
 }
 
 // ----------------------------------------------------------------------------------------- forward kernel
@@ -434,9 +450,20 @@ extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb
   if (int e = build_layout(p, &L)) return e;
   MC_ARG(wf && bias);
   cudaStream_t st = (cudaStream_t)stream;
-  uint8_t* f = (uint8_t*)wf;
-  uint8_t* b = (uint8_t*)wb;
   const int D = p->depth;
+  PackArgs a;
+  a.wf = (uint8_t*)wf; a.wb = (uint8_t*)wb; a.bias = bias;
+  int nj = 0;
+  int64_t tot = 0;
+  auto add = [&](const float* src, int64_t sn, int64_t sk, int N, int K, int pad_k, int pad_n, int n_valid, int k_valid,
+                 int is_bias, size_t dst_off, int dst_sel) {
+    PackJob& j = a.j[nj];
+    j.src = src; j.sn = sn; j.sk = sk; j.N = N; j.K = K; j.pad_k = pad_k; j.pad_n = pad_n; j.n_valid = n_valid;
+    j.k_valid = k_valid; j.is_bias = is_bias; j.dst_off = dst_off; j.dst_sel = dst_sel;
+    a.prefix[nj] = tot;
+    tot += (int64_t)N * K;
+    ++nj;
+  };
   for (int s = 0; s < L.fwd.n_steps; ++s) {
     const Step& sp = L.fwd.s[s];
     const float* W;
@@ -452,24 +479,23 @@ extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb
     else { W = p->W_sh2; bs = p->b_sh2; k_in = WID; ld = WID; n_out = 27; }
     const int K = sp.n_chunks * KC;
     // forward image: rows n = output feature, reduction k = input feature (padded)
-    if (int e = pack_matrix(W, ld, 1, sp.N, K, pad, 0, n_out, k_in, f + sp.w_off, st)) return e;
+    add(W, ld, 1, sp.N, K, pad, 0, n_out, k_in, 0, sp.w_off, 0);
     // dgrad images: rows n = input feature, reduction k = output feature (sp.N, zero beyond n_out)
-    if (b) {
-      if (sp.a_src == A_ENC) {
-        if (int e = pack_matrix(W, 1, ld, ENCW, sp.N, 0, 1, 63, n_out, b + L.wb_main[s], st)) return e;
-      } else if (sp.a_src == A_ENC_ACT) {
-        if (int e = pack_matrix(W, 1, ld, ENCW, sp.N, 0, 1, 63, n_out, b + L.wb_enc[s], st)) return e;
-        if (int e = pack_matrix(W + 63, 1, ld, WID, sp.N, 0, 0, WID, n_out, b + L.wb_main[s], st)) return e;
-      } else {
-        if (int e = pack_matrix(W, 1, ld, WID, sp.N, 0, 0, WID, n_out, b + L.wb_main[s], st)) return e;
-      }
+    if (wb) {
+      if (sp.a_src == A_ENC) add(W, 1, ld, ENCW, sp.N, 0, 1, 63, n_out, 0, L.wb_main[s], 1);
+      else if (sp.a_src == A_ENC_ACT) {
+        add(W, 1, ld, ENCW, sp.N, 0, 1, 63, n_out, 0, L.wb_enc[s], 1);
+        add(W + 63, 1, ld, WID, sp.N, 0, 0, WID, n_out, 0, L.wb_main[s], 1);
+      } else add(W, 1, ld, WID, sp.N, 0, 0, WID, n_out, 0, L.wb_main[s], 1);
     }
-    pack_bias_k<<<1, 256, 0, st>>>(bs, n_out, bias + sp.bias_off, 256);
-    MC_LAUNCHED();
+    add(bs, 0, 0, 256, 1, 0, 0, n_out, 0, 1, sp.bias_off, 2);
   }
-  pack_bias_k<<<1, 256, 0, st>>>(p->W_sigma2, WID, bias + L.sig2_off, 256);
-  MC_LAUNCHED();
-  pack_bias_k<<<1, 32, 0, st>>>(p->b_sigma2, 1, bias + L.sig2_off + 256, 8);
+  add(p->W_sigma2, 0, 0, 256, 1, 0, 0, WID, 0, 1, L.sig2_off, 2);
+  add(p->b_sigma2, 0, 0, 8, 1, 0, 0, 1, 0, 1, L.sig2_off + 256, 2);
+  MC_ARG(nj <= MAX_PACK_JOBS);
+  a.prefix[nj] = tot;
+  a.n_jobs = nj;
+  pack_all_k<<<cdiv(tot, 256), 256, 0, st>>>(a);
   MC_LAUNCHED();
   return 0;
 }

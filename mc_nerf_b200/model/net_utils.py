@@ -77,6 +77,7 @@ class RAdam(Optimizer):
         stream = ops._stream()
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
+            by_step = {}                     # tensors that share a step count share every scalar of the update
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -90,18 +91,26 @@ class RAdam(Optimizer):
                     state["exp_avg"] = torch.zeros_like(p)
                     state["exp_avg_sq"] = torch.zeros_like(p)
                 state["step"] += 1
-                buffered = group["buffer"][int(state["step"] % 10)]
-                if state["step"] == buffered[0]:
+                by_step.setdefault(state["step"], []).append((p, state))
+            for step, items in by_step.items():
+                buffered = group["buffer"][int(step % 10)]
+                if step == buffered[0]:
                     n_sma, step_size = buffered[1], buffered[2]
                 else:
-                    buffered[0] = state["step"]
-                    n_sma, step_size = self.schedule(state["step"], beta1, beta2, self.degenerated_to_sgd)
+                    buffered[0] = step
+                    n_sma, step_size = self.schedule(step, beta1, beta2, self.degenerated_to_sgd)
                     buffered[1], buffered[2] = n_sma, step_size
                 mode = 1 if n_sma >= 5 else (2 if step_size > 0 else 0)
-                g = p.grad.contiguous()
-                lib().call("mcnerf_radam_step", ops._p(p), ops._p(g), ops._p(state["exp_avg"]),
-                           ops._p(state["exp_avg_sq"]), p.numel(), float(group["lr"]), float(beta1), float(beta2),
-                           float(group["eps"]), float(group["weight_decay"]), float(step_size), mode, 1.0, stream)
+                n = len(items)
+                grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p, _ in items]
+                vp = ctypes.c_void_p * n
+                lib().call("mcnerf_radam_multi", n,
+                           vp(*[p.data_ptr() for p, _ in items]), vp(*[g.data_ptr() for g in grads]),
+                           vp(*[st["exp_avg"].data_ptr() for _, st in items]),
+                           vp(*[st["exp_avg_sq"].data_ptr() for _, st in items]),
+                           (ctypes.c_int64 * n)(*[p.numel() for p, _ in items]),
+                           float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
+                           float(group["weight_decay"]), float(step_size), mode, 1.0, stream)
         return loss
 
 

@@ -117,6 +117,17 @@ def _branch_bwd(cfg, net, tensors, grads, rays_o, rays_d, jitter, S, band_w, sel
                _p(g_rays_o), _p(g_rays_d), _stream())
 
 
+def _flat_zero_grads(tensors):
+    """zero gradients for every tensor of a network as views of ONE zero-filled buffer (1 fill instead of 24)."""
+    total = sum(v.numel() for v in tensors.values())
+    flat = torch.zeros(total, dtype=torch.float32, device=next(iter(tensors.values())).device)
+    out, off = {}, 0
+    for k, v in tensors.items():
+        out[k] = flat[off:off + v.numel()].view_as(v)
+        off += v.numel()
+    return out
+
+
 def select_and_cap(cfg, out_c, noise_sel, jitter, B, train, cap_perm=None):
     """Selection weights with their own noise draw, device-side compaction; the reference's train-only
     128-per-ray cap (model/mc_nerf.py:630-632) is reproduced when it can trigger (Sf > 128)."""
@@ -189,8 +200,7 @@ class RenderFn(torch.autograd.Function):
         rays_d, rays_o, jitter, noise_c, noise_f, out_c, saved_c, sel_idx, n_rows_dev, dense, saved_f, out_sel = ctx.saved
         B, dev = rays_d.shape[0], rays_d.device
         tc, tf = ctx.tc, ctx.tf
-        gc = {k: torch.zeros_like(v) for k, v in tc.items()}
-        gf = {k: torch.zeros_like(v) for k, v in tf.items()}
+        gc, gf = _flat_zero_grads(tc), _flat_zero_grads(tf)
         g_o = torch.zeros_like(rays_o)
         g_d = torch.zeros_like(rays_d)
         if g_rgb_f is not None and n_rows > 0:
