@@ -239,12 +239,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
         tc::tcgen05_fence_after();
         if (jb.kind == BK_MASK_STORE) {
           uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES;
-#pragma unroll
-          for (int cg = 0; cg < WID / 32; ++cg) {
-            uint32_t v[32];
-            tc::tmem_ld32(taddr + cg * 32, v);
-            tc::tmem_ld_wait();
-            const uint32_t gb = gate[cg];
+          auto block = [&](const uint32_t (&v)[32], int cg, uint32_t gb) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
@@ -255,6 +250,17 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
               sts_v4(bufX_t + (cg * 4 + j) * PLANE + q * 16, o);
               if (tile_ok) *reinterpret_cast<uint4*>(dyo + stash_off(q, cg * 4 + j, 32)) = o;
             }
+          };
+          uint32_t va[32], vb[32];
+          tc::tmem_ld32(taddr, va);
+#pragma unroll
+          for (int cg = 0; cg < WID / 32; cg += 2) {
+            tc::tmem_ld_wait();
+            tc::tmem_ld32(taddr + (cg + 1) * 32, vb);
+            block(va, cg, gate[cg]);
+            tc::tmem_ld_wait();
+            if (cg + 2 < WID / 32) tc::tmem_ld32(taddr + (cg + 2) * 32, va);
+            block(vb, cg + 1, gate[cg + 1]);
           }
         } else if (jb.kind == BK_SIGMA_INJECT) {
           // d relu(sigma.0) pre-activation = g_sigma * w_sigma2 gated by the forward gate bits; the accumulator

@@ -371,11 +371,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
           const float* w2 = a.bias + a.sig2_off;
           float dot = 0.f;
           uint32_t gate[8];
-#pragma unroll 1
-          for (int cg = 0; cg < WID / 32; ++cg) {
-            uint32_t v[32];
-            tc::tmem_ld32(taddr + cg * 32, v);
-            tc::tmem_ld_wait();
+          // one 32-column block of the accumulator: +bias, ReLU, bf16, -> next A operand (smem) / stash / sigma dot
+          auto block = [&](const uint32_t (&v)[32], int cg) {
             uint32_t gbits = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -402,6 +399,18 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) if (TRAIN && i == cg) gate[i] = gbits;
+          };
+          // software pipeline: the TMEM load of block cg+1 is in flight while block cg is processed
+          uint32_t va[32], vb[32];
+          tc::tmem_ld32(taddr, va);
+#pragma unroll 1
+          for (int cg = 0; cg < WID / 32; cg += 2) {
+            tc::tmem_ld_wait();
+            tc::tmem_ld32(taddr + (cg + 1) * 32, vb);
+            block(va, cg);
+            tc::tmem_ld_wait();
+            if (cg + 2 < WID / 32) tc::tmem_ld32(taddr + (cg + 2) * 32, va);
+            block(vb, cg + 1);
           }
           if (st_tile) {
             uint4* gp = reinterpret_cast<uint4*>(a.stash_bits + ((size_t)tile * a.n_slots + st.stash_slot) * BITS_BYTES + q * 32);

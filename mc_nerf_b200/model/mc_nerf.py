@@ -93,6 +93,7 @@ class MC_Model(nn.Module):
         loss_dict = {}
         gt_rgbs, img_id, intr_wpts, intr_pts, extr_wpts, extr_pts, epoch, epoch_type, cur_ratio = \
             self.data2device(*args)
+        img_id_host = args[0][1]            # camera id as the loader produced it (CPU tensor in main.py): no sync
         if epoch_type == "CAM_PARAM_EPOCH":          # ref: model/mc_nerf.py:64-71
             self.nerf.emmbedding_xyz.barf_mode = False
             self.intr_adj, self.pose_adj, self.calib_pose_adj = self.add_weights2param(True, True, True)
@@ -104,14 +105,16 @@ class MC_Model(nn.Module):
             self.nerf.emmbedding_xyz.barf_mode = glob
             self.intr_adj, self.pose_adj, self.calib_pose_adj = self.add_weights2param(True, glob, True)
             reproj = self.get_reproject_pixels(intr_wpts, self.intr_adj, self.calib_pose_adj)
-            rays_d, rays_o, rand_idx = self.generate_train_rays(img_id)
+            rays_d, rays_o, rand_idx = self.generate_train_rays(img_id_host)
             rgbs_c, rgbs_f = self.nerf(rays_d, rays_o, epoch, cur_ratio if glob else 1)
             gt_sel = gt_rgbs.reshape(-1, 3)[rand_idx]
             loss_dict["intr"] = [reproj, intr_pts]
             loss_dict["rgb"] = [rgbs_c, rgbs_f, gt_sel]
             self.opt_idx = 1 if glob else 2
-        rays_valid = _LazyValidRays(self, img_id)
-        intr_show = [self.intr_train.to(self.device).detach(), self.intr_adj.detach()]
+        rays_valid = _LazyValidRays(self, img_id_host)
+        if self.__dict__.get("_intr_train_dev") is None:
+            self.__dict__["_intr_train_dev"] = self.intr_train.to(self.device).detach()
+        intr_show = [self._intr_train_dev, self.intr_adj.detach()]
         pose_show = [self.gt_pose.detach(), self.pose_adj.detach()]
         self.last_epoch_type = epoch_type
         return loss_dict, intr_show, pose_show, rays_valid
@@ -129,17 +132,21 @@ class MC_Model(nn.Module):
         return torch.cat(rgbs, 0).cpu(), torch.cat(depth, 0).cpu(), torch.cat(opacity, 0).cpu()
 
     # ------------------------------------------------------------------ rays
-    def _cam_index(self, img_id):
-        if torch.is_tensor(img_id):
-            return int(img_id.reshape(-1)[0].item())
+    def _cam_index(self, img_id, n_rays=None):
+        """Camera selector for the ray kernels: a Python int when the id lives on the host, otherwise a per-ray
+        int32 device tensor - never a device->host synchronisation (the reference indexes `pose[img_id]` on device)."""
         if isinstance(img_id, (tuple, list)):
-            return self._cam_index(img_id[0])
+            return self._cam_index(img_id[0], n_rays)
+        if torch.is_tensor(img_id):
+            if not img_id.is_cuda:
+                return int(img_id.reshape(-1)[0])
+            return img_id.reshape(-1)[:1].to(torch.int32).expand(n_rays).contiguous()
         return int(img_id)
 
     def get_rays(self, pose, img_id, intr_inv):
         """All H*W rays of camera img_id, row-major pixels with +0.5 centres.  ref: model/mc_nerf.py:124-145."""
-        cam = self._cam_index(img_id)
         n = self.img_h * self.img_w
+        cam = self._cam_index(img_id, n)
         rays_o, rays_d = ops.RaygenFn.apply(intr_inv.to(self.device), pose, cam, None, n, self.img_w)
         return rays_d, rays_o
 
@@ -148,7 +155,7 @@ class MC_Model(nn.Module):
         rays are generated, straight from (camera, pixel)."""
         n = self.img_h * self.img_w
         rand_idx = torch.randperm(n, device=self.device)[:self.batch]
-        cam = self._cam_index(img_id)
+        cam = self._cam_index(img_id, rand_idx.shape[0])
         rays_o, rays_d = ops.RaygenFn.apply(self.inverse_intrinsic(self.intr_adj), self.pose_adj, cam,
                                             rand_idx.to(torch.int32), rand_idx.shape[0], self.img_w)
         self.count_rays += 1
@@ -269,11 +276,14 @@ class MC_Model(nn.Module):
             self.register_parameter(name, nn.Parameter(torch.ones(shape, device=self.device), requires_grad=True))
 
     def data2device(self, *args):
+        dev = torch.device(self.device)
+
+        def mv(t):
+            return t if t.device == dev or (t.is_cuda and dev.type == "cuda" and dev.index is None) \
+                else t.to(dev, non_blocking=True)
         gt_rgbs, img_id, intr_wpts, intr_pts, extr_wpts, extr_pts = args[0]
-        dev = self.device
-        return (gt_rgbs.to(dev, non_blocking=True), img_id.to(dev), intr_wpts.to(dev, non_blocking=True),
-                intr_pts.to(dev, non_blocking=True), extr_wpts.to(dev, non_blocking=True),
-                extr_pts.to(dev, non_blocking=True), args[1], args[2], args[3])
+        return (mv(gt_rgbs), mv(img_id), mv(intr_wpts), mv(intr_pts), mv(extr_wpts), mv(extr_pts),
+                args[1], args[2], args[3])
 
     # ------------------------------------------------------------------ epoch-end reporting (not hot path)
     def show_estimate_param(self, intr_show, pose_show, epoch, epoch_type):

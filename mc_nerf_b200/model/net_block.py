@@ -58,9 +58,14 @@ class CorseFine_NeRF(nn.Module):
                                 nn.Linear(self.width, 3 * (self.deg + 1) ** 2))
 
     def param_dict(self):
-        """reference state_dict name -> Parameter, in ops.param_names order."""
-        sd = dict(self.named_parameters())
-        return {k: sd[k] for k in ops.param_names(self.depth)}
+        """reference state_dict name -> Parameter, in ops.param_names order (cached: Parameter objects are stable
+        under .to(), load_state_dict and optimiser updates, which all work in place on .data)."""
+        pd = self.__dict__.get("_param_dict")
+        if pd is None:
+            sd = dict(self.named_parameters())
+            pd = {k: sd[k] for k in ops.param_names(self.depth)}
+            self.__dict__["_param_dict"] = pd
+        return pd
 
     def cfg(self):
         return (self.depth, self.width, tuple(self.skips))

@@ -13,7 +13,11 @@ from ._lib import CompositeCfg, Dirs, MlpGrads, MlpParams, Sampling, TcInput, li
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """current CUDA stream of the current device as a raw cudaStream_t (fast path: no Stream object is built)."""
+    try:
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+    except AttributeError:      # private helpers moved: fall back to the public API
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def _p(t, dtype=torch.float32):
@@ -34,6 +38,8 @@ def _c(t):
 
 
 def _f32(t):
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t.detach()
     return t.detach().to(torch.float32).contiguous()
 
 
