@@ -39,7 +39,7 @@ struct __align__(16) BwdBars {
   uint64_t w_full[NSTAGE], w_empty[NSTAGE], a_ready[2], acc_full[2];
   uint32_t tmem_base;
 };
-constexpr int SMEM_BWD = 2 * ACT_BYTES + 2 * HEAD_BYTES + NSTAGE * STAGE_BYTES + 256;
+constexpr int SMEM_BWD = 2 * ACT_BYTES + 2 * HEAD_BYTES + NSTAGE * STAGE_BYTES + 1024 + 256;
 
 __constant__ float bC0 = 0.28209479177387814f;
 __constant__ float bC1 = 0.4886025119029199f;
@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
   uint8_t* bufX = smem;                                    // [2][ACT_BYTES]  dY tile (A operand)
   uint8_t* small = smem + 2 * ACT_BYTES;                   // [2][HEAD_BYTES] head-gradient tile
   uint8_t* wst = small + 2 * HEAD_BYTES;                   // [NSTAGE][STAGE_BYTES]
-  BwdBars* bars = reinterpret_cast<BwdBars*>(wst + NSTAGE * STAGE_BYTES);
+  float* w2s = reinterpret_cast<float*>(wst + NSTAGE * STAGE_BYTES);     // w_sigma2 [256] (no L1 left: keep it on chip)
+  BwdBars* bars = reinterpret_cast<BwdBars*>(w2s + 256);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   const int n_tiles = (rows + TM - 1) / TM;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
     tc::mbar_init_fence();
   }
   if (warp == 9) tc::tmem_alloc(&bars->tmem_base, 512);
+  if (tid < 256) w2s[tid] = a.bias[a.sig2_off + tid];
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
     const int q = tid - t * 128;
     const uint32_t bufX_t = tc::smem_u32(bufX + t * ACT_BYTES), small_t = tc::smem_u32(small + t * HEAD_BYTES);
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * 256;
-    const float* w2 = a.bias + a.sig2_off;
+    const float* w2 = w2s;
     uint32_t par = 0;
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int tile = 2 * pair + t;
@@ -268,8 +270,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
           uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES;
 #pragma unroll
           for (int kg = 0; kg < WID / 8; ++kg) {
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(w2 + kg * 8));
-            const float4 s1 = __ldg(reinterpret_cast<const float4*>(w2 + kg * 8 + 4));
+            const float4 s0 = *reinterpret_cast<const float4*>(w2 + kg * 8);
+            const float4 s1 = *reinterpret_cast<const float4*>(w2 + kg * 8 + 4);
             const uint32_t gb = gate[kg >> 2];
             const int pos = (kg & 3) * 8;
             uint4 o;

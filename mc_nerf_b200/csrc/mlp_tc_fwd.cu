@@ -155,6 +155,7 @@ struct FwdArgs {
   const uint8_t* wpack;
   const float* bias;
   int sig2_off;
+  int bias_floats;
   const float *rays_o, *rays_d, *jitter;
   mcnerf_sampling smp;
   const int32_t* sel_idx;
@@ -171,12 +172,17 @@ struct FwdArgs {
   int n_slots;
 };
 
+// The forward kernel trades one ring stage for an on-chip copy of every bias (+ w_sigma2): with 224 KB of the
+// 228 KB L1/shared array carved out as shared memory there is practically no L1 left, so __ldg'd biases came
+// from L2 (~300 cycles) inside the epilogue's dependent chain.
+constexpr int FSTAGE = 3;
+constexpr int BIAS_SMEM_FLOATS = (12 + 3) * 256 + 264;     // deepest supported network
 struct __align__(16) SmemBars {
-  uint64_t w_full[NSTAGE], w_empty[NSTAGE], a_ready[2], acc_full[2];
+  uint64_t w_full[FSTAGE], w_empty[FSTAGE], a_ready[2], acc_full[2];
   uint32_t tmem_base;
 };
 
-constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + NSTAGE * STAGE_BYTES + 256;
+constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + FSTAGE * STAGE_BYTES + BIAS_SMEM_FLOATS * 4 + 256;
 
 __constant__ float cC0 = 0.28209479177387814f;
 __constant__ float cC1 = 0.4886025119029199f;
@@ -235,8 +241,9 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;                                   // [2][ACT_BYTES]
   uint8_t* enc = smem + 2 * ACT_BYTES;                   // [2][ENC_BYTES]
-  uint8_t* wst = enc + 2 * ENC_BYTES;                    // [NSTAGE][STAGE_BYTES]
-  SmemBars* bars = reinterpret_cast<SmemBars*>(wst + NSTAGE * STAGE_BYTES);
+  uint8_t* wst = enc + 2 * ENC_BYTES;                    // [FSTAGE][STAGE_BYTES]
+  float* bias_s = reinterpret_cast<float*>(wst + FSTAGE * STAGE_BYTES);
+  SmemBars* bars = reinterpret_cast<SmemBars*>(bias_s + BIAS_SMEM_FLOATS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   const int n_tiles = (rows + TM - 1) / TM;
@@ -244,11 +251,12 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
   const int n_steps = a.plan.n_steps;
 
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < FSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 128); tc::mbar_init(&bars->acc_full[i], 1); }
     tc::mbar_init_fence();
   }
   if (warp == 9) tc::tmem_alloc(&bars->tmem_base, 512);
+  for (int i = tid; i < a.bias_floats; i += blockDim.x) bias_s[i] = a.bias[i];
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
@@ -268,7 +276,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
               tc::mbar_wait(&bars->w_empty[stage], par ^ 1);
               tc::mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
               tc::bulk_g2s(wst + stage * STAGE_BYTES, a.wpack + st.w_off + (size_t)c * bytes, bytes, &bars->w_full[stage]);
-              if (++stage == NSTAGE) { stage = 0; par ^= 1; }
+              if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             }
         }
     }
@@ -301,7 +309,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
                 tc::umma_bf16(tmem + t * 256, da, db, idesc, (c | kk) != 0);
               }
               tc::umma_commit(&bars->w_empty[stage]);
-              if (++stage == NSTAGE) { stage = 0; par ^= 1; }
+              if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             }
             tc::umma_commit(&bars->acc_full[t]);
           }
@@ -329,7 +337,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
         tc::mbar_wait(&bars->acc_full[t], par);
         par ^= 1;
         tc::tcgen05_fence_after();
-        const float* bias = a.bias + st.bias_off;
+        const float* bias = bias_s + st.bias_off;
         if (st.epi == EPI_OUT) {
           uint32_t v[32];
           tc::tmem_ld32(taddr, v);
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
           if (valid) {
             float sh[27];
 #pragma unroll
-            for (int i = 0; i < 27; ++i) sh[i] = __uint_as_float(v[i]) + __ldg(bias + i);
+            for (int i = 0; i < 27; ++i) sh[i] = __uint_as_float(v[i]) + bias[i];
             const float* dp;
             if (a.x_enc) dp = a.dirs_rows + (size_t)row_g * 3;
             else {
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
                                  ? a.stash + ((size_t)tile * a.n_slots + st.stash_slot) * ACT_BYTES
                                  : nullptr;
           const bool to_smem = st.epi == EPI_RELU;
-          const float* w2 = a.bias + a.sig2_off;
+          const float* w2 = bias_s + a.sig2_off;
           float dot = 0.f;
           uint32_t gate[8];
           // one 32-column block of the accumulator: +bias, ReLU, bf16, -> next A operand (smem) / stash / sigma dot
@@ -377,8 +385,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float x[8];
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cg * 32 + j * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cg * 32 + j * 8 + 4));
+              const float4 b0 = *reinterpret_cast<const float4*>(bias + cg * 32 + j * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias + cg * 32 + j * 8 + 4);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -386,8 +394,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
                 if (TRAIN) gbits |= (x[i] > 0.f ? 1u : 0u) << (j * 8 + i);
               }
               if (!to_smem) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8 + 4));
+                const float4 s0 = *reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8);
+                const float4 s1 = *reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8 + 4);
                 dot += x[0] * s0.x + x[1] * s0.y + x[2] * s0.z + x[3] * s0.w + x[4] * s1.x + x[5] * s1.y + x[6] * s1.z +
                        x[7] * s1.w;
               }
@@ -417,7 +425,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
             gp[0] = make_uint4(gate[0], gate[1], gate[2], gate[3]);
             gp[1] = make_uint4(gate[4], gate[5], gate[6], gate[7]);
           }
-          if (!to_smem) sigma_raw = dot + __ldg(w2 + 256);
+          if (!to_smem) sigma_raw = dot + w2[256];
         }
         if (s + 1 < n_steps) {
           tc::fence_proxy_async();
@@ -529,6 +537,8 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   a.wpack = (const uint8_t*)wf;
   a.bias = bias;
   a.sig2_off = L.sig2_off;
+  a.bias_floats = L.bias_floats;
+  MC_ARG(L.bias_floats <= BIAS_SMEM_FLOATS);
   a.rays_o = in->rays_o; a.rays_d = in->rays_d; a.jitter = in->jitter; a.smp = in->smp;
   a.sel_idx = in->sample_idx; a.n_rows = in->n_rows; a.n_rows_dev = in->n_rows_dev;
   a.x_enc = in->x_enc; a.ld_enc = in->ld_enc; a.dirs_rows = in->dirs_rows;
