@@ -68,9 +68,11 @@ __device__ __forceinline__ bool seg_reduce(int key, float (&v)[NV], int lane) {
 }
 
 __device__ __forceinline__ uint32_t relu_gate2(uint32_t bits, int pos, float lo, float hi) {
-  // bits: forward ReLU gate word (bit c set <=> activation c of this 32-column block was > 0)
-  float a = (bits >> pos & 1u) ? lo : 0.f;
-  float b = (bits >> (pos + 1) & 1u) ? hi : 0.f;
+  // bits: forward ReLU gate word of a 32-column block; element e = 2k+h (k = pair index, h = 0 lo / 1 hi) is at
+  // bit k + 16h (tc::gate_bits).  `pos` = index of the lo element within the block (even).
+  const int k = pos >> 1;
+  float a = (bits >> k & 1u) ? lo : 0.f;
+  float b = (bits >> (16 + k) & 1u) ? hi : 0.f;
   return tc::pack_bf16(a, b);
 }
 

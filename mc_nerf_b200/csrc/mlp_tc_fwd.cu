@@ -13,6 +13,7 @@
 //                     alternating slots per layer so one slot's epilogue overlaps the other slot's MMAs
 // Weights are re-streamed from L2 per tile (1.26 MB per net: L2 resident); activations never touch HBM in
 // inference; in training each layer's bf16 activation tile is also written to the stash for the backward pass.
+#include <stdlib.h>
 #include "mlp_tc.cuh"
 
 namespace mlptc {
@@ -156,6 +157,7 @@ struct FwdArgs {
   const float* bias;
   int sig2_off;
   int bias_floats;
+  int debug;             // timing experiments only (MCNERF_TC_DEBUG): 1 = epilogue skips math/stores, 2 = skips TMEM loads
   const float *rays_o, *rays_d, *jitter;
   mcnerf_sampling smp;
   const int32_t* sel_idx;
@@ -182,7 +184,11 @@ struct __align__(16) SmemBars {
   uint32_t tmem_base;
 };
 
-constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + FSTAGE * STAGE_BYTES + BIAS_SMEM_FLOATS * 4 + 256;
+constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + FSTAGE * STAGE_BYTES + BIAS_SMEM_FLOATS * 4 + 1024 + 256;
+// 18 warps: 8 epilogue warps per tile slot (two per TMEM lane quarter, splitting the 32-column blocks even/odd:
+// a single warp per scheduler cannot hide its own ALU/LDS latency), 1 weight producer, 1 MMA issuer.
+constexpr int FWD_THREADS = 576;
+constexpr int W_PROD = 16, W_MMA = 17;
 
 __constant__ float cC0 = 0.28209479177387814f;
 __constant__ float cC1 = 0.4886025119029199f;
@@ -237,55 +243,64 @@ __device__ __forceinline__ void encode_row(const FwdArgs& a, int row_g, bool val
 }
 
 template <bool TRAIN>
-__global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_constant__ FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;                                   // [2][ACT_BYTES]
   uint8_t* enc = smem + 2 * ACT_BYTES;                   // [2][ENC_BYTES]
   uint8_t* wst = enc + 2 * ENC_BYTES;                    // [FSTAGE][STAGE_BYTES]
   float* bias_s = reinterpret_cast<float*>(wst + FSTAGE * STAGE_BYTES);
-  SmemBars* bars = reinterpret_cast<SmemBars*>(bias_s + BIAS_SMEM_FLOATS);
+  float* sig_part = bias_s + BIAS_SMEM_FLOATS;           // [2 slots][128 rows] partial sigma.2 dot of warp set 1
+  SmemBars* bars = reinterpret_cast<SmemBars*>(sig_part + 256);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   const int n_tiles = (rows + TM - 1) / TM;
   const int n_pairs = (n_tiles + 1) / 2;
   const int n_steps = a.plan.n_steps;
+  // CTA pairs (cluster of 2) share the weight stream: each CTA fetches half of every chunk and multicasts it to
+  // both, halving the L2 -> SM weight traffic that bounded the single-CTA version.  Both CTAs therefore run the
+  // same number of tile-pair iterations (surplus iterations work on an all-invalid tile).
+  const uint32_t crank = tc::cluster_ctarank();
+  const int n_iter = (n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (tid == 0) {
-    for (int i = 0; i < FSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 128); tc::mbar_init(&bars->acc_full[i], 1); }
+    for (int i = 0; i < FSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 256); tc::mbar_init(&bars->acc_full[i], 1); }
     tc::mbar_init_fence();
   }
-  if (warp == 9) tc::tmem_alloc(&bars->tmem_base, 512);
+  if (warp == W_MMA) tc::tmem_alloc(&bars->tmem_base, 512);
   for (int i = tid; i < a.bias_floats; i += blockDim.x) bias_s[i] = a.bias[i];
   tc::tcgen05_fence_before();
   __syncthreads();
+  tc::cluster_sync();            // peer barriers are initialised before anything is multicast into this CTA
   tc::tcgen05_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 8) {
+  if (warp == W_PROD) {
     // ------------------------------------------------------------------ weight producer
     if (lane == 0) {
       int stage = 0;
       uint32_t par = 0;
-      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+      for (int it = 0; it < n_iter; ++it)
         for (int s = 0; s < n_steps; ++s) {
           const Step& st = a.plan.s[s];
-          const uint32_t bytes = (uint32_t)st.N * KC * 2;
+          const uint32_t bytes = (uint32_t)st.N * KC * 2, half = bytes / 2;
           for (int t = 0; t < 2; ++t)
             for (int c = 0; c < st.n_chunks; ++c) {
-              tc::mbar_wait(&bars->w_empty[stage], par ^ 1);
+              tc::mbar_wait(&bars->w_empty[stage], par ^ 1);       // both CTAs are done with this stage
               tc::mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
-              tc::bulk_g2s(wst + stage * STAGE_BYTES, a.wpack + st.w_off + (size_t)c * bytes, bytes, &bars->w_full[stage]);
+              tc::bulk_g2s_multicast(wst + stage * STAGE_BYTES + crank * half,
+                                     a.wpack + st.w_off + (size_t)c * bytes + crank * half, half,
+                                     &bars->w_full[stage], (uint16_t)3);
               if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             }
         }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       int stage = 0;
       uint32_t par = 0, apar[2] = {0, 0};
-      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+      for (int it = 0; it < n_iter; ++it)
         for (int s = 0; s < n_steps; ++s) {
           const Step& st = a.plan.s[s];
           const uint32_t idesc = tc::umma_idesc_bf16(TM, st.N);
@@ -308,7 +323,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
                 uint64_t db = tc::umma_desc(b_base + kk * 2 * st.N * 16, st.N * 16, 128);
                 tc::umma_bf16(tmem + t * 256, da, db, idesc, (c | kk) != 0);
               }
-              tc::umma_commit(&bars->w_empty[stage]);
+              tc::umma_commit_multicast(&bars->w_empty[stage], (uint16_t)3);
               if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             }
             tc::umma_commit(&bars->acc_full[t]);
@@ -317,17 +332,19 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
     }
   } else {
     // ------------------------------------------------------------------ input stage + epilogues (slot t)
-    const int t = warp >> 2;
-    const int q = tid - t * 128;                      // row in tile == TMEM lane
+    const int t = warp >> 3;
+    const int set = (warp >> 2) & 1;                  // which half of the 32-column blocks this warp owns
+    const int q = (warp & 3) * 32 + lane;             // row in tile == TMEM lane
     const uint32_t act_t = tc::smem_u32(act + t * ACT_BYTES), enc_t = tc::smem_u32(enc + t * ENC_BYTES);
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * 256;
     uint32_t par = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int it = 0; it < n_iter; ++it) {
+      const int pair = blockIdx.x + it * gridDim.x;
       const int tile = 2 * pair + t;
       const int row_g = tile * TM + q;
-      const bool valid = row_g < rows;
+      const bool valid = tile < n_tiles && row_g < rows;
       uint8_t* st_enc = (TRAIN && tile < n_tiles) ? a.stash_enc + (size_t)tile * ENC_BYTES : nullptr;
-      encode_row(a, row_g, valid, enc_t, q, st_enc);
+      if (set == 0) encode_row(a, row_g, valid, enc_t, q, st_enc);
       tc::fence_proxy_async();
       tc::tcgen05_fence_before();
       tc::mbar_arrive(&bars->a_ready[t]);
@@ -339,9 +356,11 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
         tc::tcgen05_fence_after();
         const float* bias = bias_s + st.bias_off;
         if (st.epi == EPI_OUT) {
+          if (set != 0) continue;            // last step: nothing to arrive on
           uint32_t v[32];
           tc::tmem_ld32(taddr, v);
           tc::tmem_ld_wait();
+          sigma_raw += sig_part[t * 128 + q];
           if (valid) {
             float sh[27];
 #pragma unroll
@@ -378,54 +397,74 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
           const bool to_smem = st.epi == EPI_RELU;
           const float* w2 = bias_s + a.sig2_off;
           float dot = 0.f;
-          uint32_t gate[8];
+          uint32_t* gate_out = st_tile ? reinterpret_cast<uint32_t*>(a.stash_bits + ((size_t)tile * a.n_slots + st.stash_slot) * BITS_BYTES + q * 32)
+                                       : nullptr;
           // one 32-column block of the accumulator: +bias, ReLU, bf16, -> next A operand (smem) / stash / sigma dot
           auto block = [&](const uint32_t (&v)[32], int cg) {
+            if (a.debug == 1) { if (v[0] == 0x7fc00001u && v[31] == 0x7fc00002u) dot += 1.f; return; }
             uint32_t gbits = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float x[8];
               const float4 b0 = *reinterpret_cast<const float4*>(bias + cg * 32 + j * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(bias + cg * 32 + j * 8 + 4);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              float x[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                x[i] = fmaxf(__uint_as_float(v[j * 8 + i]) + bb[i], 0.f);
-                if (TRAIN) gbits |= (x[i] > 0.f ? 1u : 0u) << (j * 8 + i);
-              }
-              if (!to_smem) {
+              for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[j * 8 + i]) + bb[i];
+              uint32_t w[4];
+              if (!to_smem) {       // sigma.0: the fp32 activations feed the sigma.2 dot product
                 const float4 s0 = *reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8);
                 const float4 s1 = *reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8 + 4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
                 dot += x[0] * s0.x + x[1] * s0.y + x[2] * s0.z + x[3] * s0.w + x[4] * s1.x + x[5] * s1.y + x[6] * s1.z +
                        x[7] * s1.w;
-              }
-              const uint32_t w0 = tc::pack_bf16(x[0], x[1]), w1 = tc::pack_bf16(x[2], x[3]);
-              const uint32_t w2p = tc::pack_bf16(x[4], x[5]), w3 = tc::pack_bf16(x[6], x[7]);
-              const int kg = cg * 4 + j;
-              if (to_smem) st_shared_v4(act_t + kg * PLANE + q * 16, w0, w1, w2p, w3);
-              if (st_tile) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w0, w1, w2p, w3);
-            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) if (TRAIN && i == cg) gate[i] = gbits;
+                for (int i = 0; i < 4; ++i) w[i] = tc::pack_bf16(x[2 * i], x[2 * i + 1]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w[i] = tc::pack_bf16_relu(x[2 * i], x[2 * i + 1]);
+              }
+              const int kg = cg * 4 + j;
+              if (to_smem) st_shared_v4(act_t + kg * PLANE + q * 16, w[0], w[1], w[2], w[3]);
+              if (TRAIN) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gbits |= tc::gate_bits(w[i], j * 4 + i);
+                if (st_tile) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+            if (TRAIN && gate_out) gate_out[cg] = gbits;
           };
           // software pipeline: the TMEM load of block cg+1 is in flight while block cg is processed
-          uint32_t va[32], vb[32];
-          tc::tmem_ld32(taddr, va);
+          // this warp owns blocks set, set+2, set+4, set+6; the next block's TMEM load flies while one is processed
+          if (TRAIN) {
+            // training variant: one buffer (the extra stash/gate state would spill at 96 registers, and with
+            // the whole L1 carved out as shared memory a spill costs an L2 round trip); latency is hidden by
+            // the second warp of the lane quarter instead
+            uint32_t va[32];
 #pragma unroll 1
-          for (int cg = 0; cg < WID / 32; cg += 2) {
-            tc::tmem_ld_wait();
-            tc::tmem_ld32(taddr + (cg + 1) * 32, vb);
-            block(va, cg);
-            tc::tmem_ld_wait();
-            if (cg + 2 < WID / 32) tc::tmem_ld32(taddr + (cg + 2) * 32, va);
-            block(vb, cg + 1);
+            for (int cg = set; cg < WID / 32; cg += 2) {
+              tc::tmem_ld32(taddr + cg * 32, va);
+              tc::tmem_ld_wait();
+              block(va, cg);
+            }
+          } else {
+            uint32_t va[32], vb[32];
+            tc::tmem_ld32(taddr + set * 32, va);
+#pragma unroll 1
+            for (int cg = set; cg < WID / 32; cg += 4) {
+              tc::tmem_ld_wait();
+              tc::tmem_ld32(taddr + (cg + 2) * 32, vb);
+              block(va, cg);
+              tc::tmem_ld_wait();
+              if (cg + 4 < WID / 32) tc::tmem_ld32(taddr + (cg + 4) * 32, va);
+              block(vb, cg + 2);
+            }
           }
-          if (st_tile) {
-            uint4* gp = reinterpret_cast<uint4*>(a.stash_bits + ((size_t)tile * a.n_slots + st.stash_slot) * BITS_BYTES + q * 32);
-            gp[0] = make_uint4(gate[0], gate[1], gate[2], gate[3]);
-            gp[1] = make_uint4(gate[4], gate[5], gate[6], gate[7]);
+          if (!to_smem) {
+            if (set == 0) sigma_raw = dot + w2[256];
+            else sig_part[t * 128 + q] = dot;
           }
-          if (!to_smem) sigma_raw = dot + w2[256];
         }
         if (s + 1 < n_steps) {
           tc::fence_proxy_async();
@@ -437,7 +476,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_fwd_k(const __grid_constant__ F
   }
   tc::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 9) tc::tmem_dealloc(tmem, 512);
+  tc::cluster_sync();            // no CTA leaves while its peer may still multicast into it / arrive on its barriers
+  if (warp == W_MMA) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace mlptc
@@ -538,6 +578,10 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   a.bias = bias;
   a.sig2_off = L.sig2_off;
   a.bias_floats = L.bias_floats;
+  {
+    const char* dbg = getenv("MCNERF_TC_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
+  }
   MC_ARG(L.bias_floats <= BIAS_SMEM_FLOATS);
   a.rays_o = in->rays_o; a.rays_d = in->rays_d; a.jitter = in->jitter; a.smp = in->smp;
   a.sel_idx = in->sample_idx; a.n_rows = in->n_rows; a.n_rows_dev = in->n_rows_dev;
@@ -565,8 +609,20 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = n_pairs < sms ? n_pairs : sms;
-  if (stash) mlp_tc_fwd_k<true><<<grid, 320, SMEM_FWD, (cudaStream_t)stream>>>(a);
-  else mlp_tc_fwd_k<false><<<grid, 320, SMEM_FWD, (cudaStream_t)stream>>>(a);
+  grid = (grid + 1) & ~1;                                  // whole clusters of 2
+  if (grid > sms) grid = sms & ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.dynamicSmemBytes = SMEM_FWD;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (stash) MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<true>, a));
+  else MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<false>, a));
   MC_LAUNCHED();
   return 0;
 }

@@ -58,6 +58,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// global -> the SAME shared-memory offset of every CTA in `cta_mask` (cluster multicast); each destination CTA's
+// mbarrier at the same offset receives the complete_tx.
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // shared -> global (bulk group completion)
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -124,6 +142,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// same, arriving on the barrier at this offset in every CTA of `cta_mask` (frees a multicast-filled ring stage)
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ TMEM -> registers
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base_lane + i), columns col..col+31.
 // The warp may only touch lanes [32*(warp_id%4), +32).
@@ -141,6 +166,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// relu + round-to-nearest bf16 pack in ONE instruction (negative / NaN inputs clamp to +0)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// ReLU gate flags of a packed non-negative bf16 pair, word index k (0..15) of a 32-column block:
+// flag(lo) -> bit k, flag(hi) -> bit 16+k.  (x != 0  <=>  x + 0x7FFF carries into bit 15 of its half.)
+__device__ __forceinline__ uint32_t gate_bits(uint32_t packed, int k) {
+  return ((packed + 0x7FFF7FFFu) >> (15 - k)) & (0x00010001u << k);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
