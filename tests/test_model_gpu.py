@@ -210,3 +210,66 @@ def test_cfg1_train_step_bf16_tensor_core_path():
     print("relative errors:", {k: f"{v:.1e}" for k, v in rel.items()})
     for k, v in rel.items():
         assert v < 0.15, (k, v)
+
+
+def test_demo_mode_renders_from_checkpoint(tmp_path):
+    """main.py --demo path: MC_Model(mode=1) loads a checkpoint written by save_model and renders a whole test
+    view in `batch`-sized chunks (ref: model/mc_nerf.py:106-122, 577-584), returning CPU tensors."""
+    from mc_nerf_b200.model import MC_Model
+    sp_kw = dict(n_cam=4, img_h=12, img_w=16, batch=50, samples=8, scale=2, coarse=(3, 32, (1,)), fine=(4, 64, (2,)))
+    sp0 = syn.make_sys_param(**sp_kw)
+    cfg = orc.cfg_from_sys_param(sp0)
+    pc, pf = orc.init_mlp_params(*cfg["coarse"], seed=5), orc.init_mlp_params(*cfg["fine"], seed=6)
+    sp, m = build_model(sp_kw, syn.init_camera_weights(sp0), pc, pf)
+    m.nerf.weights_pth = str(tmp_path)
+    m.nerf.save_model(m, 0)
+    sp_demo = syn.make_sys_param(device=DEV, mode=1, **sp_kw)
+    sp_demo["mlp_precision"] = "fp32"
+    sp_demo["demo_ckpt"] = m.nerf.file_path
+    demo = MC_Model(sp_demo).to(DEV).eval()
+    H, W, B = 12, 16, 50
+    n_chunks = -(-H * W // B)
+    g = torch.Generator().manual_seed(9)
+    draws = []
+    for c in range(n_chunks):
+        nb = min(B, H * W - c * B)
+        draws += [torch.randn(nb, 8, generator=g), torch.randn(nb, 8, generator=g), torch.randn(nb, 16, generator=g)]
+    with torch.no_grad(), Replay(randn=[d.clone() for d in draws]):
+        rgb, dep, opa = demo(torch.tensor([2]))
+    assert rgb.device.type == "cpu" and rgb.shape == (H * W, 3) and dep.shape == (H * W, 1) and opa.shape == (H * W, 1)
+    # oracle: same rays (ground-truth test intrinsics/pose), same draws, chunk by chunk
+    rd, ro = orc.get_rays(sp0["test_pose"][2], sp0["intr_mat_inv"][1][2], H, W)
+    outs = []
+    for c in range(n_chunks):
+        sl = slice(c * B, min(H * W, (c + 1) * B))
+        rng = dict(noise_c=draws[3 * c], noise_sel=draws[3 * c + 1], noise_f=draws[3 * c + 2])
+        outs.append(orc.render_rays(pc, pf, cfg, rd[sl], ro[sl], rng, train=False))
+    close(rgb, torch.cat([o[0] for o in outs]), rtol=1e-4, atol=5e-6)
+    close(dep, torch.cat([o[1] for o in outs]), rtol=1e-4, atol=2e-5)
+    close(opa, torch.cat([o[2] for o in outs]), rtol=1e-4, atol=5e-6)
+
+
+def test_fine_cap_path_matches_reference_semantics():
+    """samples*scale > 128: the reference keeps a random 128*B subset of the selected fine samples in training
+    (CPU randperm, model/mc_nerf.py:630-632).  Same permutation -> same render as the oracle."""
+    sp_kw = dict(n_cam=4, img_h=8, img_w=8, batch=8, samples=48, scale=4, coarse=(2, 32, ()), fine=(2, 32, ()))
+    sp0 = syn.make_sys_param(**sp_kw)
+    cfg = orc.cfg_from_sys_param(sp0)
+    pc, pf = orc.init_mlp_params(*cfg["coarse"], seed=7), orc.init_mlp_params(*cfg["fine"], seed=8)
+    sp, m = build_model(sp_kw, syn.init_camera_weights(sp0), pc, pf)
+    g = torch.Generator().manual_seed(10)
+    B, Sc, Sf = 8, 48, 192
+    rd = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1)
+    ro = torch.randn(B, 3, generator=g) * 0.2
+    rng = dict(jitter=torch.rand(B, 1, generator=g) * (7.0 / Sc), noise_c=torch.randn(B, Sc, generator=g),
+               noise_sel=torch.randn(B, Sc, generator=g), noise_f=torch.randn(B, Sf, generator=g))
+    perm = torch.randperm(B * Sf, generator=g)
+    aux = orc.render_rays(pc, pf, cfg, rd, ro, rng, train=True, cap_perm=torch.arange(B * Sf), return_aux=True)
+    n_sel_uncapped = orc.select_fine(aux["w_sel"], cfg["thresh"], cfg["scale"]).shape[0]
+    assert n_sel_uncapped > B * 128, "test must exercise the cap"
+    perm_n = perm[perm < n_sel_uncapped]            # the reference draws randperm(n_selected); emulate with a filtered one
+    aux = orc.render_rays(pc, pf, cfg, rd, ro, rng, train=True, cap_perm=perm_n, return_aux=True)
+    dev_rng = {k: v.to(DEV) for k, v in rng.items()}
+    rgb_c, rgb_f = m.nerf.render_rays_train(rd.to(DEV), ro.to(DEV), 25, 1.0, rng=dev_rng, cap_perm=perm_n)
+    close(rgb_c, aux["rgb_c"], rtol=1e-4, atol=5e-6)
+    close(rgb_f, aux["rgb_f"], rtol=1e-4, atol=5e-6)
