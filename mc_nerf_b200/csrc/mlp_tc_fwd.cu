@@ -430,10 +430,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
               if (TRAIN) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) gbits |= tc::gate_bits(w[i], j * 4 + i);
-                if (st_tile) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w[0], w[1], w[2], w[3]);
+                if (st_tile && a.debug != 3) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w[0], w[1], w[2], w[3]);
               }
             }
-            if (TRAIN && gate_out) gate_out[cg] = gbits;
+            if (TRAIN && gate_out && a.debug != 4) gate_out[cg] = gbits;
           };
           // software pipeline: the TMEM load of block cg+1 is in flight while block cg is processed
           // this warp owns blocks set, set+2, set+4, set+6; the next block's TMEM load flies while one is processed
