@@ -273,3 +273,44 @@ def test_fine_cap_path_matches_reference_semantics():
     rgb_c, rgb_f = m.nerf.render_rays_train(rd.to(DEV), ro.to(DEV), 25, 1.0, rng=dev_rng, cap_perm=perm_n)
     close(rgb_c, aux["rgb_c"], rtol=1e-4, atol=5e-6)
     close(rgb_f, aux["rgb_f"], rtol=1e-4, atol=5e-6)
+
+
+def test_reference_default_config_shapes_mixed_paths():
+    """config.yaml defaults (ref: config/config.yaml:65-82): coarse 4x128 skip[2] (-> fp32 CUDA-core path), fine 8x256
+    skip[4] (-> bf16 tcgen05 path), 128 coarse samples x scale 5 = 640 fine samples (-> 128-per-ray cap with the CPU
+    randperm).  One train step + backward; compared with the oracle on identical draws."""
+    from mc_nerf_b200 import render
+    sp_kw = dict(n_cam=5, img_h=16, img_w=16, batch=32, samples=128, scale=5, coarse=(4, 128, (2,)), fine=(8, 256, (4,)))
+    sp0 = syn.make_sys_param(**sp_kw)
+    cfg = orc.cfg_from_sys_param(sp0)
+    pc, pf = orc.init_mlp_params(*cfg["coarse"], seed=11), orc.init_mlp_params(*cfg["fine"], seed=12)
+    sp, m = build_model(sp_kw, syn.init_camera_weights(sp0), pc, pf, precision="bf16")
+    rc = m.nerf.render_cfg
+    assert not render.use_tc(rc, rc.coarse) and render.use_tc(rc, rc.fine)
+    g = torch.Generator().manual_seed(13)
+    B, Sc, Sf = 32, 128, 640
+    rd = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1)
+    ro = torch.randn(B, 3, generator=g) * 0.2
+    rng = dict(jitter=torch.rand(B, 1, generator=g) * (7.0 / Sc), noise_c=torch.randn(B, Sc, generator=g),
+               noise_sel=torch.randn(B, Sc, generator=g), noise_f=torch.randn(B, Sf, generator=g))
+    gt = torch.rand(B, 3, generator=g)
+    aux0 = orc.render_rays(pc, pf, cfg, rd, ro, rng, train=True, cap_perm=torch.arange(B * Sf), return_aux=True)
+    n_unc = orc.select_fine(aux0["w_sel"], cfg["thresh"], cfg["scale"]).shape[0]
+    assert n_unc > B * 128
+    perm = torch.randperm(n_unc, generator=g)
+    pcr = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    pfr = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+    rgb_c_r, rgb_f_r = orc.render_rays(pcr, pfr, cfg, rd, ro, rng, train=True, cap_perm=perm)
+    (torch.nn.functional.mse_loss(rgb_c_r, gt) + torch.nn.functional.mse_loss(rgb_f_r, gt)).backward()
+    dev_rng = {k: v.to(DEV) for k, v in rng.items()}
+    rgb_c, rgb_f = m.nerf.render_rays_train(rd.to(DEV), ro.to(DEV), 25, 1.0, rng=dev_rng, cap_perm=perm)
+    (torch.nn.functional.mse_loss(rgb_c, gt.to(DEV)) + torch.nn.functional.mse_loss(rgb_f, gt.to(DEV))).backward()
+    close(rgb_c, rgb_c_r.detach(), rtol=1e-4, atol=1e-5)           # fp32 path
+    close(rgb_f, rgb_f_r.detach(), rtol=1e-2, atol=1e-3)           # bf16 path: stated tolerance 1e-3
+    named = dict(m.named_parameters())
+    for k, v in pcr.items():
+        gk = named[f"nerf.nerf_coarse.{k}"].grad
+        assert ((gk.cpu() - v.grad).norm() / v.grad.norm().clamp_min(1e-12)).item() < 1e-3, k
+    for k, v in pfr.items():
+        gk = named[f"nerf.nerf_fine.{k}"].grad
+        assert ((gk.cpu() - v.grad).norm() / v.grad.norm().clamp_min(1e-12)).item() < 0.15, k
