@@ -166,7 +166,7 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step(dev_batch, False)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, period=float(os.environ.get('MCNERF_CLOCK_PERIOD', '0.05'))) if rank == 0 and os.environ.get('MCNERF_NO_CLOCKS') is None else None
     if sampler:
         sampler.start()
     n0 = lib().launch_count()
@@ -282,8 +282,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("MCNERF_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--rays", type=int, default=RAYS)

@@ -50,6 +50,14 @@ int mcnerf_intrinsics_bwd(const float* w_fx, const float* w_fy, const float* w_u
 int mcnerf_se3_fwd(const float* wu /*[n,6]*/, int n, float* Rt /*[n,3,4] world->camera*/, void* stream);
 int mcnerf_se3_bwd(const float* wu, const float* gRt, int n, float* g_wu /*overwritten*/, void* stream);
 
+/* Calibration-point reprojection (a7): pix[c,p] = (K_c [R|t]_c X_cp)_{xy} / z.  wpts [n_cam,n_pts,3] -> pix [n_cam,n_pts,2].
+ * ref: model/mc_nerf.py:147-152 (get_reproject_pixels), :236-241 (cam2pix), :260-267 (world2cam).
+ * bwd: gK [n_cam,3,3], gRt [n_cam,3,4] overwritten. */
+int mcnerf_reproject_fwd(const float* wpts, const float* K, const float* Rt, int n_cam, int n_pts, float* pix,
+                         void* stream);
+int mcnerf_reproject_bwd(const float* wpts, const float* K, const float* Rt, const float* g_pix, int n_cam, int n_pts,
+                         float* gK, float* gRt, void* stream);
+
 /* ------------------------------------------------------------------ ray generation (a5, a6)
  * ref: model/mc_nerf.py:124-145 (get_rays), :229-256 (pix2cam, cam2world), :327-345 (gather of the
  * randperm subset).  Ray r uses camera cam_id[r] (or `cam_const` when cam_id is NULL) and pixel

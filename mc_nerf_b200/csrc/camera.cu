@@ -188,7 +188,88 @@ __global__ void se3_bwd_k(const float* __restrict__ wu, const float* __restrict_
   }
 }
 
+// Calibration-point reprojection px = K [R|t] X / z, one thread per camera (P points each).
+// ref: model/mc_nerf.py:147-152, 236-241, 260-267.
+__global__ void reproject_fwd_k(const float* __restrict__ wpts, const float* __restrict__ K,
+                                const float* __restrict__ Rt, int n, int P, float* __restrict__ pix) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const float* k = K + 9 * c;
+  const float* m = Rt + 12 * c;
+  for (int p = 0; p < P; ++p) {
+    const float* X = wpts + ((size_t)c * P + p) * 3;
+    float xc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) xc[r] = m[4 * r] * X[0] + m[4 * r + 1] * X[1] + m[4 * r + 2] * X[2] + m[4 * r + 3];
+    float h[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) h[r] = k[3 * r] * xc[0] + k[3 * r + 1] * xc[1] + k[3 * r + 2] * xc[2];
+    pix[((size_t)c * P + p) * 2] = h[0] / h[2];
+    pix[((size_t)c * P + p) * 2 + 1] = h[1] / h[2];
+  }
+}
+
+__global__ void reproject_bwd_k(const float* __restrict__ wpts, const float* __restrict__ K,
+                                const float* __restrict__ Rt, const float* __restrict__ gpix, int n, int P,
+                                float* __restrict__ gK, float* __restrict__ gRt) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const float* k = K + 9 * c;
+  const float* m = Rt + 12 * c;
+  float dk[9], dm[12];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) dk[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) dm[i] = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const float* X = wpts + ((size_t)c * P + p) * 3;
+    float xc[3], h[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) xc[r] = m[4 * r] * X[0] + m[4 * r + 1] * X[1] + m[4 * r + 2] * X[2] + m[4 * r + 3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) h[r] = k[3 * r] * xc[0] + k[3 * r + 1] * xc[1] + k[3 * r + 2] * xc[2];
+    const float gx = gpix[((size_t)c * P + p) * 2], gy = gpix[((size_t)c * P + p) * 2 + 1];
+    const float iz = 1.f / h[2];
+    const float gh[3] = {gx * iz, gy * iz, -(gx * h[0] + gy * h[1]) * iz * iz};
+    float gxc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        dk[3 * r + j] += gh[r] * xc[j];
+        gxc[j] += k[3 * r + j] * gh[r];
+      }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      dm[4 * r] += gxc[r] * X[0];
+      dm[4 * r + 1] += gxc[r] * X[1];
+      dm[4 * r + 2] += gxc[r] * X[2];
+      dm[4 * r + 3] += gxc[r];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gK[9 * c + i] = dk[i];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) gRt[12 * c + i] = dm[i];
+}
+
 }  // namespace
+
+extern "C" int mcnerf_reproject_fwd(const float* wpts, const float* K, const float* Rt, int n_cam, int n_pts,
+                                    float* pix, void* stream) {
+  MC_ARG(wpts && K && Rt && pix && n_cam > 0 && n_pts > 0);
+  reproject_fwd_k<<<cdiv(n_cam, 128), 128, 0, (cudaStream_t)stream>>>(wpts, K, Rt, n_cam, n_pts, pix);
+  MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcnerf_reproject_bwd(const float* wpts, const float* K, const float* Rt, const float* g_pix, int n_cam,
+                                    int n_pts, float* gK, float* gRt, void* stream) {
+  MC_ARG(wpts && K && Rt && g_pix && gK && gRt && n_cam > 0 && n_pts > 0);
+  reproject_bwd_k<<<cdiv(n_cam, 128), 128, 0, (cudaStream_t)stream>>>(wpts, K, Rt, g_pix, n_cam, n_pts, gK, gRt);
+  MC_LAUNCHED();
+  return 0;
+}
 
 extern "C" int mcnerf_intrinsics_fwd(const float* w_fx, const float* w_fy, const float* w_ux, const float* w_uy,
                                      int n_cam, int img_h, int img_w, float* K, float* Kinv, void* stream) {

@@ -107,6 +107,9 @@ class MC_Model(nn.Module):
             reproj = self.get_reproject_pixels(intr_wpts, self.intr_adj, self.calib_pose_adj)
             rays_d, rays_o, rand_idx = self.generate_train_rays(img_id_host)
             rgbs_c, rgbs_f = self.nerf(rays_d, rays_o, epoch, cur_ratio if glob else 1)
+            if self._gt_event is not None:          # side-stream H2D of the image must have landed
+                torch.cuda.current_stream().wait_event(self._gt_event)
+                gt_rgbs.record_stream(torch.cuda.current_stream())
             gt_sel = gt_rgbs.reshape(-1, 3)[rand_idx]
             loss_dict["intr"] = [reproj, intr_pts]
             loss_dict["rgb"] = [rgbs_c, rgbs_f, gt_sel]
@@ -177,6 +180,8 @@ class MC_Model(nn.Module):
 
     def get_reproject_pixels(self, tag_wpts, intr_adj, pose_adj):
         """Calibration-point reprojection px = K [R|t] X / z.  ref: model/mc_nerf.py:147-152."""
+        if tag_wpts.is_cuda and tag_wpts.dim() == 4 and tag_wpts.shape[0] == 1 and not tag_wpts.requires_grad:
+            return ops.ReprojectFn.apply(tag_wpts, intr_adj, pose_adj)
         cam = self.world2cam(self.world2hom(tag_wpts), pose_adj.unsqueeze(0))
         return self.cam2pix(cam, intr_adj.unsqueeze(0))
 
@@ -282,7 +287,19 @@ class MC_Model(nn.Module):
             return t if t.device == dev or (t.is_cuda and dev.type == "cuda" and dev.index is None) \
                 else t.to(dev, non_blocking=True)
         gt_rgbs, img_id, intr_wpts, intr_pts, extr_wpts, extr_pts = args[0]
-        return (mv(gt_rgbs), mv(img_id), mv(intr_wpts), mv(intr_pts), mv(extr_wpts), mv(extr_pts),
+        # The ground-truth image (H*W*3 fp32: 7.7 MB at 800x800) is only needed for the loss at the END of the forward
+        # pass: copy it on a side stream so the transfer overlaps ray generation and the coarse/fine MLPs.
+        self._gt_event = None
+        if dev.type == "cuda" and not gt_rgbs.is_cuda and gt_rgbs.is_pinned():
+            if self.__dict__.get("_h2d_stream") is None:
+                self.__dict__["_h2d_stream"] = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(self._h2d_stream):
+                gt_dev = gt_rgbs.to(dev, non_blocking=True)
+                self._gt_event = torch.cuda.Event()
+                self._gt_event.record(self._h2d_stream)
+        else:
+            gt_dev = mv(gt_rgbs)
+        return (gt_dev, mv(img_id), mv(intr_wpts), mv(intr_pts), mv(extr_wpts), mv(extr_pts),
                 args[1], args[2], args[3])
 
     # ------------------------------------------------------------------ epoch-end reporting (not hot path)

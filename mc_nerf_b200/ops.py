@@ -116,6 +116,28 @@ class SE3Fn(torch.autograd.Function):
         return g.reshape(*ctx.shape, 6)
 
 
+class ReprojectFn(torch.autograd.Function):
+    """Calibration-point reprojection: wpts [1,n,P,3], K [n,3,3], Rt [n,3,4] -> pixels [1,n,P,2].
+    ref: model/mc_nerf.py:147-152.  One launch each way instead of ~30 small ATen kernels."""
+
+    @staticmethod
+    def forward(ctx, wpts, K, Rt):
+        wpts, K, Rt = _f32(wpts), _f32(K), _f32(Rt)
+        n, P = K.shape[0], wpts.shape[-2]
+        pix = torch.empty(*wpts.shape[:-1], 2, device=K.device)
+        lib().call("mcnerf_reproject_fwd", _p(wpts), _p(K), _p(Rt), n, P, _p(pix), _stream())
+        ctx.save_for_backward(wpts, K, Rt)
+        return pix
+
+    @staticmethod
+    def backward(ctx, g):
+        wpts, K, Rt = ctx.saved_tensors
+        gK, gRt = torch.empty_like(K), torch.empty_like(Rt)
+        lib().call("mcnerf_reproject_bwd", _p(wpts), _p(K), _p(Rt), _p(_f32(g)), K.shape[0], wpts.shape[-2],
+                   _p(gK), _p(gRt), _stream())
+        return None, gK, gRt
+
+
 class RaygenFn(torch.autograd.Function):
     """(Kinv [n,3,3], Rt [n,3,4], cam, pix) -> rays_o, rays_d [B,3].  ref: model/mc_nerf.py:124-145, 327-345.
     `cam` is an int or an int32 tensor [B]; `pix` is None (whole image, row-major) or an int32 tensor [B]."""

@@ -257,3 +257,17 @@ def test_scatter_gather_fine():
     assert torch.equal(s.grad.cpu(), gd[idx.long()])
     empty = ops().ScatterFineFn.apply(torch.zeros(0, 4, device=DEV), torch.zeros(0, dtype=torch.int32, device=DEV), 6, -20.0)
     assert torch.equal(empty.cpu(), ref[:6] * 0 + torch.tensor([-20.0, 1, 1, 1]))
+
+
+def test_reprojection_golden_and_backward(mods):
+    c, r = mods["cam"], mods["reproj"]
+    K = c["K"].to(DEV).requires_grad_(True)
+    Rt = c["calib"].to(DEV).requires_grad_(True)
+    pix = ops().ReprojectFn.apply(r["wpts"].to(DEV), K, Rt)
+    close(pix, r["out"], rtol=1e-5, atol=1e-4)
+    g = torch.randn(pix.shape, generator=torch.Generator().manual_seed(8))
+    pix.backward(g.to(DEV))
+    Kc, Rc = c["K"].clone().requires_grad_(True), c["calib"].clone().requires_grad_(True)
+    orc.reproject(r["wpts"], Kc, Rc).backward(g)
+    close(K.grad, Kc.grad, rtol=1e-4, atol=1e-3)
+    close(Rt.grad, Rc.grad, rtol=1e-4, atol=1e-2)
