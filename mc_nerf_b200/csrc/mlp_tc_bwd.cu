@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
 
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 128); tc::mbar_init(&bars->acc_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 4); /* one arrive per epilogue warp */ tc::mbar_init(&bars->acc_full[i], 1); }
     tc::mbar_init_fence();
   }
   if (warp == 9) tc::tmem_alloc(&bars->tmem_base, 512);
@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
       }
       tc::fence_proxy_async();
       tc::tcgen05_fence_before();
-      tc::mbar_arrive(&bars->a_ready[t]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->a_ready[t]);
 
       for (int jn = 0; jn < n_jobs; ++jn) {
         const BJob& jb = a.plan.j[jn];
@@ -343,7 +344,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
         if (jn + 1 < n_jobs) {
           tc::fence_proxy_async();
           tc::tcgen05_fence_before();
-          tc::mbar_arrive(&bars->a_ready[t]);
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bars->a_ready[t]);
         }
       }
     }

@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
 
   if (tid == 0) {
     for (int i = 0; i < FSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 2); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 256); tc::mbar_init(&bars->acc_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 8); /* one arrive per epilogue warp */ tc::mbar_init(&bars->acc_full[i], 1); }
     tc::mbar_init_fence();
   }
   if (warp == W_MMA) tc::tmem_alloc(&bars->tmem_base, 512);
@@ -347,7 +347,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
       if (set == 0) encode_row(a, row_g, valid, enc_t, q, st_enc);
       tc::fence_proxy_async();
       tc::tcgen05_fence_before();
-      tc::mbar_arrive(&bars->a_ready[t]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bars->a_ready[t]);
       float sigma_raw = 0.f;
       for (int s = 0; s < n_steps; ++s) {
         const Step& st = a.plan.s[s];
@@ -469,7 +470,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
         if (s + 1 < n_steps) {
           tc::fence_proxy_async();
           tc::tcgen05_fence_before();
-          tc::mbar_arrive(&bars->a_ready[t]);
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bars->a_ready[t]);
         }
       }
     }
