@@ -200,8 +200,17 @@ def run_ours(args):
         peaks = load_peaks()
         flops = 6.0 * MACS_PER_EVAL * evals          # fwd + dgrad + wgrad
         ach = flops / (mlp_ms / 1e3) / 1e12
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per MLP evaluation from the committed ncu --set full capture (dram__bytes_read+write)
+            summ = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+            per_eval = sum(k["dram_bytes_per_eval"] for k in summ["kernels"].values())
+            traffic = round(per_eval * evals / 1e9, 3)
+            traffic_src = "GB per step = ncu dram bytes/evaluation (fwd+bwd-chain+wgrad, profiles/r01_ncu_summary.json) x evaluations"
+        except Exception:
+            pass
         roof = dict(bound="tensor", achieved=round(ach, 2), peak=peaks["tensor"], unit="TFLOP/s",
-                    frac=round(ach / peaks["tensor"], 4), traffic=None, peak_source=peaks["src"],
+                    frac=round(ach / peaks["tensor"], 4), traffic=traffic, traffic_unit="GB", traffic_source=traffic_src,
+                    peak_source=peaks["src"],
                     kernel="mcnerf_mlp_* (fwd+bwd, coarse+fine)", kernel_ms_per_step=round(mlp_ms, 3),
                     mlp_evals_per_step=evals, fine_selected_frac=round(n_fine / (args.rays * SC * SCALE), 4),
                     kernel_ms_by_name={k: round(v / 3, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:12]})
