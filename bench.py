@@ -298,7 +298,7 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--allreduce", default="ddp", choices=["flat", "ddp"])
+    ap.add_argument("--allreduce", default="flat", choices=["flat", "ddp"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

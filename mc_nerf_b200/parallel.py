@@ -11,43 +11,58 @@ def world():
 
 
 class FlatGradAllReduce:
-    """Averages the gradients of `params` across ranks with a single all-reduce.
+    """Averages the gradients of `params` across ranks with as few all-reduces as the memory layout allows.
 
-    Parameters a rank did not touch this step (grad is None: e.g. `weights_pose` in the fine-tune stage, the MLPs
-    in the camera stage) contribute zeros, which is what DistributedDataParallel(find_unused_parameters=True)
-    does in the reference."""
+    The renderer's backward hands autograd the MLP gradients as views of ONE buffer per network (render.py), and
+    autograd keeps those views as `.grad` - so each network's gradients are all-reduced IN PLACE through an alias
+    of that buffer (no flatten / unflatten copies); the handful of small remaining tensors (camera parameters) go
+    through one concatenated buffer.  Parameters a rank did not touch this step (grad is None: e.g. `weights_pose`
+    in the fine-tune stage) contribute zeros, which is what DistributedDataParallel(find_unused_parameters=True)
+    does in the reference (ref: main.py:61)."""
 
     def __init__(self, params):
         self.params = [p for p in params]
-        self.numel = sum(p.numel() for p in self.params)
-        self.flat = None
+
+    @staticmethod
+    def _runs(grads):
+        """maximal runs of gradients that sit back to back in one storage -> [(first_index, count, numel)]"""
+        runs, i = [], 0
+        while i < len(grads):
+            g = grads[i]
+            j, end, numel = i + 1, g.data_ptr() + g.numel() * g.element_size(), g.numel()
+            base = g.untyped_storage().data_ptr()
+            while (j < len(grads) and grads[j].data_ptr() == end and grads[j].untyped_storage().data_ptr() == base
+                   and grads[j].is_contiguous() and g.is_contiguous()):
+                end += grads[j].numel() * grads[j].element_size()
+                numel += grads[j].numel()
+                j += 1
+            runs.append((i, j - i, numel))
+            i = j
+        return runs
 
     def __call__(self):
         n = world()
         if n == 1:
             return
-        p0 = self.params[0]
-        if self.flat is None or self.flat.device != p0.device:
-            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=p0.device)
-        off = 0
         for p in self.params:
-            k = p.numel()
             if p.grad is None:
-                self.flat[off:off + k].zero_()
+                p.grad = torch.zeros_like(p)
+        grads = [p.grad for p in self.params]
+        singles = []
+        for first, count, numel in self._runs(grads):
+            g0 = grads[first]
+            if count > 1 and g0.is_contiguous():
+                alias = torch.empty(0, dtype=g0.dtype, device=g0.device).set_(g0.untyped_storage(), g0.storage_offset(),
+                                                                                (numel,))
+                dist.all_reduce(alias, op=dist.ReduceOp.SUM)
+                alias.mul_(1.0 / n)
             else:
-                self.flat[off:off + k].copy_(p.grad.reshape(-1))
-            off += k
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.mul_(1.0 / n)
-        off = 0
-        for p in self.params:
-            k = p.numel()
-            g = self.flat[off:off + k].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            off += k
+                singles += grads[first:first + count]
+        if singles:
+            flat = torch.cat([g.reshape(-1) for g in singles])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.mul_(1.0 / n)
+            torch._foreach_copy_(singles, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in singles]), singles)])
 
 
 def shard_rays(n_rays, rank=None, n_ranks=None):

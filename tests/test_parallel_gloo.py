@@ -83,3 +83,45 @@ def test_shard_rays_partitions_the_batch():
         cuts = [shard_rays(n, r, w) for r in range(w)]
         assert cuts[0][0] == 0 and cuts[-1][1] == n
         assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+
+
+def _worker_flat(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from mc_nerf_b200.parallel import FlatGradAllReduce
+    g = torch.Generator().manual_seed(100 + rank)
+    shapes = [(4, 3), (4,), (2, 4), (2,)]
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes] + [torch.nn.Parameter(torch.zeros(5))]
+    flat = torch.randn(sum(torch.Size(s).numel() for s in shapes), generator=g)      # one buffer, as render.py produces
+    off = 0
+    for p_, s_ in zip(params, shapes):
+        k = torch.Size(s_).numel()
+        p_.grad = flat[off:off + k].view(s_)
+        off += k
+    params[-1].grad = torch.randn(5, generator=g)
+    ar = FlatGradAllReduce(params)
+    assert ar._runs([p_.grad for p_ in params]) == [(0, 4, flat.numel()), (4, 1, 5)]
+    ar()
+    if rank == 0:
+        torch.save([p_.grad.clone() for p_ in params] + [flat.clone()], out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_buffer_runs_are_reduced_in_place(tmp_path):
+    out = str(tmp_path / "f.pt")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_flat, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    shapes = [(4, 3), (4,), (2, 4), (2,)]
+    flats, lasts = [], []
+    for rank in range(2):
+        g = torch.Generator().manual_seed(100 + rank)
+        flats.append(torch.randn(sum(torch.Size(s).numel() for s in shapes), generator=g))
+        lasts.append(torch.randn(5, generator=g))
+    mean_flat = (flats[0] + flats[1]) / 2
+    torch.testing.assert_close(got[-1], mean_flat)                     # the shared buffer itself was reduced
+    torch.testing.assert_close(torch.cat([t.reshape(-1) for t in got[:4]]), mean_flat)
+    torch.testing.assert_close(got[4], (lasts[0] + lasts[1]) / 2)
