@@ -254,6 +254,10 @@ int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, const float* b
  * D = A^T B (mn_major = 1: A [K,128], B [K,N], MN-major operands).  Used by tests/ to pin the UMMA
  * shared-memory / instruction descriptor conventions the fused MLP kernels rely on. */
 int mcnerf_tc_selftest(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int mn_major, void* stream);
+/* MMA issue-rate probe (one CTA): the K/16 MMAs repeated `reps` times on resident operands; cycles_out (device,
+ * 2 x int64) = clock ticks to issue them / until the commit barrier fired. */
+int mcnerf_tc_mma_rate(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int mn_major, int reps,
+                       long long* cycles_out, void* stream);
 
 #ifdef __cplusplus
 }

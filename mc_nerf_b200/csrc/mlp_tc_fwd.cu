@@ -157,6 +157,7 @@ struct FwdArgs {
   const float* bias;
   int sig2_off;
   int bias_floats;
+  long long* dbg;        // MCNERF_TC_DEBUG=7: clock64 trace of CTA 0 [event][step] (see tools/trace_fwd.py)
   int debug;             // timing experiments only (MCNERF_TC_DEBUG): 1 = epilogue skips math/stores, 2 = skips TMEM loads
   const float *rays_o, *rays_d, *jitter;
   mcnerf_sampling smp;
@@ -306,11 +307,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
           const uint32_t idesc = tc::umma_idesc_bf16(TM, st.N);
           for (int t = 0; t < 2; ++t) {
             tc::mbar_wait(&bars->a_ready[t], apar[t]);
+            if (a.dbg && blockIdx.x == 0 && it == 0) a.dbg[(0 + t) * 32 + s] = clock64();
             apar[t] ^= 1;
             tc::tcgen05_fence_after();
             const uint32_t act_t = tc::smem_u32(act + t * ACT_BYTES), enc_t = tc::smem_u32(enc + t * ENC_BYTES);
             for (int c = 0; c < st.n_chunks; ++c) {
+              long long tw0 = 0;
+              if (a.dbg) tw0 = clock64();
               tc::mbar_wait(&bars->w_full[stage], par);
+              if (a.dbg && blockIdx.x == 0 && it == 0 && t == 0) a.dbg[7 * 32 + 16 + s] += clock64() - tw0;   // cycles waiting for weights
               tc::tcgen05_fence_after();
               uint32_t a_base;
               if (st.a_src == A_ENC) a_base = enc_t + c * (KC / 8) * PLANE;
@@ -327,6 +332,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
               if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             }
             tc::umma_commit(&bars->acc_full[t]);
+            if (a.dbg && blockIdx.x == 0 && it == 0) a.dbg[(2 + t) * 32 + s] = clock64();
           }
         }
     }
@@ -353,6 +359,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
       for (int s = 0; s < n_steps; ++s) {
         const Step& st = a.plan.s[s];
         tc::mbar_wait(&bars->acc_full[t], par);
+        if (a.dbg && blockIdx.x == 0 && it == 0 && (warp & 7) == 0 && lane == 0) a.dbg[(4 + t) * 32 + s] = clock64();
         par ^= 1;
         tc::tcgen05_fence_after();
         const float* bias = bias_s + st.bias_off;
@@ -472,6 +479,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
           tc::tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&bars->a_ready[t]);
+          if (a.dbg && blockIdx.x == 0 && it == 0 && (warp & 7) == 0 && lane == 0) a.dbg[(6 + t) * 32 + s] = clock64();
         }
       }
     }
@@ -583,6 +591,13 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   {
     const char* dbg = getenv("MCNERF_TC_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
+    static long long* dbg_buf = nullptr;
+    a.dbg = nullptr;
+    if (a.debug == 7) {
+      if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * 32 * sizeof(long long));
+      cudaMemsetAsync(dbg_buf, 0, 8 * 32 * sizeof(long long), (cudaStream_t)stream);
+      a.dbg = dbg_buf;
+    }
   }
   MC_ARG(L.bias_floats <= BIAS_SMEM_FLOATS);
   a.rays_o = in->rays_o; a.rays_d = in->rays_d; a.jitter = in->jitter; a.smp = in->smp;
@@ -626,5 +641,19 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   if (stash) MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<true>, a));
   else MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<false>, a));
   MC_LAUNCHED();
+  if (a.dbg) {     // debug trace: clock64 deltas of CTA 0's first tile pair
+    cudaStreamSynchronize((cudaStream_t)stream);
+    long long h[8 * 32];
+    cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const char* names[8] = {"mma:a_rdy0", "mma:a_rdy1", "mma:iss0", "mma:iss1", "epi:full0", "epi:full1",
+                            "epi:arr0", "epi:arr1"};
+    long long t0 = h[0];
+    for (int s = 0; s < L.fwd.n_steps; ++s) {
+      printf("step %2d:", s);
+      for (int e = 0; e < 8; ++e) printf(" %s=%lld", names[e], h[e * 32 + s] ? h[e * 32 + s] - t0 : -1);
+      printf(" wait_w0=%lld\n", h[7 * 32 + 16 + s]);
+    }
+  }
   return 0;
 }
+

@@ -13,7 +13,7 @@ __device__ __forceinline__ uint32_t canon_off(int r, int k, int rows) { return (
 
 __global__ void __launch_bounds__(128) tc_selftest_k(const __nv_bfloat16* __restrict__ A,
                                                      const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int N,
-                                                     int K, int variant) {
+                                                     int K, int variant, int reps, long long* cycles) {
   const int mn_major = variant & 1;
   const bool swap_ls = (variant & 2) != 0;   // diagnostic: exchange the lead/stride byte offsets
   extern __shared__ __align__(128) uint8_t smem[];
@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(128) tc_selftest_k(const __nv_bfloat16* __rest
   const uint32_t tmem = tmem_base;
   if (tid == 0) {
     const uint32_t idesc = tc::umma_idesc_bf16(128, N, mn_major, mn_major);
+    const long long t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep)
     for (int k0 = 0; k0 < K; k0 += 16) {
       uint64_t da, db;
       if (!mn_major) {
@@ -75,9 +77,12 @@ __global__ void __launch_bounds__(128) tc_selftest_k(const __nv_bfloat16* __rest
         da = tc::umma_desc(sa, ta, la);
         db = tc::umma_desc(sb, tb, lb);
       }
-      tc::umma_bf16(tmem, da, db, idesc, k0 > 0);
+      tc::umma_bf16(tmem, da, db, idesc, (k0 | rep) > 0);
     }
     tc::umma_commit(&bar);
+    const long long t1 = clock64();
+    tc::mbar_wait(&bar, 0);
+    if (cycles) { cycles[0] = t1 - t0; cycles[1] = clock64() - t0; }
   }
   tc::mbar_wait(&bar, 0);
   tc::tcgen05_fence_after();
@@ -95,14 +100,29 @@ __global__ void __launch_bounds__(128) tc_selftest_k(const __nv_bfloat16* __rest
 
 }  // namespace
 
+static int selftest_launch(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int mn_major, int reps,
+                           long long* cycles, void* stream);
+
+// MMA issue-rate probe: the same K/16 MMAs repeated `reps` times on resident operands (result is reps x the product).
+// cycles_out[0] = clock64 ticks to ISSUE them, [1] = until the commit barrier fired (device pointer, 2 x int64).
+extern "C" int mcnerf_tc_mma_rate(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int mn_major,
+                                  int reps, long long* cycles_out, void* stream) {
+  return selftest_launch(A_bf16, B_bf16, D, N, K, mn_major, reps, cycles_out, stream);
+}
+
 extern "C" int mcnerf_tc_selftest(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int mn_major,
                                   void* stream) {
+  return selftest_launch(A_bf16, B_bf16, D, N, K, mn_major, 1, nullptr, stream);
+}
+
+static int selftest_launch(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int mn_major, int reps,
+                           long long* cycles, void* stream) {
   MC_ARG(A_bf16 && B_bf16 && D && N >= 16 && N <= 256 && N % 32 == 0 && K >= 16 && K % 16 == 0);
   size_t smem = (size_t)(128 + N) * K * 2;
   MC_ARG(smem <= 200 * 1024);
   MC_CUDA(cudaFuncSetAttribute(tc_selftest_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest_k<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A_bf16, (const __nv_bfloat16*)B_bf16, D, N,
-                                                         K, mn_major);
+                                                         K, mn_major, reps, cycles);
   MC_LAUNCHED();
   return 0;
 }
