@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OUT = os.path.join(CSRC, "libmcnerf.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = (["-DMCNERF_SPIN_TEST_WAIT"] if os.environ.get("MCNERF_SPIN") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+FLAGS = (["-DMCNERF_SPIN_TEST_WAIT"] if os.environ.get("MCNERF_SPIN") else []) + (["-DMCNERF_TC_TRACE"] if os.environ.get("MCNERF_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC",
          "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 

@@ -119,30 +119,37 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
         }
     }
   } else if (warp == 9) {
+    // MMA issuer: per-job constants hoisted, descriptors advance by 32-bit adds (the single issuing thread has to
+    // stay below the ~128 cycles one 128x256x16 MMA takes, or the tensor pipe idles).
     if (lane == 0) {
       int stage = 0;
-      uint32_t par = 0, apar[2] = {0, 0};
+      uint32_t par = 0, apar = 0;
+      const uint32_t hi = tc::umma_desc_hi(128);
+      const uint32_t bufX_lo = tc::umma_desc_lo(tc::smem_u32(bufX), PLANE), small_lo = tc::umma_desc_lo(tc::smem_u32(small), PLANE);
+      const uint32_t wst_addr = tc::smem_u32(wst);
+      const uint32_t full0 = tc::smem_u32(&bars->w_full[0]), empty0 = tc::smem_u32(&bars->w_empty[0]);
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
         for (int jn = 0; jn < n_jobs; ++jn) {
-          const BJob& jb = a.plan.j[jn];
-          const uint32_t idesc = tc::umma_idesc_bf16(TM, jb.N);
-          for (int t = 0; t < 2; ++t) {
-            tc::mbar_wait(&bars->a_ready[t], apar[t]);
-            apar[t] ^= 1;
-            tc::tcgen05_fence_after();
-            const uint32_t a_tile = jb.a_small ? tc::smem_u32(small + t * HEAD_BYTES) : tc::smem_u32(bufX + t * ACT_BYTES);
-            for (int c = 0; c < jb.n_chunks; ++c) {
-              tc::mbar_wait(&bars->w_full[stage], par);
-              tc::tcgen05_fence_after();
-              const uint32_t a_base = a_tile + c * (KC / 8) * PLANE;
-              const uint32_t b_base = tc::smem_u32(wst + stage * STAGE_BYTES);
+          const int N = a.plan.j[jn].N, n_chunks = a.plan.j[jn].n_chunks;
+          const bool a_small = a.plan.j[jn].a_small != 0, acc0 = a.plan.j[jn].accumulate != 0;
+          const uint32_t idesc = tc::umma_idesc_bf16(TM, N);
+          const uint32_t b_lo0 = tc::umma_desc_lo(wst_addr, N * 16), b_inc = (2u * N * 16) >> 4;
 #pragma unroll
-              for (int kk = 0; kk < KC / 16; ++kk) {
-                uint64_t da = tc::umma_desc(a_base + kk * 2 * PLANE, PLANE, 128);
-                uint64_t db = tc::umma_desc(b_base + kk * 2 * jb.N * 16, jb.N * 16, 128);
-                tc::umma_bf16(tmem + t * 256, da, db, idesc, (jb.accumulate | c | kk) != 0);
-              }
-              tc::umma_commit(&bars->w_empty[stage]);
+          for (int t = 0; t < 2; ++t) {
+            tc::mbar_wait(&bars->a_ready[t], (apar >> t) & 1);
+            apar ^= 1u << t;
+            tc::tcgen05_fence_after();
+            const uint32_t d_tmem = tmem + t * 256;
+            uint32_t a_lo = a_small ? small_lo + t * (HEAD_BYTES >> 4) : bufX_lo + t * (ACT_BYTES >> 4);
+            for (int c = 0; c < n_chunks; ++c) {
+              tc::mbar_wait_addr(full0 + stage * 8, par);
+              tc::tcgen05_fence_after();
+              const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
+              tc::umma_bf16_w(d_tmem, a_lo, hi, b_lo, hi, idesc, acc0 || c != 0);
+              tc::umma_bf16_w(d_tmem, a_lo + ((2 * PLANE) >> 4), hi, b_lo + b_inc, hi, idesc, true);
+              static_assert(KC == 32, "two K=16 MMAs per weight chunk");
+              tc::umma_commit_addr(empty0 + stage * 8);
+              a_lo += (4 * PLANE) >> 4;
               if (++stage == NSTAGE) { stage = 0; par ^= 1; }
             }
             tc::umma_commit(&bars->acc_full[t]);

@@ -16,6 +16,14 @@
 #include <stdlib.h>
 #include "mlp_tc.cuh"
 
+// clock64 tracing of CTA 0 (tools/trace_fwd.py) is compiled in only with -DMCNERF_TC_TRACE: the probes sit in the
+// MMA issue loop, whose instruction count bounds the tensor-pipe utilisation.
+#ifdef MCNERF_TC_TRACE
+#define MC_TRACE(x) x
+#else
+#define MC_TRACE(x)
+#endif
+
 namespace mlptc {
 
 // ----------------------------------------------------------------------------------------- packing
@@ -298,41 +306,48 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
     }
   } else if (warp == W_MMA) {
     // ------------------------------------------------------------------ MMA issuer
+    // tcgen05.mma is asynchronous: the tensor pipe stays busy only if this one thread needs fewer cycles per MMA
+    // than the MMA takes (~128 for 128x256x16).  So everything per step is hoisted, descriptors advance by one
+    // 32-bit add, and the loop body is: wait, 2 MMAs, commit.
     if (lane == 0) {
       int stage = 0;
-      uint32_t par = 0, apar[2] = {0, 0};
+      uint32_t par = 0, apar = 0;
+      const uint32_t hi = tc::umma_desc_hi(128);
+      const uint32_t act_lo = tc::umma_desc_lo(tc::smem_u32(act), PLANE), enc_lo = tc::umma_desc_lo(tc::smem_u32(enc), PLANE);
+      const uint32_t wst_addr = tc::smem_u32(wst);
+      const uint32_t full0 = tc::smem_u32(&bars->w_full[0]), empty0 = tc::smem_u32(&bars->w_empty[0]);
       for (int it = 0; it < n_iter; ++it)
         for (int s = 0; s < n_steps; ++s) {
-          const Step& st = a.plan.s[s];
-          const uint32_t idesc = tc::umma_idesc_bf16(TM, st.N);
-          for (int t = 0; t < 2; ++t) {
-            tc::mbar_wait(&bars->a_ready[t], apar[t]);
-            if (a.dbg && blockIdx.x == 0 && it == 0) a.dbg[(0 + t) * 32 + s] = clock64();
-            apar[t] ^= 1;
-            tc::tcgen05_fence_after();
-            const uint32_t act_t = tc::smem_u32(act + t * ACT_BYTES), enc_t = tc::smem_u32(enc + t * ENC_BYTES);
-            for (int c = 0; c < st.n_chunks; ++c) {
-              long long tw0 = 0;
-              if (a.dbg) tw0 = clock64();
-              tc::mbar_wait(&bars->w_full[stage], par);
-              if (a.dbg && blockIdx.x == 0 && it == 0 && t == 0) a.dbg[7 * 32 + 16 + s] += clock64() - tw0;   // cycles waiting for weights
-              tc::tcgen05_fence_after();
-              uint32_t a_base;
-              if (st.a_src == A_ENC) a_base = enc_t + c * (KC / 8) * PLANE;
-              else if (st.a_src == A_ACT) a_base = act_t + c * (KC / 8) * PLANE;
-              else a_base = (c < ENCW / KC) ? enc_t + c * (KC / 8) * PLANE : act_t + (c - ENCW / KC) * (KC / 8) * PLANE;
-              const uint32_t b_base = tc::smem_u32(wst + stage * STAGE_BYTES);
+          const int N = a.plan.s[s].N, n_chunks = a.plan.s[s].n_chunks, a_src = a.plan.s[s].a_src;
+          const uint32_t idesc = tc::umma_idesc_bf16(TM, N);
+          const uint32_t b_lo0 = tc::umma_desc_lo(wst_addr, N * 16), b_inc = (2u * N * 16) >> 4;
 #pragma unroll
-              for (int kk = 0; kk < KC / 16; ++kk) {
-                uint64_t da = tc::umma_desc(a_base + kk * 2 * PLANE, PLANE, 128);
-                uint64_t db = tc::umma_desc(b_base + kk * 2 * st.N * 16, st.N * 16, 128);
-                tc::umma_bf16(tmem + t * 256, da, db, idesc, (c | kk) != 0);
-              }
-              tc::umma_commit_multicast(&bars->w_empty[stage], (uint16_t)3);
+          for (int t = 0; t < 2; ++t) {
+            tc::mbar_wait(&bars->a_ready[t], (apar >> t) & 1);
+            MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2) a.dbg[(0 + t) * 32 + s] = clock64();)
+            apar ^= 1u << t;
+            tc::tcgen05_fence_after();
+            const uint32_t d_tmem = tmem + t * 256;
+            const uint32_t act_t = act_lo + t * (ACT_BYTES >> 4), enc_t = enc_lo + t * (ENC_BYTES >> 4);
+            uint32_t a_lo = (a_src == A_ACT) ? act_t : enc_t;
+            // the skip layer reads the encoding tile first, then the activation tile
+            const int switch_c = (a_src == A_ENC_ACT) ? ENCW / KC : -1;
+            for (int c = 0; c < n_chunks; ++c) {
+              MC_TRACE(long long tw0 = a.dbg ? clock64() : 0;)
+              tc::mbar_wait_addr(full0 + stage * 8, par);
+              MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && t == 0) a.dbg[7 * 32 + 16 + s] += clock64() - tw0;)
+              tc::tcgen05_fence_after();
+              if (c == switch_c) a_lo = act_t;
+              const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
+              tc::umma_bf16_w(d_tmem, a_lo, hi, b_lo, hi, idesc, c != 0);
+              tc::umma_bf16_w(d_tmem, a_lo + ((2 * PLANE) >> 4), hi, b_lo + b_inc, hi, idesc, true);
+              static_assert(KC == 32, "two K=16 MMAs per weight chunk");
+              tc::umma_commit_multicast_addr(empty0 + stage * 8, (uint16_t)3);
+              a_lo += (4 * PLANE) >> 4;
               if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             }
             tc::umma_commit(&bars->acc_full[t]);
-            if (a.dbg && blockIdx.x == 0 && it == 0) a.dbg[(2 + t) * 32 + s] = clock64();
+            MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2) a.dbg[(2 + t) * 32 + s] = clock64();)
           }
         }
     }
@@ -359,7 +374,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
       for (int s = 0; s < n_steps; ++s) {
         const Step& st = a.plan.s[s];
         tc::mbar_wait(&bars->acc_full[t], par);
-        if (a.dbg && blockIdx.x == 0 && it == 0 && (warp & 7) == 0 && lane == 0) a.dbg[(4 + t) * 32 + s] = clock64();
+        MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && (warp & 7) == 0 && lane == 0) a.dbg[(4 + t) * 32 + s] = clock64();)
         par ^= 1;
         tc::tcgen05_fence_after();
         const float* bias = bias_s + st.bias_off;
@@ -479,7 +494,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
           tc::tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&bars->a_ready[t]);
-          if (a.dbg && blockIdx.x == 0 && it == 0 && (warp & 7) == 0 && lane == 0) a.dbg[(6 + t) * 32 + s] = clock64();
+          MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && (warp & 7) == 0 && lane == 0) a.dbg[(6 + t) * 32 + s] = clock64();)
         }
       }
     }
@@ -641,7 +656,7 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   if (stash) MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<true>, a));
   else MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<false>, a));
   MC_LAUNCHED();
-  if (a.dbg) {     // debug trace: clock64 deltas of CTA 0's first tile pair
+  if (a.dbg) {     // debug trace: clock64 deltas of CTA 0's third tile pair (steady state)
     cudaStreamSynchronize((cudaStream_t)stream);
     long long h[8 * 32];
     cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);

@@ -96,22 +96,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_tc_wgrad_k(const __grid_con
   } else if (warp == 1) {
     if (lane == 0 && n_stages_total > 0) {
       const uint32_t idesc = tc::umma_idesc_bf16(128, N, 1, 1);
+      // both operands MN-major: lead (K-direction) offset 128 B, stride (MN-direction) offset = one plane
+      const uint32_t hi = tc::umma_desc_hi(WG_PLANE);
+      const uint32_t s_lo0 = tc::umma_desc_lo(tc::smem_u32(smem), 128);
+      const uint32_t full0 = tc::smem_u32(&bars->full[0]), empty0 = tc::smem_u32(&bars->empty[0]);
       int stage = 0;
       uint32_t par = 0;
       for (int i = 0; i < n_stages_total; ++i) {
-        tc::mbar_wait(&bars->full[stage], par);
+        tc::mbar_wait_addr(full0 + stage * 8, par);
         tc::tcgen05_fence_after();
-        const uint32_t sA = tc::smem_u32(smem + stage * WG_STAGE), sB = sA + 32 * WG_PLANE;
+        const uint32_t a_lo = s_lo0 + stage * (WG_STAGE >> 4), b_lo = a_lo + ((32 * WG_PLANE) >> 4);
 #pragma unroll
         for (int k16 = 0; k16 < WG_ROWS / 16; ++k16) {
-          const uint64_t db = tc::umma_desc(sB + k16 * 256, 128, WG_PLANE);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint64_t da = tc::umma_desc(sA + h * 16 * WG_PLANE + k16 * 256, 128, WG_PLANE);
-            tc::umma_bf16(tmem + h * 256, da, db, idesc, (i | k16) != 0);
-          }
+          for (int h = 0; h < 2; ++h)
+            tc::umma_bf16_w(tmem + h * 256, a_lo + ((h * 16 * WG_PLANE + k16 * 256) >> 4), hi, b_lo + ((k16 * 256) >> 4), hi,
+                            idesc, (i | k16) != 0);
         }
-        tc::umma_commit(&bars->empty[stage]);
+        tc::umma_commit_addr(empty0 + stage * 8);
         if (++stage == WG_NSTAGE) { stage = 0; par ^= 1; }
       }
       tc::umma_commit(&bars->acc_full);

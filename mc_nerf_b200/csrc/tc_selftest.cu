@@ -57,6 +57,22 @@ __global__ void __launch_bounds__(128) tc_selftest_k(const __nv_bfloat16* __rest
   if (tid == 0) {
     const uint32_t idesc = tc::umma_idesc_bf16(128, N, mn_major, mn_major);
     const long long t0 = clock64();
+    if (variant & 4) {
+      // tight issue loop (K-major): descriptor words precomputed, one add per operand and MMA
+      const uint32_t a_hi = tc::umma_desc_hi(128), b_hi = a_hi;
+      const uint32_t a_lo0 = tc::umma_desc_lo(tc::smem_u32(sA), 128 * 16), b_lo0 = tc::umma_desc_lo(tc::smem_u32(sB), N * 16);
+      const uint32_t a_inc = (2 * 128 * 16) >> 4, b_inc = (2 * N * 16) >> 4;
+      const int nk = K / 16;
+      for (int rep = 0; rep < reps; ++rep) {
+        uint32_t a_lo = a_lo0, b_lo = b_lo0;
+        tc::umma_bf16_w(tmem, a_lo, a_hi, b_lo, b_hi, idesc, rep > 0);
+#pragma unroll 4
+        for (int k = 1; k < nk; ++k) {
+          a_lo += a_inc; b_lo += b_inc;
+          tc::umma_bf16_w(tmem, a_lo, a_hi, b_lo, b_hi, idesc, true);
+        }
+      }
+    } else
     for (int rep = 0; rep < reps; ++rep)
     for (int k0 = 0; k0 < K; k0 += 16) {
       uint64_t da, db;
@@ -98,7 +114,87 @@ __global__ void __launch_bounds__(128) tc_selftest_k(const __nv_bfloat16* __rest
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+// CTA-pair variant: D[256,N] = A[256,K] * B[N,K]^T with ONE tcgen05.mma.cta_group::2 stream issued by the leader CTA.
+// CTA r stages A rows [128r,+128) and B rows [N/2*r, +N/2) (K-major canonical images) and reads back D rows [128r,+128).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
+tc_selftest2_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int N, int K,
+               int reps, long long* cycles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int NH = N / 2;
+  uint8_t* sA = smem;                   // 128 x K
+  uint8_t* sB = smem + 128 * K * 2;     // N/2 x K
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 128 * K; i += 128) {
+    int r = i / K, k = i % K;
+    *reinterpret_cast<__nv_bfloat16*>(sA + canon_off(r, k, 128)) = A[(rank * 128 + r) * K + k];
+  }
+  for (int i = tid; i < NH * K; i += 128) {
+    int r = i / K, k = i % K;
+    *reinterpret_cast<__nv_bfloat16*>(sB + canon_off(r, k, NH)) = B[(rank * NH + r) * K + k];
+  }
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+  }
+  if (warp == 0) tc::tmem_alloc2(&tmem_base, 256);
+  tc::fence_proxy_async();
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::cluster_sync();              // both CTAs' operands are staged, barriers initialised
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = tc::umma_idesc_bf16(256, N);
+    const uint32_t hi = tc::umma_desc_hi(128);
+    const uint32_t a_lo0 = tc::umma_desc_lo(tc::smem_u32(sA), 128 * 16), b_lo0 = tc::umma_desc_lo(tc::smem_u32(sB), NH * 16);
+    const uint32_t a_inc = (2 * 128 * 16) >> 4, b_inc = (2 * NH * 16) >> 4;
+    const int nk = K / 16;
+    const long long t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep) {
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;
+      tc::umma2_bf16_w(tmem, a_lo, hi, b_lo, hi, idesc, rep > 0);
+#pragma unroll 4
+      for (int k = 1; k < nk; ++k) {
+        a_lo += a_inc; b_lo += b_inc;
+        tc::umma2_bf16_w(tmem, a_lo, hi, b_lo, hi, idesc, true);
+      }
+    }
+    tc::umma2_commit_multicast_addr(tc::smem_u32(&bar), (uint16_t)3);
+    const long long t1 = clock64();
+    tc::mbar_wait(&bar, 0);
+    if (cycles) { cycles[0] = t1 - t0; cycles[1] = clock64() - t0; }
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::tcgen05_fence_after();
+  const int row = tid;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tc::tmem_ld_wait();
+    for (int j = 0; j < 32 && c0 + j < N; ++j) D[(size_t)(rank * 128 + row) * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::cluster_sync();              // neither CTA frees tensor memory while the other may still be using the pair
+  if (warp == 0) tc::tmem_dealloc2(tmem, 256);
+}
+
 }  // namespace
+
+extern "C" int mcnerf_tc_selftest2(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int reps,
+                                   long long* cycles_out, void* stream) {
+  MC_ARG(A_bf16 && B_bf16 && D && N >= 32 && N <= 256 && N % 32 == 0 && K >= 16 && K % 16 == 0 && reps >= 1);
+  size_t smem = (size_t)(128 + N / 2) * K * 2;
+  MC_ARG(smem <= 200 * 1024);
+  MC_CUDA(cudaFuncSetAttribute(tc_selftest2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest2_k<<<2, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A_bf16, (const __nv_bfloat16*)B_bf16, D, N, K,
+                                                          reps, cycles_out);
+  MC_LAUNCHED();
+  return 0;
+}
 
 static int selftest_launch(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int mn_major, int reps,
                            long long* cycles, void* stream);

@@ -44,3 +44,19 @@ def test_mn_major_tile(N, K):
     if not err < 1e-2:
         alt = (run(A, B, N, K, 3) - ref).abs().max().item()
         pytest.fail(f"MN-major descriptor convention wrong: err={err}, with lead/stride swapped err={alt}")
+
+
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 256), (32, 256), (64, 32), (128, 16)])
+def test_cta_pair_tile(N, K):
+    """tcgen05.mma.cta_group::2: M = 256 over a CTA pair, each CTA holding 128 rows of A and N/2 rows of B."""
+    from mc_nerf_b200 import ops
+    from mc_nerf_b200._lib import lib
+    g = torch.Generator().manual_seed(N * 1000 + K + 2)
+    A = torch.randn(256, K, generator=g).to(DEV).bfloat16()
+    B = torch.randn(N, K, generator=g).to(DEV).bfloat16()
+    D = torch.full((256, N), float("nan"), device=DEV)
+    lib().call("mcnerf_tc_selftest2", ops._p(A, torch.bfloat16), ops._p(B, torch.bfloat16), ops._p(D), N, K, 1, None,
+               ops._stream())
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    assert (D - ref).abs().max().item() < 1e-2
