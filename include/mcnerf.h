@@ -260,9 +260,11 @@ int mcnerf_tc_mma_rate(const void* A_bf16, const void* B_bf16, float* D, int N, 
                        long long* cycles_out, void* stream);
 
 /* CTA-pair tile: D[256,N] = A[256,K] B[N,K]^T through tcgen05.mma.cta_group::2 (cluster of 2 CTAs, each holding
- * 128 rows of A and N/2 rows of B); reps/cycles_out as in mcnerf_tc_mma_rate (cycles_out may be NULL). */
+ * 128 rows of A and N/2 rows of B); reps/cycles_out as in mcnerf_tc_mma_rate (cycles_out may be NULL).
+ * bias (N floats, may be NULL): D += bias[n] through one extra MMA against a broadcast "ones" operand - the way the
+ * fused forward kernel adds its biases. */
 int mcnerf_tc_selftest2(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int reps,
-                        long long* cycles_out, void* stream);
+                        long long* cycles_out, const float* bias, void* stream);
 
 #ifdef __cplusplus
 }

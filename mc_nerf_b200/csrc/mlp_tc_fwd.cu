@@ -5,12 +5,17 @@
 // ref: model/mc_nerf.py:599-602/633-635 (sampling), model/net_block.py:20-35 (encoding), :67-78 (MLP),
 //      model/net_utils.py:154-169 (eval_sh).
 //
-// CTA = 10 warps on one SM, two 128-row tiles in flight (TMEM: 2 x 256 fp32 columns):
-//   warps 0-3 / 4-7 : input stage + epilogues of tile slot 0 / 1 (thread = row = TMEM lane)
-//   warp 8          : weight producer - 1-D bulk async copies (TMA engine) of pre-packed 16 KB UMMA-ready
-//                     chunks into a 4-deep ring, mbarrier full/empty
-//   warp 9          : MMA issuer - one thread issues tcgen05.mma (M=128, N<=256, K=16) for both slots,
-//                     alternating slots per layer so one slot's epilogue overlaps the other slot's MMAs
+// A CTA PAIR (cluster of 2, tcgen05 cta_group::2) works on four 128-row tiles: two slots per CTA, and every MMA
+// covers M = 256 rows (slot t of both CTAs) x N columns.  Each CTA stages only HALF of every weight chunk (its N/2
+// output features); the tensor cores exchange the halves, so the shared-memory traffic per MMA that bounded the
+// single-CTA version (A 4 KB + B 8 KB read + 8 KB of B filled per 128x256x16) drops to 4 + 4 + 4 KB.
+// CTA = 18 warps, two 128-row tiles in flight (TMEM: 2 x 256 fp32 columns):
+//   warps 0-7 / 8-15 : input stage + epilogues of tile slot 0 / 1 (TMEM lane quarter = warp % 4, column half = warp / 4 % 2)
+//   warp 16          : weight producer - 1-D bulk async copies (TMA engine) of pre-packed UMMA-ready half chunks
+//                      (64 reduction columns x N/2 rows = 16 KB) into a 3-deep ring, mbarrier full/empty
+//   warp 17          : leader CTA: MMA issuer - one thread issues tcgen05.mma.cta_group::2 (M=256, N<=256, K=16) for
+//                      both slots, alternating slots per layer so one slot's epilogue overlaps the other slot's MMAs;
+//                      peer CTA: relays "my half of the chunk has landed" to the leader's full barrier
 // Weights are re-streamed from L2 per tile (1.26 MB per net: L2 resident); activations never touch HBM in
 // inference; in training each layer's bf16 activation tile is also written to the stash for the backward pass.
 #include <stdlib.h>
@@ -29,6 +34,8 @@ namespace mlptc {
 // ----------------------------------------------------------------------------------------- packing
 // dst chunk image for a [N x K] K-major B operand: chunk c (32 k), plane kg (8 k), row n: ((c*4+kg)*N + n)*16 B.
 // value(n,k) = src[n*sn + kk*sk] with the 63->64 pad remap applied to k (pad_k) or n (pad_n): see pack_all_k.
+// Forward images use the CTA-pair layout instead: chunk C (KC2 = 64 k), half h (rows h*N/2 .. of the N output
+// features), plane kg (8 k), row nn: (((C*2+h)*8+kg)*(N/2) + nn)*16 B - each CTA's half chunk is contiguous.
 
 // ----------------------------------------------------------------------------------------- plan
 int build_layout(const mcnerf_mlp_params* p, PackLayout* L) {
@@ -121,6 +128,7 @@ struct PackJob {
   int64_t sn, sk;          // source strides of the (n, k) indices (floats); bias jobs: unused
   int N, K;                // packed extents (bias jobs: N = padded length, K = 1)
   int pad_k, pad_n, n_valid, k_valid;
+  int pair;                // 1: CTA-pair layout (forward images)
   int is_bias;             // 1: fp32 copy of n_valid floats padded with zeros to N
   size_t dst_off;          // byte offset in wf / wb (is_bias: float offset in the bias block)
   int dst_sel;             // 0: wf, 1: wb, 2: bias block
@@ -155,13 +163,20 @@ __global__ void __launch_bounds__(256) pack_all_k(const __grid_constant__ PackAr
   if (pj.pad_n) { if (n == 63) ok = false; else if (n > 63) ns = n - 1; }
   if (ns >= pj.n_valid || ks >= pj.k_valid) ok = false;
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>((pj.dst_sel == 0 ? a.wf : a.wb) + pj.dst_off);
-  dst[i] = __float2bfloat16(ok ? pj.src[ns * pj.sn + ks * pj.sk] : 0.f);
+  int64_t di = i;
+  if (pj.pair) {
+    const int kgi = (int)(t / N), NH = N / 2;
+    di = ((((int64_t)(kgi >> 3) * 2 + n / NH) * 8 + (kgi & 7)) * NH + n % NH) * 8 + j;
+  }
+  dst[di] = __float2bfloat16(ok ? pj.src[ns * pj.sn + ks * pj.sk] : 0.f);
 }
 
 // ----------------------------------------------------------------------------------------- forward kernel
 struct FwdArgs {
   Plan plan;
   const uint8_t* wpack;
+  int n_repl;            // weight image replicas (spread the L2 slices all CTAs read at once)
+  size_t repl_stride;
   const float* bias;
   int sig2_off;
   int bias_floats;
@@ -183,17 +198,20 @@ struct FwdArgs {
   int n_slots;
 };
 
-// The forward kernel trades one ring stage for an on-chip copy of every bias (+ w_sigma2): with 224 KB of the
-// 228 KB L1/shared array carved out as shared memory there is practically no L1 left, so __ldg'd biases came
-// from L2 (~300 cycles) inside the epilogue's dependent chain.
-constexpr int FSTAGE = 3;
+// Biases (+ w_sigma2) are read through the constant cache: every warp of a step reads the same 1 KB, the constant
+// path does not compete with the shared-memory data pipe that bounds this kernel (tensor-core operand reads, TMA
+// fills, activation stores), and the 15 KB they used to take in shared memory pay for a 4th ring stage.  (With
+// ~227 KB carved out as shared memory there is no L1 left, so __ldg'd biases would come from L2.)
+// The block is copied device-to-device into the symbol, stream-ordered, before each launch.
+constexpr int FSTAGE = 4;
 constexpr int BIAS_SMEM_FLOATS = (12 + 3) * 256 + 264;     // deepest supported network
+__constant__ float c_bias[BIAS_SMEM_FLOATS];
 struct __align__(16) SmemBars {
   uint64_t w_full[FSTAGE], w_empty[FSTAGE], a_ready[2], acc_full[2];
   uint32_t tmem_base;
 };
 
-constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + FSTAGE * STAGE_BYTES + BIAS_SMEM_FLOATS * 4 + 1024 + 256;
+constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + FSTAGE * STAGE_BYTES + 1024 + 256;
 // 18 warps: 8 epilogue warps per tile slot (two per TMEM lane quarter, splitting the 32-column blocks even/odd:
 // a single warp per scheduler cannot hide its own ALU/LDS latency), 1 weight producer, 1 MMA issuer.
 constexpr int FWD_THREADS = 576;
@@ -257,27 +275,25 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
   uint8_t* act = smem;                                   // [2][ACT_BYTES]
   uint8_t* enc = smem + 2 * ACT_BYTES;                   // [2][ENC_BYTES]
   uint8_t* wst = enc + 2 * ENC_BYTES;                    // [FSTAGE][STAGE_BYTES]
-  float* bias_s = reinterpret_cast<float*>(wst + FSTAGE * STAGE_BYTES);
-  float* sig_part = bias_s + BIAS_SMEM_FLOATS;           // [2 slots][128 rows] partial sigma.2 dot of warp set 1
+  float* sig_part = reinterpret_cast<float*>(wst + FSTAGE * STAGE_BYTES);   // [2 slots][128 rows] partial sigma.2 dot of warp set 1
   SmemBars* bars = reinterpret_cast<SmemBars*>(sig_part + 256);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   const int n_tiles = (rows + TM - 1) / TM;
   const int n_pairs = (n_tiles + 1) / 2;
   const int n_steps = a.plan.n_steps;
-  // CTA pairs (cluster of 2) share the weight stream: each CTA fetches half of every chunk and multicasts it to
-  // both, halving the L2 -> SM weight traffic that bounded the single-CTA version.  Both CTAs therefore run the
-  // same number of tile-pair iterations (surplus iterations work on an all-invalid tile).
+  // Both CTAs of a pair run the same number of tile-pair iterations (surplus iterations work on an all-invalid tile).
   const uint32_t crank = tc::cluster_ctarank();
   const int n_iter = (n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (tid == 0) {
-    for (int i = 0; i < FSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 2); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 8); /* one arrive per epilogue warp */ tc::mbar_init(&bars->acc_full[i], 1); }
+    // leader: a stage is full when its own half has landed (expect_tx arrive) AND the peer relayed the same for its half
+    for (int i = 0; i < FSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], crank == 0 ? 2 : 1); tc::mbar_init(&bars->w_empty[i], 1); }
+    // a_ready (leader's copy is the one waited on): one arrive per epilogue warp of BOTH CTAs
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 16); tc::mbar_init(&bars->acc_full[i], 1); }
     tc::mbar_init_fence();
   }
-  if (warp == W_MMA) tc::tmem_alloc(&bars->tmem_base, 512);
-  for (int i = tid; i < a.bias_floats; i += blockDim.x) bias_s[i] = a.bias[i];
+  if (warp == W_MMA) tc::tmem_alloc2(&bars->tmem_base, 512);
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::cluster_sync();            // peer barriers are initialised before anything is multicast into this CTA
@@ -285,69 +301,90 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == W_PROD) {
-    // ------------------------------------------------------------------ weight producer
+    // ------------------------------------------------------------------ weight producer (this CTA's half chunks)
     if (lane == 0) {
       int stage = 0;
       uint32_t par = 0;
+      const uint8_t* wsrc = a.wpack + (size_t)((blockIdx.x >> 1) % a.n_repl) * a.repl_stride;
       for (int it = 0; it < n_iter; ++it)
         for (int s = 0; s < n_steps; ++s) {
           const Step& st = a.plan.s[s];
-          const uint32_t bytes = (uint32_t)st.N * KC * 2, half = bytes / 2;
+          const uint32_t half = (uint32_t)(st.N / 2) * KC2 * 2;
+          const int nc2 = st.n_chunks * KC / KC2;
           for (int t = 0; t < 2; ++t)
-            for (int c = 0; c < st.n_chunks; ++c) {
-              tc::mbar_wait(&bars->w_empty[stage], par ^ 1);       // both CTAs are done with this stage
-              tc::mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
-              tc::bulk_g2s_multicast(wst + stage * STAGE_BYTES + crank * half,
-                                     a.wpack + st.w_off + (size_t)c * bytes + crank * half, half,
-                                     &bars->w_full[stage], (uint16_t)3);
+            for (int c = 0; c < nc2; ++c) {
+              tc::mbar_wait(&bars->w_empty[stage], par ^ 1);       // the pair's MMAs are done with this stage
+              MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && s == 2) a.dbg[9 * 32 + t * 4 + c] = clock64();)
+              tc::mbar_arrive_expect_tx(&bars->w_full[stage], half);
+              tc::bulk_g2s(wst + stage * STAGE_BYTES, wsrc + st.w_off + (size_t)(c * 2 + crank) * half, half,
+                           &bars->w_full[stage]);
               if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             }
         }
     }
   } else if (warp == W_MMA) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ MMA issuer (leader) / relay (peer)
     // tcgen05.mma is asynchronous: the tensor pipe stays busy only if this one thread needs fewer cycles per MMA
-    // than the MMA takes (~128 for 128x256x16).  So everything per step is hoisted, descriptors advance by one
-    // 32-bit add, and the loop body is: wait, 2 MMAs, commit.
-    if (lane == 0) {
+    // than the MMA takes (128 for 128x256x16 per SM).  So everything per step is hoisted, descriptors advance by
+    // one 32-bit add, and the loop body is: wait, 4 MMAs, commit.
+    if (lane == 0 && crank == 0) {
       int stage = 0;
       uint32_t par = 0, apar = 0;
       const uint32_t hi = tc::umma_desc_hi(128);
       const uint32_t act_lo = tc::umma_desc_lo(tc::smem_u32(act), PLANE), enc_lo = tc::umma_desc_lo(tc::smem_u32(enc), PLANE);
       const uint32_t wst_addr = tc::smem_u32(wst);
       const uint32_t full0 = tc::smem_u32(&bars->w_full[0]), empty0 = tc::smem_u32(&bars->w_empty[0]);
+      const uint32_t ardy0 = tc::smem_u32(&bars->a_ready[0]), accf0 = tc::smem_u32(&bars->acc_full[0]);
       for (int it = 0; it < n_iter; ++it)
         for (int s = 0; s < n_steps; ++s) {
-          const int N = a.plan.s[s].N, n_chunks = a.plan.s[s].n_chunks, a_src = a.plan.s[s].a_src;
-          const uint32_t idesc = tc::umma_idesc_bf16(TM, N);
-          const uint32_t b_lo0 = tc::umma_desc_lo(wst_addr, N * 16), b_inc = (2u * N * 16) >> 4;
+          const int N = a.plan.s[s].N, nc2 = a.plan.s[s].n_chunks * KC / KC2, a_src = a.plan.s[s].a_src;
+          const uint32_t idesc = tc::umma_idesc_bf16(2 * TM, N);
+          const uint32_t b_lo0 = tc::umma_desc_lo(wst_addr, (N / 2) * 16), b_inc = (2u * (N / 2) * 16) >> 4;
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            tc::mbar_wait(&bars->a_ready[t], (apar >> t) & 1);
+            tc::mbar_wait_addr(ardy0 + t * 8, (apar >> t) & 1);        // slot t of both CTAs holds the A operand
             MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2) a.dbg[(0 + t) * 32 + s] = clock64();)
             apar ^= 1u << t;
             tc::tcgen05_fence_after();
             const uint32_t d_tmem = tmem + t * 256;
             const uint32_t act_t = act_lo + t * (ACT_BYTES >> 4), enc_t = enc_lo + t * (ENC_BYTES >> 4);
             uint32_t a_lo = (a_src == A_ACT) ? act_t : enc_t;
-            // the skip layer reads the encoding tile first, then the activation tile
-            const int switch_c = (a_src == A_ENC_ACT) ? ENCW / KC : -1;
-            for (int c = 0; c < n_chunks; ++c) {
+            // the skip layer reads the encoding tile first (exactly one 64-column chunk), then the activation tile
+            const int switch_c = (a_src == A_ENC_ACT) ? ENCW / KC2 : -1;
+            for (int c = 0; c < nc2; ++c) {
               MC_TRACE(long long tw0 = a.dbg ? clock64() : 0;)
               tc::mbar_wait_addr(full0 + stage * 8, par);
               MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && t == 0) a.dbg[7 * 32 + 16 + s] += clock64() - tw0;)
+              MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && s == 2) a.dbg[8 * 32 + t * 16 + c * 2] = clock64();)
               tc::tcgen05_fence_after();
               if (c == switch_c) a_lo = act_t;
               const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
-              tc::umma_bf16_w(d_tmem, a_lo, hi, b_lo, hi, idesc, c != 0);
-              tc::umma_bf16_w(d_tmem, a_lo + ((2 * PLANE) >> 4), hi, b_lo + b_inc, hi, idesc, true);
-              static_assert(KC == 32, "two K=16 MMAs per weight chunk");
-              tc::umma_commit_multicast_addr(empty0 + stage * 8, (uint16_t)3);
-              a_lo += (4 * PLANE) >> 4;
+#pragma unroll
+              for (int j = 0; j < KC2 / 16; ++j)
+                tc::umma2_bf16_w(d_tmem, a_lo + j * ((2 * PLANE) >> 4), hi, b_lo + j * b_inc, hi, idesc, (c | j) != 0);
+              tc::umma2_commit_multicast_addr(empty0 + stage * 8, (uint16_t)3);
+              MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && s == 2) a.dbg[8 * 32 + t * 16 + c * 2 + 1] = clock64();)
+              a_lo += ((KC2 / 8) * PLANE) >> 4;
               if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             }
-            tc::umma_commit(&bars->acc_full[t]);
+            tc::umma2_commit_multicast_addr(accf0 + t * 8, (uint16_t)3);
             MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2) a.dbg[(2 + t) * 32 + s] = clock64();)
+          }
+        }
+    } else if (lane == 0) {
+      // peer CTA: tell the leader when this CTA's half of each stage has landed
+      int stage = 0;
+      uint32_t par = 0;
+      const uint32_t full0 = tc::smem_u32(&bars->w_full[0]);
+      const uint32_t leader_full0 = tc::mapa(full0, 0);
+      for (int it = 0; it < n_iter; ++it)
+        for (int s = 0; s < n_steps; ++s) {
+          const int n = 2 * (a.plan.s[s].n_chunks * KC / KC2);
+          for (int c = 0; c < n; ++c) {
+            tc::mbar_wait_addr(full0 + stage * 8, par);
+            MC_TRACE(if (a.dbg && blockIdx.x == 1 && it == 2 && s == 2) a.dbg[9 * 32 + 8 + c] = clock64();)
+            tc::mbar_arrive_remote(leader_full0 + stage * 8);
+            if (++stage == FSTAGE) { stage = 0; par ^= 1; }
           }
         }
     }
@@ -359,6 +396,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
     const uint32_t act_t = tc::smem_u32(act + t * ACT_BYTES), enc_t = tc::smem_u32(enc + t * ENC_BYTES);
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * 256;
     uint32_t par = 0;
+    const uint32_t a_ready_leader = tc::mapa(tc::smem_u32(&bars->a_ready[t]), 0);
     for (int it = 0; it < n_iter; ++it) {
       const int pair = blockIdx.x + it * gridDim.x;
       const int tile = 2 * pair + t;
@@ -369,7 +407,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
       tc::fence_proxy_async();
       tc::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars->a_ready[t]);
+      if (lane == 0) tc::mbar_arrive_remote(a_ready_leader);
       float sigma_raw = 0.f;
       for (int s = 0; s < n_steps; ++s) {
         const Step& st = a.plan.s[s];
@@ -377,7 +415,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
         MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && (warp & 7) == 0 && lane == 0) a.dbg[(4 + t) * 32 + s] = clock64();)
         par ^= 1;
         tc::tcgen05_fence_after();
-        const float* bias = bias_s + st.bias_off;
+        const float* bias = c_bias + st.bias_off;
         if (st.epi == EPI_OUT) {
           if (set != 0) continue;            // last step: nothing to arrive on
           uint32_t v[32];
@@ -418,7 +456,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
                                  ? a.stash + ((size_t)tile * a.n_slots + st.stash_slot) * ACT_BYTES
                                  : nullptr;
           const bool to_smem = st.epi == EPI_RELU;
-          const float* w2 = bias_s + a.sig2_off;
+          const float* w2 = c_bias + a.sig2_off;
           float dot = 0.f;
           uint32_t* gate_out = st_tile ? reinterpret_cast<uint32_t*>(a.stash_bits + ((size_t)tile * a.n_slots + st.stash_slot) * BITS_BYTES + q * 32)
                                        : nullptr;
@@ -428,8 +466,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
             uint32_t gbits = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 b0 = *reinterpret_cast<const float4*>(bias + cg * 32 + j * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(bias + cg * 32 + j * 8 + 4);
+              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+              if (a.debug != 5) {
+                b0 = *reinterpret_cast<const float4*>(bias + cg * 32 + j * 8);
+                b1 = *reinterpret_cast<const float4*>(bias + cg * 32 + j * 8 + 4);
+              }
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               float x[8];
 #pragma unroll
@@ -493,7 +534,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
           tc::fence_proxy_async();
           tc::tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&bars->a_ready[t]);
+          if (lane == 0) tc::mbar_arrive_remote(a_ready_leader);
           MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && (warp & 7) == 0 && lane == 0) a.dbg[(6 + t) * 32 + s] = clock64();)
         }
       }
@@ -502,7 +543,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::cluster_sync();            // no CTA leaves while its peer may still multicast into it / arrive on its barriers
-  if (warp == W_MMA) tc::tmem_dealloc(tmem, 512);
+  if (warp == W_MMA) tc::tmem_dealloc2(tmem, 512);
 }
 
 }  // namespace mlptc
@@ -541,7 +582,7 @@ extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb
                  int is_bias, size_t dst_off, int dst_sel) {
     PackJob& j = a.j[nj];
     j.src = src; j.sn = sn; j.sk = sk; j.N = N; j.K = K; j.pad_k = pad_k; j.pad_n = pad_n; j.n_valid = n_valid;
-    j.k_valid = k_valid; j.is_bias = is_bias; j.dst_off = dst_off; j.dst_sel = dst_sel;
+    j.k_valid = k_valid; j.is_bias = is_bias; j.dst_off = dst_off; j.dst_sel = dst_sel; j.pair = (dst_sel == 0);
     a.prefix[nj] = tot;
     tot += (int64_t)N * K;
     ++nj;
@@ -600,6 +641,18 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   FwdArgs a;
   a.plan = L.fwd;
   a.wpack = (const uint8_t*)wf;
+  a.n_repl = 1; a.repl_stride = 0;
+  {   // EXPERIMENT: replicate the weight image so that CTA pairs read different L2 slices
+    const char* e = getenv("MCNERF_TC_REPL");
+    int R = e ? atoi(e) : 1;
+    if (R > 1) {
+      static uint8_t* repl = nullptr; static size_t cap = 0;
+      size_t stride = (L.wf_bytes + 4095) & ~(size_t)4095; stride += 4096 * 3;   // odd-ish stride
+      if (cap < stride * R) { if (repl) cudaFree(repl); cudaMalloc(&repl, stride * R); cap = stride * R; }
+      for (int r = 0; r < R; ++r) cudaMemcpyAsync(repl + r * stride, wf, L.wf_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+      a.wpack = repl; a.n_repl = R; a.repl_stride = stride;
+    }
+  }
   a.bias = bias;
   a.sig2_off = L.sig2_off;
   a.bias_floats = L.bias_floats;
@@ -609,8 +662,8 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
     static long long* dbg_buf = nullptr;
     a.dbg = nullptr;
     if (a.debug == 7) {
-      if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * 32 * sizeof(long long));
-      cudaMemsetAsync(dbg_buf, 0, 8 * 32 * sizeof(long long), (cudaStream_t)stream);
+      if (!dbg_buf) cudaMalloc(&dbg_buf, 10 * 32 * sizeof(long long));
+      cudaMemsetAsync(dbg_buf, 0, 10 * 32 * sizeof(long long), (cudaStream_t)stream);
       a.dbg = dbg_buf;
     }
   }
@@ -653,12 +706,14 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  MC_CUDA(cudaMemcpyToSymbolAsync(c_bias, bias, (size_t)L.bias_floats * sizeof(float), 0, cudaMemcpyDeviceToDevice,
+                                  (cudaStream_t)stream));
   if (stash) MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<true>, a));
   else MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<false>, a));
   MC_LAUNCHED();
   if (a.dbg) {     // debug trace: clock64 deltas of CTA 0's third tile pair (steady state)
     cudaStreamSynchronize((cudaStream_t)stream);
-    long long h[8 * 32];
+    long long h[10 * 32];
     cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
     const char* names[8] = {"mma:a_rdy0", "mma:a_rdy1", "mma:iss0", "mma:iss1", "epi:full0", "epi:full1",
                             "epi:arr0", "epi:arr1"};
@@ -667,6 +722,18 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
       printf("step %2d:", s);
       for (int e = 0; e < 8; ++e) printf(" %s=%lld", names[e], h[e * 32 + s] ? h[e * 32 + s] - t0 : -1);
       printf(" wait_w0=%lld\n", h[7 * 32 + 16 + s]);
+    }
+    printf("step 2 producer(CTA0) after-empty-wait:");
+    for (int c = 0; c < 8; ++c) printf(" %lld", h[9 * 32 + c] ? h[9 * 32 + c] - t0 : -1);
+    printf("\nstep 2 relay(CTA1) local-full seen:");
+    for (int c = 0; c < 8; ++c) printf(" %lld", h[9 * 32 + 8 + c] ? h[9 * 32 + 8 + c] - t0 : -1);
+    printf("\nstep 2 leader own-full seen:");
+    for (int c = 0; c < 8; ++c) printf(" %lld", h[9 * 32 + 16 + c] ? h[9 * 32 + 16 + c] - t0 : -1);
+    printf("\n");
+    for (int t = 0; t < 2; ++t) {
+      printf("step 2 slot %d chunks (after wait / after commit):", t);
+      for (int c = 0; c < 8; ++c) printf(" %lld", h[8 * 32 + t * 16 + c] ? h[8 * 32 + t * 16 + c] - t0 : -1);
+      printf("\n");
     }
   }
   return 0;

@@ -179,10 +179,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// arrive on a barrier that lives in another CTA of the cluster (release at cluster scope: prior shared-memory
-// writes of this thread are visible to whoever acquires the barrier phase)
+// arrive on a barrier that lives in another CTA of the cluster.  Default (CTA-scope) semantics on purpose: a
+// cluster-scope acquire on the waiting side measured ~850 cycles per wait, and nothing here needs it - what the
+// arrive publishes is shared memory of the ARRIVING CTA, read only by that CTA's own tensor core (async proxy, made
+// visible by fence.proxy.async before the arrive) once the leader issues the pair MMA.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 
 // ------------------------------------------------------------------ UMMA descriptors

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128) tc_selftest_k(const __nv_bfloat16* __rest
 // CTA r stages A rows [128r,+128) and B rows [N/2*r, +N/2) (K-major canonical images) and reads back D rows [128r,+128).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128)
 tc_selftest2_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int N, int K,
-               int reps, long long* cycles) {
+               int reps, long long* cycles, const float* __restrict__ bias) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -126,10 +126,29 @@ tc_selftest2_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restr
   const int NH = N / 2;
   uint8_t* sA = smem;                   // 128 x K
   uint8_t* sB = smem + 128 * K * 2;     // N/2 x K
+  uint8_t* sOnes = sB + NH * K * 2;     // 2 core matrices: 8 rows x (1, 1, 0 ... 0) and zeros
+  uint8_t* sBias = sOnes + 256;         // N/2 x 16: (hi(b), lo(b), 0 ... 0)
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < 128 * K; i += 128) {
     int r = i / K, k = i % K;
     *reinterpret_cast<__nv_bfloat16*>(sA + canon_off(r, k, 128)) = A[(rank * 128 + r) * K + k];
+  }
+  if (bias) {
+    // the bias rides in the accumulator: one extra K=16 MMA whose A operand is a broadcast "ones" block (every
+    // 8-row group of the 128 rows reads the SAME 128-byte core matrix: stride-byte offset 0) and whose B operand
+    // holds the bias split into two bf16 (hi + lo reproduces the fp32 value to ~2^-17)
+    for (int i = tid; i < 128; i += 128) {
+      int r = i >> 3 & 7, j = i & 7;   // (unused r) fill 2 core matrices = 128 bf16
+      (void)r;
+      reinterpret_cast<__nv_bfloat16*>(sOnes)[i] = __float2bfloat16((i < 64 && j < 2) ? 1.f : 0.f);
+    }
+    for (int i = tid; i < NH * 16; i += 128) {
+      int r = i / 16, k = i % 16;
+      float b = bias[rank * NH + r];
+      __nv_bfloat16 hi = __float2bfloat16(b);
+      float v = k == 0 ? __bfloat162float(hi) : k == 1 ? b - __bfloat162float(hi) : 0.f;
+      *reinterpret_cast<__nv_bfloat16*>(sBias + canon_off(r, k, NH)) = __float2bfloat16(v);
+    }
   }
   for (int i = tid; i < NH * K; i += 128) {
     int r = i / K, k = i % K;
@@ -162,6 +181,9 @@ tc_selftest2_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restr
         tc::umma2_bf16_w(tmem, a_lo, hi, b_lo, hi, idesc, true);
       }
     }
+    if (bias)
+      tc::umma2_bf16_w(tmem, tc::umma_desc_lo(tc::smem_u32(sOnes), 128), tc::umma_desc_hi(0),
+                       tc::umma_desc_lo(tc::smem_u32(sBias), NH * 16), hi, idesc, true);
     tc::umma2_commit_multicast_addr(tc::smem_u32(&bar), (uint16_t)3);
     const long long t1 = clock64();
     tc::mbar_wait(&bar, 0);
@@ -185,13 +207,13 @@ tc_selftest2_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restr
 }  // namespace
 
 extern "C" int mcnerf_tc_selftest2(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int reps,
-                                   long long* cycles_out, void* stream) {
+                                   long long* cycles_out, const float* bias, void* stream) {
   MC_ARG(A_bf16 && B_bf16 && D && N >= 32 && N <= 256 && N % 32 == 0 && K >= 16 && K % 16 == 0 && reps >= 1);
-  size_t smem = (size_t)(128 + N / 2) * K * 2;
+  size_t smem = (size_t)(128 + N / 2) * K * 2 + 256 + (size_t)(N / 2) * 32;
   MC_ARG(smem <= 200 * 1024);
   MC_CUDA(cudaFuncSetAttribute(tc_selftest2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest2_k<<<2, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A_bf16, (const __nv_bfloat16*)B_bf16, D, N, K,
-                                                          reps, cycles_out);
+                                                          reps, cycles_out, bias);
   MC_LAUNCHED();
   return 0;
 }

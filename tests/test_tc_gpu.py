@@ -56,7 +56,14 @@ def test_cta_pair_tile(N, K):
     B = torch.randn(N, K, generator=g).to(DEV).bfloat16()
     D = torch.full((256, N), float("nan"), device=DEV)
     lib().call("mcnerf_tc_selftest2", ops._p(A, torch.bfloat16), ops._p(B, torch.bfloat16), ops._p(D), N, K, 1, None,
-               ops._stream())
+               None, ops._stream())
     torch.cuda.synchronize()
     ref = A.float() @ B.float().t()
     assert (D - ref).abs().max().item() < 1e-2
+    # bias folded into the accumulator by one more MMA (broadcast ones operand, bias as bf16 hi + lo)
+    bias = torch.randn(N, generator=g).to(DEV) * 3
+    D2 = torch.full((256, N), float("nan"), device=DEV)
+    lib().call("mcnerf_tc_selftest2", ops._p(A, torch.bfloat16), ops._p(B, torch.bfloat16), ops._p(D2), N, K, 1, None,
+               ops._p(bias), ops._stream())
+    torch.cuda.synchronize()
+    assert (D2 - D - bias[None, :]).abs().max().item() < 2e-4

@@ -25,7 +25,7 @@ for N, K in ((256, 256), (128, 256), (32, 256)):
     cyc = torch.zeros(2, dtype=torch.int64, device=DEV)
     reps = 64
     lib().call("mcnerf_tc_selftest2", ops._p(A, torch.bfloat16), ops._p(B, torch.bfloat16), ops._p(D), N, K, reps,
-               ops._p(cyc, torch.int64), ops._stream())
+               ops._p(cyc, torch.int64), None, ops._stream())
     torch.cuda.synchronize()
     n_mma = reps * K // 16
     print(f"cta_group::2 M=256 N={N} K={K}: issue {cyc[0].item()/n_mma:.1f} cyc/MMA, complete {cyc[1].item()/n_mma:.1f} cyc/MMA")

@@ -50,7 +50,7 @@ def timed(fn, n):
 
 
 n = 1 if profile else iters
-if not profile:
+if not profile or "--infer" in sys.argv:
     ms = timed(lambda: ops.mlp_tc_fwd(ps, tcw, tin, out, None), n)
     print(f"fwd inference   : rows={M} {ms:.3f} ms  {flop_f/ms/1e9:.1f} TFLOP/s")
 ms = timed(lambda: ops.mlp_tc_fwd(ps, tcw, tin, out, stash), n)
