@@ -11,6 +11,7 @@ constexpr int ENCW = 64;                     // encoding width padded 63 -> 64 (
 constexpr int KC = 32;                       // reduction elements per streamed weight chunk
 constexpr int NSTAGE = 4;                    // weight ring depth
 constexpr int STAGE_BYTES = WID * KC * 2;    // 16 KB
+constexpr int BIAS_K = 16;                   // forward images: reduction depth of the bias block appended to every step
 constexpr int KC2 = 64;                      // forward (CTA-pair) kernel: reduction elements per half chunk (N/2 rows x 64 k)
 constexpr int ACT_BYTES = TM * WID * 2;      // 64 KB: one activation tile image
 constexpr int ENC_BYTES = TM * ENCW * 2;     // 16 KB

@@ -51,7 +51,7 @@ int build_layout(const mcnerf_mlp_params* p, PackLayout* L) {
   auto add = [&](int a_src, int K, int N, int epi, int slot) {
     Step& s = P.s[ns];
     s.a_src = a_src; s.n_chunks = K / KC; s.N = N; s.epi = epi; s.w_off = off; s.bias_off = bias; s.stash_slot = slot;
-    off += (uint32_t)N * K * 2;
+    off += (uint32_t)N * K * 2 + (uint32_t)N * BIAS_K * 2;     // weight chunks, then the bias block (see pack_all_k)
     // transposed images: rows = inputs, reduction = outputs (N).  Encoding inputs get their own 64-row image.
     L->wb_enc[ns] = L->wb_main[ns] = 0;
     if (a_src == A_ENC) { L->wb_main[ns] = boff; boff += (uint32_t)ENCW * N * 2; }
@@ -122,13 +122,14 @@ int build_layout(const mcnerf_mlp_params* p, PackLayout* L) {
 
 // One launch packs every matrix of a network: a table of jobs, each thread resolves its job by a linear scan
 // over the (<= 48) element-count prefixes.
-constexpr int MAX_PACK_JOBS = 48;
+constexpr int MAX_PACK_JOBS = 64;
 struct PackJob {
   const float* src;
   int64_t sn, sk;          // source strides of the (n, k) indices (floats); bias jobs: unused
   int N, K;                // packed extents (bias jobs: N = padded length, K = 1)
   int pad_k, pad_n, n_valid, k_valid;
-  int pair;                // 1: CTA-pair layout (forward images)
+  int pair;                // 1: CTA-pair layout (forward images); 2: bias block of a forward image (src = bias[n]):
+                           //    rows n, 16 k: k=0 bf16(b), k=1 bf16(b - bf16(b)), rest 0 - multiplied by the ones operand
   int is_bias;             // 1: fp32 copy of n_valid floats padded with zeros to N
   size_t dst_off;          // byte offset in wf / wb (is_bias: float offset in the bias block)
   int dst_sel;             // 0: wf, 1: wb, 2: bias block
@@ -164,6 +165,15 @@ __global__ void __launch_bounds__(256) pack_all_k(const __grid_constant__ PackAr
   if (ns >= pj.n_valid || ks >= pj.k_valid) ok = false;
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>((pj.dst_sel == 0 ? a.wf : a.wb) + pj.dst_off);
   int64_t di = i;
+  if (pj.pair == 2) {
+    const int NH = N / 2, kgi = (int)(t / N);                      // K = 16: kgi in {0, 1}
+    di = (((int64_t)(n / NH) * 2 + kgi) * NH + n % NH) * 8 + j;
+    float b = n < pj.n_valid ? pj.src[n] : 0.f, v = 0.f;
+    const float hi = __bfloat162float(__float2bfloat16(b));
+    if (k == 0) v = hi; else if (k == 1) v = b - hi;
+    dst[di] = __float2bfloat16(v);
+    return;
+  }
   if (pj.pair) {
     const int kgi = (int)(t / N), NH = N / 2;
     di = ((((int64_t)(kgi >> 3) * 2 + n / NH) * 8 + (kgi & 7)) * NH + n % NH) * 8 + j;
@@ -175,13 +185,10 @@ __global__ void __launch_bounds__(256) pack_all_k(const __grid_constant__ PackAr
 struct FwdArgs {
   Plan plan;
   const uint8_t* wpack;
-  int n_repl;            // weight image replicas (spread the L2 slices all CTAs read at once)
-  size_t repl_stride;
   const float* bias;
   int sig2_off;
   int bias_floats;
   long long* dbg;        // MCNERF_TC_DEBUG=7: clock64 trace of CTA 0 [event][step] (see tools/trace_fwd.py)
-  int debug;             // timing experiments only (MCNERF_TC_DEBUG): 1 = epilogue skips math/stores, 2 = skips TMEM loads
   const float *rays_o, *rays_d, *jitter;
   mcnerf_sampling smp;
   const int32_t* sel_idx;
@@ -198,22 +205,23 @@ struct FwdArgs {
   int n_slots;
 };
 
-// Biases (+ w_sigma2) are read through the constant cache: every warp of a step reads the same 1 KB, the constant
-// path does not compete with the shared-memory data pipe that bounds this kernel (tensor-core operand reads, TMA
-// fills, activation stores), and the 15 KB they used to take in shared memory pay for a 4th ring stage.  (With
-// ~227 KB carved out as shared memory there is no L1 left, so __ldg'd biases would come from L2.)
-// The block is copied device-to-device into the symbol, stream-ordered, before each launch.
+// Biases ride in the accumulator: every step ends with one extra K=16 MMA whose A operand is a broadcast "ones"
+// block (2 core matrices; stride-byte offset 0 makes all sixteen 8-row groups read the same one) and whose B operand
+// is the step's bias block (bf16 hi + lo) streamed through the ring like a small weight chunk.  That removes the
+// bias loads from the epilogue - through shared memory they competed with the tensor core's operand reads for the
+// data pipe, through the constant cache they cost 0.25 ms per 786k rows - and the 15 KB they used to occupy pay
+// for a 4th ring stage.
 constexpr int FSTAGE = 4;
-constexpr int BIAS_SMEM_FLOATS = (12 + 3) * 256 + 264;     // deepest supported network
-__constant__ float c_bias[BIAS_SMEM_FLOATS];
 struct __align__(16) SmemBars {
   uint64_t w_full[FSTAGE], w_empty[FSTAGE], a_ready[2], acc_full[2];
   uint32_t tmem_base;
 };
-
-constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + FSTAGE * STAGE_BYTES + 1024 + 256;
-// 18 warps: 8 epilogue warps per tile slot (two per TMEM lane quarter, splitting the 32-column blocks even/odd:
-// a single warp per scheduler cannot hide its own ALU/LDS latency), 1 weight producer, 1 MMA issuer.
+constexpr int ONES_BYTES = 256;
+constexpr int W2_FLOATS = 264;         // w_sigma2[256], b_sigma2, pad
+constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + FSTAGE * STAGE_BYTES + ONES_BYTES + W2_FLOATS * 4 + 128;
+// 18 warps: 16 epilogue warps (TMEM lane quarter = warp % 4, column quarter = warp / 4) that serve BOTH tile slots in
+// turn - the slot whose accumulator just completed gets all 16, four per scheduler, which is what hides the
+// TMEM-load / pack / store latency of one warp - plus 1 weight producer and 1 MMA issuer / relay.
 constexpr int FWD_THREADS = 576;
 constexpr int W_PROD = 16, W_MMA = 17;
 
@@ -224,6 +232,9 @@ __constant__ float cC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.315391
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
 // Encode one row (sample) into 64 bf16 features and store them as 8 planes of the enc tile image
@@ -275,8 +286,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
   uint8_t* act = smem;                                   // [2][ACT_BYTES]
   uint8_t* enc = smem + 2 * ACT_BYTES;                   // [2][ENC_BYTES]
   uint8_t* wst = enc + 2 * ENC_BYTES;                    // [FSTAGE][STAGE_BYTES]
-  float* sig_part = reinterpret_cast<float*>(wst + FSTAGE * STAGE_BYTES);   // [2 slots][128 rows] partial sigma.2 dot of warp set 1
-  SmemBars* bars = reinterpret_cast<SmemBars*>(sig_part + 256);
+  uint8_t* ones = wst + FSTAGE * STAGE_BYTES;            // broadcast ones operand of the bias MMAs
+  float* w2s = reinterpret_cast<float*>(ones + ONES_BYTES);   // w_sigma2[256], b_sigma2
+  SmemBars* bars = reinterpret_cast<SmemBars*>(w2s + W2_FLOATS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   const int n_tiles = (rows + TM - 1) / TM;
@@ -290,13 +302,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
     // leader: a stage is full when its own half has landed (expect_tx arrive) AND the peer relayed the same for its half
     for (int i = 0; i < FSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], crank == 0 ? 2 : 1); tc::mbar_init(&bars->w_empty[i], 1); }
     // a_ready (leader's copy is the one waited on): one arrive per epilogue warp of BOTH CTAs
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 16); tc::mbar_init(&bars->acc_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 32); tc::mbar_init(&bars->acc_full[i], 1); }
     tc::mbar_init_fence();
   }
   if (warp == W_MMA) tc::tmem_alloc2(&bars->tmem_base, 512);
+  for (int i = tid; i < 257; i += blockDim.x) w2s[i] = a.bias[a.sig2_off + i];
+  if (tid < 128)   // core matrix 0: 8 rows x (1, 1, 0, 0, 0, 0, 0, 0); core matrix 1: zeros
+    reinterpret_cast<__nv_bfloat16*>(ones)[tid] = __float2bfloat16((tid < 64 && (tid & 7) < 2) ? 1.f : 0.f);
+  tc::fence_proxy_async();
   tc::tcgen05_fence_before();
   __syncthreads();
-  tc::cluster_sync();            // peer barriers are initialised before anything is multicast into this CTA
+  tc::cluster_sync();            // peer barriers are initialised before anything arrives on them
   tc::tcgen05_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
@@ -305,18 +321,18 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t par = 0;
-      const uint8_t* wsrc = a.wpack + (size_t)((blockIdx.x >> 1) % a.n_repl) * a.repl_stride;
       for (int it = 0; it < n_iter; ++it)
         for (int s = 0; s < n_steps; ++s) {
           const Step& st = a.plan.s[s];
-          const uint32_t half = (uint32_t)(st.N / 2) * KC2 * 2;
+          const uint32_t half = (uint32_t)(st.N / 2) * KC2 * 2, bias_half = (uint32_t)(st.N / 2) * BIAS_K * 2;
           const int nc2 = st.n_chunks * KC / KC2;
+          const uint8_t* src = a.wpack + st.w_off;
           for (int t = 0; t < 2; ++t)
-            for (int c = 0; c < nc2; ++c) {
+            for (int c = 0; c <= nc2; ++c) {                        // c == nc2: the bias block
+              const uint32_t bytes = c < nc2 ? half : bias_half;
               tc::mbar_wait(&bars->w_empty[stage], par ^ 1);       // the pair's MMAs are done with this stage
-              MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && s == 2) a.dbg[9 * 32 + t * 4 + c] = clock64();)
-              tc::mbar_arrive_expect_tx(&bars->w_full[stage], half);
-              tc::bulk_g2s(wst + stage * STAGE_BYTES, wsrc + st.w_off + (size_t)(c * 2 + crank) * half, half,
+              tc::mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
+              tc::bulk_g2s(wst + stage * STAGE_BYTES, src + (size_t)c * 2 * half + (size_t)crank * bytes, bytes,
                            &bars->w_full[stage]);
               if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             }
@@ -330,8 +346,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
     if (lane == 0 && crank == 0) {
       int stage = 0;
       uint32_t par = 0, apar = 0;
-      const uint32_t hi = tc::umma_desc_hi(128);
+      const uint32_t hi = tc::umma_desc_hi(128), ones_hi = tc::umma_desc_hi(0);
       const uint32_t act_lo = tc::umma_desc_lo(tc::smem_u32(act), PLANE), enc_lo = tc::umma_desc_lo(tc::smem_u32(enc), PLANE);
+      const uint32_t ones_lo = tc::umma_desc_lo(tc::smem_u32(ones), 128);
       const uint32_t wst_addr = tc::smem_u32(wst);
       const uint32_t full0 = tc::smem_u32(&bars->w_full[0]), empty0 = tc::smem_u32(&bars->w_empty[0]);
       const uint32_t ardy0 = tc::smem_u32(&bars->a_ready[0]), accf0 = tc::smem_u32(&bars->acc_full[0]);
@@ -355,7 +372,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
               MC_TRACE(long long tw0 = a.dbg ? clock64() : 0;)
               tc::mbar_wait_addr(full0 + stage * 8, par);
               MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && t == 0) a.dbg[7 * 32 + 16 + s] += clock64() - tw0;)
-              MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && s == 2) a.dbg[8 * 32 + t * 16 + c * 2] = clock64();)
               tc::tcgen05_fence_after();
               if (c == switch_c) a_lo = act_t;
               const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
@@ -363,10 +379,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
               for (int j = 0; j < KC2 / 16; ++j)
                 tc::umma2_bf16_w(d_tmem, a_lo + j * ((2 * PLANE) >> 4), hi, b_lo + j * b_inc, hi, idesc, (c | j) != 0);
               tc::umma2_commit_multicast_addr(empty0 + stage * 8, (uint16_t)3);
-              MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && s == 2) a.dbg[8 * 32 + t * 16 + c * 2 + 1] = clock64();)
               a_lo += ((KC2 / 8) * PLANE) >> 4;
               if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             }
+            // + bias: ones[128 x 16] * bias_block[N x 16]^T
+            tc::mbar_wait_addr(full0 + stage * 8, par);
+            tc::tcgen05_fence_after();
+            tc::umma2_bf16_w(d_tmem, ones_lo, ones_hi, b_lo0 + stage * (STAGE_BYTES >> 4), hi, idesc, true);
+            tc::umma2_commit_multicast_addr(empty0 + stage * 8, (uint16_t)3);
+            if (++stage == FSTAGE) { stage = 0; par ^= 1; }
             tc::umma2_commit_multicast_addr(accf0 + t * 8, (uint16_t)3);
             MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2) a.dbg[(2 + t) * 32 + s] = clock64();)
           }
@@ -379,170 +400,157 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
       const uint32_t leader_full0 = tc::mapa(full0, 0);
       for (int it = 0; it < n_iter; ++it)
         for (int s = 0; s < n_steps; ++s) {
-          const int n = 2 * (a.plan.s[s].n_chunks * KC / KC2);
+          const int n = 2 * (a.plan.s[s].n_chunks * KC / KC2 + 1);
           for (int c = 0; c < n; ++c) {
             tc::mbar_wait_addr(full0 + stage * 8, par);
-            MC_TRACE(if (a.dbg && blockIdx.x == 1 && it == 2 && s == 2) a.dbg[9 * 32 + 8 + c] = clock64();)
             tc::mbar_arrive_remote(leader_full0 + stage * 8);
             if (++stage == FSTAGE) { stage = 0; par ^= 1; }
           }
         }
     }
   } else {
-    // ------------------------------------------------------------------ input stage + epilogues (slot t)
-    const int t = warp >> 3;
-    const int set = (warp >> 2) & 1;                  // which half of the 32-column blocks this warp owns
-    const int q = (warp & 3) * 32 + lane;             // row in tile == TMEM lane
-    const uint32_t act_t = tc::smem_u32(act + t * ACT_BYTES), enc_t = tc::smem_u32(enc + t * ENC_BYTES);
-    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * 256;
+    // ------------------------------------------------------------------ input stage + epilogues (both slots)
+    const int lq = warp & 3, cq = warp >> 2;          // TMEM lane quarter, accumulator column quarter
+    const int q = lq * 32 + lane;                     // row in tile == TMEM lane
+    const uint32_t act0 = tc::smem_u32(act), enc0 = tc::smem_u32(enc);
+    const uint32_t a_ready_leader = tc::mapa(tc::smem_u32(&bars->a_ready[0]), 0);
     uint32_t par = 0;
-    const uint32_t a_ready_leader = tc::mapa(tc::smem_u32(&bars->a_ready[t]), 0);
     for (int it = 0; it < n_iter; ++it) {
       const int pair = blockIdx.x + it * gridDim.x;
-      const int tile = 2 * pair + t;
-      const int row_g = tile * TM + q;
-      const bool valid = tile < n_tiles && row_g < rows;
-      uint8_t* st_enc = (TRAIN && tile < n_tiles) ? a.stash_enc + (size_t)tile * ENC_BYTES : nullptr;
-      if (set == 0) encode_row(a, row_g, valid, enc_t, q, st_enc);
+      if (cq < 2) {       // warps 0-3 encode the rows of slot 0, warps 4-7 those of slot 1
+        const int tile = 2 * pair + cq, row_g = tile * TM + q;
+        uint8_t* st_enc = (TRAIN && tile < n_tiles) ? a.stash_enc + (size_t)tile * ENC_BYTES : nullptr;
+        encode_row(a, row_g, tile < n_tiles && row_g < rows, enc0 + cq * ENC_BYTES, q, st_enc);
+      }
       tc::fence_proxy_async();
       tc::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive_remote(a_ready_leader);
-      float sigma_raw = 0.f;
+      if (lane == 0) { tc::mbar_arrive_remote(a_ready_leader); tc::mbar_arrive_remote(a_ready_leader + 8); }
+      float sig_dot[2] = {0.f, 0.f};                  // this warp's part of the sigma.2 dot product, per slot
       for (int s = 0; s < n_steps; ++s) {
         const Step& st = a.plan.s[s];
-        tc::mbar_wait(&bars->acc_full[t], par);
-        MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && (warp & 7) == 0 && lane == 0) a.dbg[(4 + t) * 32 + s] = clock64();)
-        par ^= 1;
-        tc::tcgen05_fence_after();
-        const float* bias = c_bias + st.bias_off;
-        if (st.epi == EPI_OUT) {
-          if (set != 0) continue;            // last step: nothing to arrive on
-          uint32_t v[32];
-          tc::tmem_ld32(taddr, v);
-          tc::tmem_ld_wait();
-          sigma_raw += sig_part[t * 128 + q];
-          if (valid) {
-            float sh[27];
 #pragma unroll
-            for (int i = 0; i < 27; ++i) sh[i] = __uint_as_float(v[i]) + bias[i];
-            const float* dp;
-            if (a.x_enc) dp = a.dirs_rows + (size_t)row_g * 3;
-            else {
-              int flat = a.sel_idx ? a.sel_idx[row_g] : row_g;
-              dp = a.rays_d + 3 * (size_t)(flat / a.smp.S);
+        for (int t = 0; t < 2; ++t) {
+          const int tile = 2 * pair + t, row_g = tile * TM + q;
+          const bool valid = tile < n_tiles && row_g < rows;
+          const uint32_t act_t = act0 + t * ACT_BYTES;
+          const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + t * 256;
+          tc::mbar_wait(&bars->acc_full[t], par);
+          MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && warp == 0 && lane == 0) a.dbg[(4 + t) * 32 + s] = clock64();)
+          tc::tcgen05_fence_after();
+          if (st.epi == EPI_OUT) {
+            // sigma.2: gather the four column-quarter partial sums through the (now idle) activation tile
+            float* part = reinterpret_cast<float*>(act + t * ACT_BYTES);
+            if (cq != 0) part[(cq - 1) * 128 + q] = sig_dot[t];
+            named_bar_sync(1 + t * 4 + lq, 128);       // the 4 warps of this lane quarter
+            if (cq != 0) continue;                     // last step: nothing to arrive on
+            uint32_t v[32];
+            tc::tmem_ld32(taddr, v);
+            tc::tmem_ld_wait();
+            const float sigma_raw = sig_dot[t] + part[q] + part[128 + q] + part[256 + q] + w2s[256];
+            if (valid) {
+              float sh[27];
+#pragma unroll
+              for (int i = 0; i < 27; ++i) sh[i] = __uint_as_float(v[i]);
+              const float* dp;
+              if (a.x_enc) dp = a.dirs_rows + (size_t)row_g * 3;
+              else {
+                int flat = a.sel_idx ? a.sel_idx[row_g] : row_g;
+                dp = a.rays_d + 3 * (size_t)(flat / a.smp.S);
+              }
+              float x = dp[0], y = dp[1], z = dp[2];
+              float Y[9] = {cC0, -cC1 * y, cC1 * z, -cC1 * x, cC2[0] * x * y, cC2[1] * y * z,
+                            cC2[2] * (2.f * z * z - x * x - y * y), cC2[3] * x * z, cC2[4] * (x * x - y * y)};
+              float c[3];
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) {
+                float acc = 0.f;
+#pragma unroll
+                for (int b = 0; b < 9; ++b) acc += Y[b] * sh[9 * ch + b];
+                c[ch] = sigmoid_f(acc);
+              }
+              reinterpret_cast<float4*>(a.out4)[row_g] = make_float4(sigma_raw, c[0], c[1], c[2]);
+              if (TRAIN) {
+                float4* dst = reinterpret_cast<float4*>(a.stash_sh + (size_t)row_g * SH_LD);
+#pragma unroll
+                for (int i = 0; i < 7; ++i)
+                  dst[i] = make_float4(sh[4 * i], sh[4 * i + 1], sh[4 * i + 2], i < 6 ? sh[4 * i + 3] : 0.f);
+              }
             }
-            float x = dp[0], y = dp[1], z = dp[2];
-            float Y[9] = {cC0, -cC1 * y, cC1 * z, -cC1 * x, cC2[0] * x * y, cC2[1] * y * z,
-                          cC2[2] * (2.f * z * z - x * x - y * y), cC2[3] * x * z, cC2[4] * (x * x - y * y)};
-            float c[3];
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              float acc = 0.f;
-#pragma unroll
-              for (int b = 0; b < 9; ++b) acc += Y[b] * sh[9 * ch + b];
-              c[ch] = sigmoid_f(acc);
-            }
-            reinterpret_cast<float4*>(a.out4)[row_g] = make_float4(sigma_raw, c[0], c[1], c[2]);
-            if (TRAIN) {
-              float4* dst = reinterpret_cast<float4*>(a.stash_sh + (size_t)row_g * SH_LD);
-#pragma unroll
-              for (int i = 0; i < 7; ++i)
-                dst[i] = make_float4(sh[4 * i], sh[4 * i + 1], sh[4 * i + 2], i < 6 ? sh[4 * i + 3] : 0.f);
-            }
+            continue;
           }
-        } else {
           uint8_t* st_tile = (TRAIN && st.stash_slot >= 0 && tile < n_tiles)
                                  ? a.stash + ((size_t)tile * a.n_slots + st.stash_slot) * ACT_BYTES
                                  : nullptr;
           const bool to_smem = st.epi == EPI_RELU;
-          const float* w2 = c_bias + a.sig2_off;
           float dot = 0.f;
           uint32_t* gate_out = st_tile ? reinterpret_cast<uint32_t*>(a.stash_bits + ((size_t)tile * a.n_slots + st.stash_slot) * BITS_BYTES + q * 32)
                                        : nullptr;
-          // one 32-column block of the accumulator: +bias, ReLU, bf16, -> next A operand (smem) / stash / sigma dot
+          // one 32-column block of the accumulator (bias already in it): ReLU, bf16, -> next A operand (smem) / stash /
+          // sigma dot
           auto block = [&](const uint32_t (&v)[32], int cg) {
-            if (a.debug == 1) { if (v[0] == 0x7fc00001u && v[31] == 0x7fc00002u) dot += 1.f; return; }
             uint32_t gbits = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-              if (a.debug != 5) {
-                b0 = *reinterpret_cast<const float4*>(bias + cg * 32 + j * 8);
-                b1 = *reinterpret_cast<const float4*>(bias + cg * 32 + j * 8 + 4);
-              }
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-              float x[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[j * 8 + i]) + bb[i];
               uint32_t w[4];
               if (!to_smem) {       // sigma.0: the fp32 activations feed the sigma.2 dot product
-                const float4 s0 = *reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8);
-                const float4 s1 = *reinterpret_cast<const float4*>(w2 + cg * 32 + j * 8 + 4);
+                const float4 s0 = *reinterpret_cast<const float4*>(w2s + cg * 32 + j * 8);
+                const float4 s1 = *reinterpret_cast<const float4*>(w2s + cg * 32 + j * 8 + 4);
+                float x[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+                for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(v[j * 8 + i]), 0.f);
                 dot += x[0] * s0.x + x[1] * s0.y + x[2] * s0.z + x[3] * s0.w + x[4] * s1.x + x[5] * s1.y + x[6] * s1.z +
                        x[7] * s1.w;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) w[i] = tc::pack_bf16(x[2 * i], x[2 * i + 1]);
               } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) w[i] = tc::pack_bf16_relu(x[2 * i], x[2 * i + 1]);
+                for (int i = 0; i < 4; ++i)
+                  w[i] = tc::pack_bf16_relu(__uint_as_float(v[j * 8 + 2 * i]), __uint_as_float(v[j * 8 + 2 * i + 1]));
               }
               const int kg = cg * 4 + j;
               if (to_smem) st_shared_v4(act_t + kg * PLANE + q * 16, w[0], w[1], w[2], w[3]);
               if (TRAIN) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) gbits |= tc::gate_bits(w[i], j * 4 + i);
-                if (st_tile && a.debug != 3) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w[0], w[1], w[2], w[3]);
+                if (st_tile) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w[0], w[1], w[2], w[3]);
               }
             }
-            if (TRAIN && gate_out && a.debug != 4) gate_out[cg] = gbits;
+            if (TRAIN && gate_out) gate_out[cg] = gbits;
           };
-          // software pipeline: the TMEM load of block cg+1 is in flight while block cg is processed
-          // this warp owns blocks set, set+2, set+4, set+6; the next block's TMEM load flies while one is processed
+          // this warp owns the 32-column blocks 2cq and 2cq+1
           if (TRAIN) {
-            // training variant: one buffer (the extra stash/gate state would spill at 96 registers, and with
-            // the whole L1 carved out as shared memory a spill costs an L2 round trip); latency is hidden by
-            // the second warp of the lane quarter instead
+            // training variant: one buffer (the extra stash/gate state would spill at 96 registers, and with the
+            // whole L1 carved out as shared memory a spill costs an L2 round trip)
             uint32_t va[32];
 #pragma unroll 1
-            for (int cg = set; cg < WID / 32; cg += 2) {
+            for (int cg = 2 * cq; cg < 2 * cq + 2; ++cg) {
               tc::tmem_ld32(taddr + cg * 32, va);
               tc::tmem_ld_wait();
               block(va, cg);
             }
           } else {
             uint32_t va[32], vb[32];
-            tc::tmem_ld32(taddr + set * 32, va);
-#pragma unroll 1
-            for (int cg = set; cg < WID / 32; cg += 4) {
-              tc::tmem_ld_wait();
-              tc::tmem_ld32(taddr + (cg + 2) * 32, vb);
-              block(va, cg);
-              tc::tmem_ld_wait();
-              if (cg + 4 < WID / 32) tc::tmem_ld32(taddr + (cg + 4) * 32, va);
-              block(vb, cg + 2);
-            }
+            tc::tmem_ld32(taddr + (2 * cq) * 32, va);
+            tc::tmem_ld32(taddr + (2 * cq + 1) * 32, vb);
+            tc::tmem_ld_wait();
+            block(va, 2 * cq);
+            block(vb, 2 * cq + 1);
           }
-          if (!to_smem) {
-            if (set == 0) sigma_raw = dot + w2[256];
-            else sig_part[t * 128 + q] = dot;
-          }
-        }
-        if (s + 1 < n_steps) {
+          if (!to_smem) sig_dot[t] = dot;
           tc::fence_proxy_async();
           tc::tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive_remote(a_ready_leader);
-          MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && (warp & 7) == 0 && lane == 0) a.dbg[(6 + t) * 32 + s] = clock64();)
+          if (lane == 0) tc::mbar_arrive_remote(a_ready_leader + t * 8);
+          MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && warp == 0 && lane == 0) a.dbg[(6 + t) * 32 + s] = clock64();)
         }
+        par ^= 1;
       }
     }
   }
   tc::tcgen05_fence_before();
   __syncthreads();
-  tc::cluster_sync();            // no CTA leaves while its peer may still multicast into it / arrive on its barriers
+  tc::cluster_sync();            // no CTA leaves while its peer may still arrive on its barriers / read its operands
   if (warp == W_MMA) tc::tmem_dealloc2(tmem, 512);
 }
 
@@ -583,6 +591,7 @@ extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb
     PackJob& j = a.j[nj];
     j.src = src; j.sn = sn; j.sk = sk; j.N = N; j.K = K; j.pad_k = pad_k; j.pad_n = pad_n; j.n_valid = n_valid;
     j.k_valid = k_valid; j.is_bias = is_bias; j.dst_off = dst_off; j.dst_sel = dst_sel; j.pair = (dst_sel == 0);
+    if (dst_sel == 3) { j.dst_sel = 0; j.pair = 2; }
     a.prefix[nj] = tot;
     tot += (int64_t)N * K;
     ++nj;
@@ -612,6 +621,7 @@ extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb
       } else add(W, 1, ld, WID, sp.N, 0, 0, WID, n_out, 0, L.wb_main[s], 1);
     }
     add(bs, 0, 0, 256, 1, 0, 0, n_out, 0, 1, sp.bias_off, 2);
+    add(bs, 0, 0, sp.N, BIAS_K, 0, 0, n_out, BIAS_K, 0, sp.w_off + (size_t)sp.N * K * 2, 3);   // bias block of the forward image
   }
   add(p->W_sigma2, 0, 0, 256, 1, 0, 0, WID, 0, 1, L.sig2_off, 2);
   add(p->b_sigma2, 0, 0, 8, 1, 0, 0, 1, 0, 1, L.sig2_off + 256, 2);
@@ -641,33 +651,20 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   FwdArgs a;
   a.plan = L.fwd;
   a.wpack = (const uint8_t*)wf;
-  a.n_repl = 1; a.repl_stride = 0;
-  {   // EXPERIMENT: replicate the weight image so that CTA pairs read different L2 slices
-    const char* e = getenv("MCNERF_TC_REPL");
-    int R = e ? atoi(e) : 1;
-    if (R > 1) {
-      static uint8_t* repl = nullptr; static size_t cap = 0;
-      size_t stride = (L.wf_bytes + 4095) & ~(size_t)4095; stride += 4096 * 3;   // odd-ish stride
-      if (cap < stride * R) { if (repl) cudaFree(repl); cudaMalloc(&repl, stride * R); cap = stride * R; }
-      for (int r = 0; r < R; ++r) cudaMemcpyAsync(repl + r * stride, wf, L.wf_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-      a.wpack = repl; a.n_repl = R; a.repl_stride = stride;
-    }
-  }
   a.bias = bias;
   a.sig2_off = L.sig2_off;
   a.bias_floats = L.bias_floats;
-  {
-    const char* dbg = getenv("MCNERF_TC_DEBUG");
-    a.debug = dbg ? atoi(dbg) : 0;
+  a.dbg = nullptr;
+#ifdef MCNERF_TC_TRACE
+  if (const char* dbg = getenv("MCNERF_TC_DEBUG")) {
     static long long* dbg_buf = nullptr;
-    a.dbg = nullptr;
-    if (a.debug == 7) {
+    if (atoi(dbg) == 7) {
       if (!dbg_buf) cudaMalloc(&dbg_buf, 10 * 32 * sizeof(long long));
       cudaMemsetAsync(dbg_buf, 0, 10 * 32 * sizeof(long long), (cudaStream_t)stream);
       a.dbg = dbg_buf;
     }
   }
-  MC_ARG(L.bias_floats <= BIAS_SMEM_FLOATS);
+#endif
   a.rays_o = in->rays_o; a.rays_d = in->rays_d; a.jitter = in->jitter; a.smp = in->smp;
   a.sel_idx = in->sample_idx; a.n_rows = in->n_rows; a.n_rows_dev = in->n_rows_dev;
   a.x_enc = in->x_enc; a.ld_enc = in->ld_enc; a.dirs_rows = in->dirs_rows;
@@ -706,8 +703,6 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MC_CUDA(cudaMemcpyToSymbolAsync(c_bias, bias, (size_t)L.bias_floats * sizeof(float), 0, cudaMemcpyDeviceToDevice,
-                                  (cudaStream_t)stream));
   if (stash) MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<true>, a));
   else MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<false>, a));
   MC_LAUNCHED();
