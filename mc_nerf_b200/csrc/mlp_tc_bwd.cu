@@ -3,6 +3,7 @@
 //   SH/sigmoid head backward (CUDA cores) -> dgrad GEMMs through sh.2, sh.0 + sigma.0, trunk layers D-1..1,
 //   layer 0 + the skip layer's encoding part (tcgen05, transposed weight images streamed by bulk copies)
 //   -> sin/cos encoding backward -> per-ray (dL/do, dL/dd) with a segmented warp reduction + atomics.
+// Runs on CTA pairs (tcgen05 cta_group::2) exactly like the forward kernel (mlp_tc_fwd.cu).
 // ReLU masks come from the forward activation stash; every layer's dY tile is written (bf16, UMMA tile image)
 // to the dY stash that the weight-gradient kernel (mlp_tc_wgrad.cu) consumes.
 // ref: autograd of model/net_block.py:67-78, model/net_utils.py:154-169, model/net_block.py:20-35.
@@ -35,11 +36,18 @@ struct BwdArgs {
   float* g_dirs_rows;             // explicit mode: [rows,3] overwritten
 };
 
+// CTA pair (tcgen05 cta_group::2) like the forward kernel: M = 256 rows per MMA (slot t of both CTAs), each CTA
+// stages half (N/2 rows) of every transposed weight chunk, the peer relays "my half landed" to the leader.
+constexpr int BSTAGE = 5;
 struct __align__(16) BwdBars {
-  uint64_t w_full[NSTAGE], w_empty[NSTAGE], a_ready[2], acc_full[2];
+  uint64_t w_full[BSTAGE], w_empty[BSTAGE], a_ready[2], acc_full[2];
   uint32_t tmem_base;
 };
-constexpr int SMEM_BWD = 2 * ACT_BYTES + 2 * HEAD_BYTES + NSTAGE * STAGE_BYTES + 1024 + 256;
+constexpr int SMEM_BWD = 2 * ACT_BYTES + 2 * HEAD_BYTES + BSTAGE * STAGE_BYTES + 1024 + 256;
+// 18 warps: 16 epilogue warps (TMEM lane quarter = warp % 4, accumulator column quarter = warp / 4) serving both tile
+// slots in turn, 1 weight producer, 1 MMA issuer (leader) / relay (peer).
+constexpr int BWD_THREADS = 576;
+constexpr int BW_PROD = 16, BW_MMA = 17;
 
 __constant__ float bC0 = 0.28209479177387814f;
 __constant__ float bC1 = 0.4886025119029199f;
@@ -70,116 +78,149 @@ __device__ __forceinline__ bool seg_reduce(int key, float (&v)[NV], int lane) {
 __device__ __forceinline__ uint32_t relu_gate2(uint32_t bits, int pos, float lo, float hi) {
   // bits: forward ReLU gate word of a 32-column block; element e = 2k+h (k = pair index, h = 0 lo / 1 hi) is at
   // bit k + 16h (tc::gate_bits).  `pos` = index of the lo element within the block (even).
-  const int k = pos >> 1;
-  float a = (bits >> k & 1u) ? lo : 0.f;
-  float b = (bits >> (16 + k) & 1u) ? hi : 0.f;
-  return tc::pack_bf16(a, b);
+  // ((bits >> k) & 0x10001) * 0xFFFF expands the two gate bits into a bf16x2 AND-mask (no carries between halves).
+  const uint32_t mask = ((bits >> (pos >> 1)) & 0x10001u) * 0xFFFFu;
+  return tc::pack_bf16(lo, hi) & mask;
 }
 
-__global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ BwdArgs a) {
+// chunk geometry of a job: reduction elements per ring stage (a K=32 job is a single half-size chunk)
+__device__ __forceinline__ int job_kc(int n_chunks) { return n_chunks * KC >= KC2 ? KC2 : n_chunks * KC; }
+
+__global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* bufX = smem;                                    // [2][ACT_BYTES]  dY tile (A operand)
   uint8_t* small = smem + 2 * ACT_BYTES;                   // [2][HEAD_BYTES] head-gradient tile
-  uint8_t* wst = small + 2 * HEAD_BYTES;                   // [NSTAGE][STAGE_BYTES]
-  float* w2s = reinterpret_cast<float*>(wst + NSTAGE * STAGE_BYTES);     // w_sigma2 [256] (no L1 left: keep it on chip)
+  uint8_t* wst = small + 2 * HEAD_BYTES;                   // [BSTAGE][STAGE_BYTES]
+  float* w2s = reinterpret_cast<float*>(wst + BSTAGE * STAGE_BYTES);     // w_sigma2 [256] (no L1 left: keep it on chip)
   BwdBars* bars = reinterpret_cast<BwdBars*>(w2s + 256);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   const int n_tiles = (rows + TM - 1) / TM;
   const int n_pairs = (n_tiles + 1) / 2;
   const int n_jobs = a.plan.n_jobs;
+  const uint32_t crank = tc::cluster_ctarank();
+  const int n_iter = (n_pairs + (int)gridDim.x - 1) / (int)gridDim.x;     // same trip count for both CTAs of a pair
 
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 4); /* one arrive per epilogue warp */ tc::mbar_init(&bars->acc_full[i], 1); }
+    for (int i = 0; i < BSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], crank == 0 ? 2 : 1); tc::mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 32); /* epilogue warps of both CTAs */ tc::mbar_init(&bars->acc_full[i], 1); }
     tc::mbar_init_fence();
   }
-  if (warp == 9) tc::tmem_alloc(&bars->tmem_base, 512);
+  if (warp == BW_MMA) tc::tmem_alloc2(&bars->tmem_base, 512);
   if (tid < 256) w2s[tid] = a.bias[a.sig2_off + tid];
   tc::tcgen05_fence_before();
   __syncthreads();
+  tc::cluster_sync();
   tc::tcgen05_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 8) {
+  if (warp == BW_PROD) {
     if (lane == 0) {
       int stage = 0;
       uint32_t par = 0;
-      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+      for (int it = 0; it < n_iter; ++it)
         for (int jn = 0; jn < n_jobs; ++jn) {
           const BJob& jb = a.plan.j[jn];
-          const uint32_t bytes = (uint32_t)jb.N * KC * 2;
+          const int kc = job_kc(jb.n_chunks), nc2 = jb.n_chunks * KC / kc;
+          const uint32_t half = (uint32_t)(jb.N / 2) * kc * 2;
           for (int t = 0; t < 2; ++t)
-            for (int c = 0; c < jb.n_chunks; ++c) {
+            for (int c = 0; c < nc2; ++c) {
               tc::mbar_wait(&bars->w_empty[stage], par ^ 1);
-              tc::mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
-              tc::bulk_g2s(wst + stage * STAGE_BYTES, a.wb + jb.w_off + (size_t)c * bytes, bytes, &bars->w_full[stage]);
-              if (++stage == NSTAGE) { stage = 0; par ^= 1; }
+              tc::mbar_arrive_expect_tx(&bars->w_full[stage], half);
+              tc::bulk_g2s(wst + stage * STAGE_BYTES, a.wb + jb.w_off + (size_t)(c * 2 + crank) * half, half,
+                           &bars->w_full[stage]);
+              if (++stage == BSTAGE) { stage = 0; par ^= 1; }
             }
         }
     }
-  } else if (warp == 9) {
-    // MMA issuer: per-job constants hoisted, descriptors advance by 32-bit adds (the single issuing thread has to
-    // stay below the ~128 cycles one 128x256x16 MMA takes, or the tensor pipe idles).
-    if (lane == 0) {
+  } else if (warp == BW_MMA) {
+    // MMA issuer (leader): per-job constants hoisted, descriptors advance by 32-bit adds (the single issuing thread
+    // has to stay below the 128 cycles one 128x256x16 MMA takes per SM, or the tensor pipe idles).
+    if (lane == 0 && crank == 0) {
       int stage = 0;
       uint32_t par = 0, apar = 0;
       const uint32_t hi = tc::umma_desc_hi(128);
       const uint32_t bufX_lo = tc::umma_desc_lo(tc::smem_u32(bufX), PLANE), small_lo = tc::umma_desc_lo(tc::smem_u32(small), PLANE);
       const uint32_t wst_addr = tc::smem_u32(wst);
       const uint32_t full0 = tc::smem_u32(&bars->w_full[0]), empty0 = tc::smem_u32(&bars->w_empty[0]);
-      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+      const uint32_t ardy0 = tc::smem_u32(&bars->a_ready[0]), accf0 = tc::smem_u32(&bars->acc_full[0]);
+      for (int it = 0; it < n_iter; ++it)
         for (int jn = 0; jn < n_jobs; ++jn) {
-          const int N = a.plan.j[jn].N, n_chunks = a.plan.j[jn].n_chunks;
+          const int N = a.plan.j[jn].N, kc = job_kc(a.plan.j[jn].n_chunks), nc2 = a.plan.j[jn].n_chunks * KC / kc;
           const bool a_small = a.plan.j[jn].a_small != 0, acc0 = a.plan.j[jn].accumulate != 0;
-          const uint32_t idesc = tc::umma_idesc_bf16(TM, N);
-          const uint32_t b_lo0 = tc::umma_desc_lo(wst_addr, N * 16), b_inc = (2u * N * 16) >> 4;
+          const uint32_t idesc = tc::umma_idesc_bf16(2 * TM, N);
+          const uint32_t b_lo0 = tc::umma_desc_lo(wst_addr, (N / 2) * 16), b_inc = (2u * (N / 2) * 16) >> 4;
+          const int n16 = kc / 16;
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            tc::mbar_wait(&bars->a_ready[t], (apar >> t) & 1);
+            tc::mbar_wait_addr(ardy0 + t * 8, (apar >> t) & 1);
             apar ^= 1u << t;
             tc::tcgen05_fence_after();
             const uint32_t d_tmem = tmem + t * 256;
             uint32_t a_lo = a_small ? small_lo + t * (HEAD_BYTES >> 4) : bufX_lo + t * (ACT_BYTES >> 4);
-            for (int c = 0; c < n_chunks; ++c) {
+            for (int c = 0; c < nc2; ++c) {
               tc::mbar_wait_addr(full0 + stage * 8, par);
               tc::tcgen05_fence_after();
               const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
-              tc::umma_bf16_w(d_tmem, a_lo, hi, b_lo, hi, idesc, acc0 || c != 0);
-              tc::umma_bf16_w(d_tmem, a_lo + ((2 * PLANE) >> 4), hi, b_lo + b_inc, hi, idesc, true);
-              static_assert(KC == 32, "two K=16 MMAs per weight chunk");
-              tc::umma_commit_addr(empty0 + stage * 8);
-              a_lo += (4 * PLANE) >> 4;
-              if (++stage == NSTAGE) { stage = 0; par ^= 1; }
+              tc::umma2_bf16_w(d_tmem, a_lo, hi, b_lo, hi, idesc, acc0 || c != 0);
+              tc::umma2_bf16_w(d_tmem, a_lo + ((2 * PLANE) >> 4), hi, b_lo + b_inc, hi, idesc, true);
+              if (n16 == 4) {
+                tc::umma2_bf16_w(d_tmem, a_lo + 2 * ((2 * PLANE) >> 4), hi, b_lo + 2 * b_inc, hi, idesc, true);
+                tc::umma2_bf16_w(d_tmem, a_lo + 3 * ((2 * PLANE) >> 4), hi, b_lo + 3 * b_inc, hi, idesc, true);
+              }
+              tc::umma2_commit_multicast_addr(empty0 + stage * 8, (uint16_t)3);
+              a_lo += ((KC2 / 8) * PLANE) >> 4;
+              if (++stage == BSTAGE) { stage = 0; par ^= 1; }
             }
-            tc::umma_commit(&bars->acc_full[t]);
+            tc::umma2_commit_multicast_addr(accf0 + t * 8, (uint16_t)3);
+          }
+        }
+    } else if (lane == 0) {
+      // peer CTA: tell the leader when this CTA's half of each stage has landed
+      int stage = 0;
+      uint32_t par = 0;
+      const uint32_t full0 = tc::smem_u32(&bars->w_full[0]);
+      const uint32_t leader_full0 = tc::mapa(full0, 0);
+      for (int it = 0; it < n_iter; ++it)
+        for (int jn = 0; jn < n_jobs; ++jn) {
+          const int n = 2 * (a.plan.j[jn].n_chunks * KC / job_kc(a.plan.j[jn].n_chunks));
+          for (int c = 0; c < n; ++c) {
+            tc::mbar_wait_addr(full0 + stage * 8, par);
+            tc::mbar_arrive_remote(leader_full0 + stage * 8);
+            if (++stage == BSTAGE) { stage = 0; par ^= 1; }
           }
         }
     }
   } else {
-    const int t = warp >> 2;
-    const int q = tid - t * 128;
-    const uint32_t bufX_t = tc::smem_u32(bufX + t * ACT_BYTES), small_t = tc::smem_u32(small + t * HEAD_BYTES);
-    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + t * 256;
+    const int lq = warp & 3, cq = warp >> 2;           // TMEM lane quarter, accumulator column quarter
+    const int q = lq * 32 + lane;                      // row in tile == TMEM lane
+    const uint32_t bufX0 = tc::smem_u32(bufX), small0 = tc::smem_u32(small);
+    const uint32_t a_ready_leader = tc::mapa(tc::smem_u32(&bars->a_ready[0]), 0);
     const float* w2 = w2s;
     uint32_t par = 0;
-    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int tile = 2 * pair + t;
-      const int row_g = tile * TM + q;
-      const bool valid = row_g < rows;
-      const bool tile_ok = tile < n_tiles;
-      const uint8_t* bits_tile = a.stash_bits + (size_t)tile * a.n_slots * BITS_BYTES + q * 32;
-      uint8_t* dy_tile = a.dy + (size_t)tile * a.n_slots * ACT_BYTES;
-      int ray = -1 - lane;
-      float z = 0.f;
-      if (valid && !a.x_enc) {
-        int flat = a.sel_idx ? a.sel_idx[row_g] : row_g;
-        ray = flat / a.smp.S;
-        z = linspace_f(a.smp.near_, a.smp.far_, a.smp.S, flat - ray * a.smp.S) + (a.jitter ? a.jitter[ray] : 0.f);
+    for (int it = 0; it < n_iter; ++it) {
+      const int pair = blockIdx.x + it * gridDim.x;
+      // per-slot row state of this thread (row q of slot t): needed by the column-split epilogues below
+      int ray[2];
+      float z[2], g_sigma[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int row_g = (2 * pair + t) * TM + q;
+        ray[t] = -1 - lane; z[t] = 0.f; g_sigma[t] = 0.f;
+        if (row_g < rows) {
+          if (!a.x_enc) {
+            int flat = a.sel_idx ? a.sel_idx[row_g] : row_g;
+            ray[t] = flat / a.smp.S;
+            z[t] = linspace_f(a.smp.near_, a.smp.far_, a.smp.S, flat - ray[t] * a.smp.S) + (a.jitter ? a.jitter[ray[t]] : 0.f);
+          }
+          g_sigma[t] = a.g_out4[4 * (size_t)row_g];
+        }
       }
-      // ---------------- head backward: eval_sh + sigmoid, builds the [128 x 32] head-gradient tile
-      float g_sigma = 0.f;
-      {
+      // ---------------- head backward: eval_sh + sigmoid, builds the [128 x 32] head-gradient tile.
+      // warps 0-3 own the rows of slot 0, warps 4-7 those of slot 1.
+      if (cq < 2) {
+        const int t = cq, tile = 2 * pair + t, row_g = tile * TM + q;
+        const bool valid = row_g < rows, tile_ok = tile < n_tiles;
         float hv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) hv[i] = 0.f;
@@ -187,7 +228,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
         if (valid) {
           const float4 g = reinterpret_cast<const float4*>(a.g_out4)[row_g];
           const float4 o = reinterpret_cast<const float4*>(a.out4)[row_g];
-          const float* dp = a.x_enc ? a.dirs_rows + (size_t)row_g * 3 : a.rays_d + 3 * (size_t)ray;
+          const float* dp = a.x_enc ? a.dirs_rows + (size_t)row_g * 3 : a.rays_d + 3 * (size_t)ray[t];
           const float x = dp[0], y = dp[1], zz = dp[2];
           const float Y[9] = {bC0, -bC1 * y, bC1 * zz, -bC1 * x, bC2[0] * x * y, bC2[1] * y * zz,
                               bC2[2] * (2.f * zz * zz - x * x - y * y), bC2[3] * x * zz, bC2[4] * (x * x - y * y)};
@@ -214,9 +255,9 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
           gd[1] = -bC1 * comb[1] + bC2[0] * x * comb[4] + bC2[1] * zz * comb[5] - 2.f * bC2[2] * y * comb[6] -
                   2.f * bC2[4] * y * comb[8];
           gd[2] = bC1 * comb[2] + bC2[1] * y * comb[5] + 4.f * bC2[2] * zz * comb[6] + bC2[3] * x * comb[7];
-          g_sigma = g.x;
-          hv[31] = g_sigma;
+          hv[31] = g.x;
         }
+        const uint32_t small_t = small0 + t * HEAD_BYTES;
 #pragma unroll
         for (int kg = 0; kg < 4; ++kg) {
           uint4 v = make_uint4(tc::pack_bf16(hv[kg * 8], hv[kg * 8 + 1]), tc::pack_bf16(hv[kg * 8 + 2], hv[kg * 8 + 3]),
@@ -227,139 +268,147 @@ __global__ void __launch_bounds__(320, 1) mlp_tc_bwd_k(const __grid_constant__ B
         if (a.x_enc) {
           if (valid) { a.g_dirs_rows[3 * (size_t)row_g] = gd[0]; a.g_dirs_rows[3 * (size_t)row_g + 1] = gd[1]; a.g_dirs_rows[3 * (size_t)row_g + 2] = gd[2]; }
         } else {
-          bool head = seg_reduce<3>(ray, gd, lane);
-          if (valid && head) { atomicAdd(a.g_rays_d + 3 * ray, gd[0]); atomicAdd(a.g_rays_d + 3 * ray + 1, gd[1]); atomicAdd(a.g_rays_d + 3 * ray + 2, gd[2]); }
+          bool head = seg_reduce<3>(ray[t], gd, lane);
+          if (valid && head) { atomicAdd(a.g_rays_d + 3 * ray[t], gd[0]); atomicAdd(a.g_rays_d + 3 * ray[t] + 1, gd[1]); atomicAdd(a.g_rays_d + 3 * ray[t] + 2, gd[2]); }
         }
       }
       tc::fence_proxy_async();
       tc::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bars->a_ready[t]);
+      if (lane == 0) { tc::mbar_arrive_remote(a_ready_leader); tc::mbar_arrive_remote(a_ready_leader + 8); }
 
       for (int jn = 0; jn < n_jobs; ++jn) {
         const BJob& jb = a.plan.j[jn];
-        // forward ReLU gate bits of this row (32 B), fetched BEFORE waiting for the accumulator
-        uint32_t gate[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (tile_ok && jb.mask_slot >= 0) {
-          const uint4* gp = reinterpret_cast<const uint4*>(bits_tile + (size_t)jb.mask_slot * BITS_BYTES);
-          const uint4 g0 = gp[0], g1 = gp[1];
-          gate[0] = g0.x; gate[1] = g0.y; gate[2] = g0.z; gate[3] = g0.w;
-          gate[4] = g1.x; gate[5] = g1.y; gate[6] = g1.z; gate[7] = g1.w;
-        }
-        tc::mbar_wait(&bars->acc_full[t], par);
-        par ^= 1;
-        tc::tcgen05_fence_after();
-        if (jb.kind == BK_MASK_STORE) {
-          uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES;
-          auto block = [&](const uint32_t (&v)[32], int cg, uint32_t gb) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+        for (int t = 0; t < 2; ++t) {
+          const int tile = 2 * pair + t, row_g = tile * TM + q;
+          const bool valid = row_g < rows, tile_ok = tile < n_tiles;
+          const uint32_t bufX_t = bufX0 + t * ACT_BYTES;
+          const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + t * 256;
+          uint8_t* dy_tile = a.dy + (size_t)tile * a.n_slots * ACT_BYTES;
+          // forward ReLU gate bits of this row for this warp's two 32-column blocks, fetched BEFORE waiting
+          uint32_t gate0 = 0, gate1 = 0;
+          if (tile_ok && jb.mask_slot >= 0) {
+            const uint2 gg = *reinterpret_cast<const uint2*>(a.stash_bits + ((size_t)tile * a.n_slots + jb.mask_slot) * BITS_BYTES +
+                                                              q * 32 + cq * 8);
+            gate0 = gg.x; gate1 = gg.y;
+          }
+          tc::mbar_wait(&bars->acc_full[t], par);
+          tc::tcgen05_fence_after();
+          if (jb.kind == BK_MASK_STORE) {
+            uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES;
+            auto block = [&](const uint32_t (&v)[32], int cg, uint32_t gb) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = relu_gate2(gb, j * 8 + 0, __uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+                o.y = relu_gate2(gb, j * 8 + 2, __uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+                o.z = relu_gate2(gb, j * 8 + 4, __uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+                o.w = relu_gate2(gb, j * 8 + 6, __uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+                sts_v4(bufX_t + (cg * 4 + j) * PLANE + q * 16, o);
+                if (tile_ok) *reinterpret_cast<uint4*>(dyo + stash_off(q, cg * 4 + j, 32)) = o;
+              }
+            };
+            uint32_t va[32], vb[32];
+            tc::tmem_ld32(taddr + (2 * cq) * 32, va);
+            tc::tmem_ld32(taddr + (2 * cq + 1) * 32, vb);
+            tc::tmem_ld_wait();
+            block(va, 2 * cq, gate0);
+            block(vb, 2 * cq + 1, gate1);
+          } else if (jb.kind == BK_SIGMA_INJECT) {
+            // d relu(sigma.0) pre-activation = g_sigma * w_sigma2 gated by the forward gate bits; the accumulator
+            // (gradient that arrived through sh.0) stays in TMEM and the next job accumulates onto it.
+            uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES;
+            const float gs = g_sigma[t];
+#pragma unroll
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const int kg = cq * 8 + k8;
+              const float4 s0 = *reinterpret_cast<const float4*>(w2 + kg * 8);
+              const float4 s1 = *reinterpret_cast<const float4*>(w2 + kg * 8 + 4);
+              const uint32_t gb = k8 < 4 ? gate0 : gate1;
+              const int pos = (kg & 3) * 8;
               uint4 o;
-              o.x = relu_gate2(gb, j * 8 + 0, __uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
-              o.y = relu_gate2(gb, j * 8 + 2, __uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
-              o.z = relu_gate2(gb, j * 8 + 4, __uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
-              o.w = relu_gate2(gb, j * 8 + 6, __uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-              sts_v4(bufX_t + (cg * 4 + j) * PLANE + q * 16, o);
-              if (tile_ok) *reinterpret_cast<uint4*>(dyo + stash_off(q, cg * 4 + j, 32)) = o;
+              o.x = relu_gate2(gb, pos + 0, gs * s0.x, gs * s0.y);
+              o.y = relu_gate2(gb, pos + 2, gs * s0.z, gs * s0.w);
+              o.z = relu_gate2(gb, pos + 4, gs * s1.x, gs * s1.y);
+              o.w = relu_gate2(gb, pos + 6, gs * s1.z, gs * s1.w);
+              sts_v4(bufX_t + kg * PLANE + q * 16, o);
+              if (tile_ok) *reinterpret_cast<uint4*>(dyo + stash_off(q, kg, 32)) = o;
             }
-          };
-          uint32_t va[32], vb[32];
-          tc::tmem_ld32(taddr, va);
+          } else if (jb.kind == BK_RELOAD_SKIP) {
+            // bring the skip layer's dY tile (written a few jobs ago by this very thread: same row, same columns)
+            // back as the A operand
+            const uint8_t* src = dy_tile + (size_t)a.plan.skip_dy_slot * ACT_BYTES;
 #pragma unroll
-          for (int cg = 0; cg < WID / 32; cg += 2) {
-            tc::tmem_ld_wait();
-            tc::tmem_ld32(taddr + (cg + 1) * 32, vb);
-            block(va, cg, gate[cg]);
-            tc::tmem_ld_wait();
-            if (cg + 2 < WID / 32) tc::tmem_ld32(taddr + (cg + 2) * 32, va);
-            block(vb, cg + 1, gate[cg + 1]);
-          }
-        } else if (jb.kind == BK_SIGMA_INJECT) {
-          // d relu(sigma.0) pre-activation = g_sigma * w_sigma2 gated by the forward gate bits; the accumulator
-          // (gradient that arrived through sh.0) stays in TMEM and the next job accumulates onto it.
-          uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES;
-#pragma unroll
-          for (int kg = 0; kg < WID / 8; ++kg) {
-            const float4 s0 = *reinterpret_cast<const float4*>(w2 + kg * 8);
-            const float4 s1 = *reinterpret_cast<const float4*>(w2 + kg * 8 + 4);
-            const uint32_t gb = gate[kg >> 2];
-            const int pos = (kg & 3) * 8;
-            uint4 o;
-            o.x = relu_gate2(gb, pos + 0, g_sigma * s0.x, g_sigma * s0.y);
-            o.y = relu_gate2(gb, pos + 2, g_sigma * s0.z, g_sigma * s0.w);
-            o.z = relu_gate2(gb, pos + 4, g_sigma * s1.x, g_sigma * s1.y);
-            o.w = relu_gate2(gb, pos + 6, g_sigma * s1.z, g_sigma * s1.w);
-            sts_v4(bufX_t + kg * PLANE + q * 16, o);
-            if (tile_ok) *reinterpret_cast<uint4*>(dyo + stash_off(q, kg, 32)) = o;
-          }
-        } else if (jb.kind == BK_RELOAD_SKIP) {
-          // bring the skip layer's dY tile (this thread's own row, written a few jobs ago) back as the A operand
-          const uint8_t* src = dy_tile + (size_t)a.plan.skip_dy_slot * ACT_BYTES;
-#pragma unroll 8
-          for (int kg = 0; kg < WID / 8; ++kg) {
-            const uint4 v = tile_ok ? *reinterpret_cast<const uint4*>(src + stash_off(q, kg, 32)) : make_uint4(0, 0, 0, 0);
-            sts_v4(bufX_t + kg * PLANE + q * 16, v);
-          }
-        } else {   // BK_ENC_OUT
-          float d[64];
-          {
-            uint32_t v[32];
-            tc::tmem_ld32(taddr, v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]);
-            tc::tmem_ld32(taddr + 32, v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) d[32 + i] = __uint_as_float(v[i]);
-          }
-          if (a.x_enc) {
-            if (valid) {
-              float* dst = a.g_x_enc + (size_t)row_g * a.ld_enc;
-#pragma unroll
-              for (int i = 0; i < 63; ++i) dst[i] = d[i];
+            for (int k8 = 0; k8 < 8; ++k8) {
+              const int kg = cq * 8 + k8;
+              const uint4 v = tile_ok ? *reinterpret_cast<const uint4*>(src + stash_off(q, kg, 32)) : make_uint4(0, 0, 0, 0);
+              sts_v4(bufX_t + kg * PLANE + q * 16, v);
             }
-          } else {
-            float gv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (valid) {
+          } else if (cq == 0) {   // BK_ENC_OUT: 64 accumulator columns, one thread per row
+            float d[64];
+            {
+              uint32_t v[32];
+              tc::tmem_ld32(taddr, v);
+              tc::tmem_ld_wait();
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                const float xc = a.rays_o[3 * ray + c] + a.rays_d[3 * ray + c] * z;
-                float sn, cs;
-                sincosf(xc, &sn, &cs);
-                float g = d[c], f = 1.f;
+              for (int i = 0; i < 32; ++i) d[i] = __uint_as_float(v[i]);
+              tc::tmem_ld32(taddr + 32, v);
+              tc::tmem_ld_wait();
 #pragma unroll
-                for (int kf = 0; kf < 10; ++kf) {
-                  g += a.smp.band_w[kf] * f * (d[3 + c * 20 + kf] * cs - d[3 + c * 20 + 10 + kf] * sn);
-                  const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
-                  sn = s2; cs = c2; f *= 2.f;
+              for (int i = 0; i < 32; ++i) d[32 + i] = __uint_as_float(v[i]);
+            }
+            if (a.x_enc) {
+              if (valid) {
+                float* dst = a.g_x_enc + (size_t)row_g * a.ld_enc;
+#pragma unroll
+                for (int i = 0; i < 63; ++i) dst[i] = d[i];
+              }
+            } else {
+              float gv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              const int ry = ray[t];
+              if (valid) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                  const float xc = a.rays_o[3 * ry + c] + a.rays_d[3 * ry + c] * z[t];
+                  float sn, cs;
+                  sincosf(xc, &sn, &cs);
+                  float g = d[c], f = 1.f;
+#pragma unroll
+                  for (int kf = 0; kf < 10; ++kf) {
+                    g += a.smp.band_w[kf] * f * (d[3 + c * 20 + kf] * cs - d[3 + c * 20 + 10 + kf] * sn);
+                    const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
+                    sn = s2; cs = c2; f *= 2.f;
+                  }
+                  gv[c] = g;
+                  gv[3 + c] = g * z[t];
                 }
-                gv[c] = g;
-                gv[3 + c] = g * z;
               }
-            }
-            bool head = seg_reduce<6>(ray, gv, lane);
-            if (valid && head) {
+              bool head = seg_reduce<6>(ry, gv, lane);
+              if (valid && head) {
 #pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                atomicAdd(a.g_rays_o + 3 * ray + c, gv[c]);
-                atomicAdd(a.g_rays_d + 3 * ray + c, gv[3 + c]);
+                for (int c = 0; c < 3; ++c) {
+                  atomicAdd(a.g_rays_o + 3 * ry + c, gv[c]);
+                  atomicAdd(a.g_rays_d + 3 * ry + c, gv[3 + c]);
+                }
               }
             }
           }
+          if (jn + 1 < n_jobs) {
+            tc::fence_proxy_async();
+            tc::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_remote(a_ready_leader + t * 8);
+          }
         }
-        if (jn + 1 < n_jobs) {
-          tc::fence_proxy_async();
-          tc::tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&bars->a_ready[t]);
-        }
+        par ^= 1;
       }
     }
   }
   tc::tcgen05_fence_before();
   __syncthreads();
-  if (warp == 9) tc::tmem_dealloc(tmem, 512);
+  tc::cluster_sync();            // no CTA leaves while its peer may still arrive on its barriers / read its operands
+  if (warp == BW_MMA) tc::tmem_dealloc2(tmem, 512);
 }
 
 }  // namespace mlptc
@@ -419,7 +468,22 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  mlp_tc_bwd_k<<<n_pairs < sms ? n_pairs : sms, 320, SMEM_BWD, st>>>(a);
+  {
+    int grid = n_pairs < sms ? n_pairs : sms;
+    grid = (grid + 1) & ~1;                                  // whole clusters of 2
+    if (grid > sms) grid = sms & ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(BWD_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BWD;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_bwd_k, a));
+  }
   MC_LAUNCHED();
   // weight gradients (tcgen05, reduction over all rows) and bias gradients (column sums of the dY stash)
   MC_ARG(sms <= WG_MAX_CTAS);

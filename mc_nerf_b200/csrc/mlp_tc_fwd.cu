@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(256) pack_all_k(const __grid_constant__ PackAr
     return;
   }
   if (pj.pair) {
-    const int kgi = (int)(t / N), NH = N / 2;
-    di = ((((int64_t)(kgi >> 3) * 2 + n / NH) * 8 + (kgi & 7)) * NH + n % NH) * 8 + j;
+    const int kgi = (int)(t / N), NH = N / 2, kgc = pj.K >= KC2 ? KC2 / 8 : pj.K / 8;   // k-groups per chunk
+    di = ((((int64_t)(kgi / kgc) * 2 + n / NH) * kgc + (kgi % kgc)) * NH + n % NH) * 8 + j;
   }
   dst[di] = __float2bfloat16(ok ? pj.src[ns * pj.sn + ks * pj.sk] : 0.f);
 }
@@ -590,7 +590,7 @@ extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb
                  int is_bias, size_t dst_off, int dst_sel) {
     PackJob& j = a.j[nj];
     j.src = src; j.sn = sn; j.sk = sk; j.N = N; j.K = K; j.pad_k = pad_k; j.pad_n = pad_n; j.n_valid = n_valid;
-    j.k_valid = k_valid; j.is_bias = is_bias; j.dst_off = dst_off; j.dst_sel = dst_sel; j.pair = (dst_sel == 0);
+    j.k_valid = k_valid; j.is_bias = is_bias; j.dst_off = dst_off; j.dst_sel = dst_sel; j.pair = 1;
     if (dst_sel == 3) { j.dst_sel = 0; j.pair = 2; }
     a.prefix[nj] = tot;
     tot += (int64_t)N * K;
