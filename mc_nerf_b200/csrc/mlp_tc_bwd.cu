@@ -297,24 +297,36 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
           tc::tcgen05_fence_after();
           if (jb.kind == BK_MASK_STORE) {
             uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES;
-            auto block = [&](const uint32_t (&v)[32], int cg, uint32_t gb) {
+            // this warp owns accumulator columns [64 cq, 64 cq + 64), walked in four 16-column halves with the TMEM
+            // load of the next half in flight while one is gated, packed, stored (next A operand + dY stash)
+            auto half = [&](const uint32_t (&v)[16], int h) {
+              const uint32_t gb = h < 2 ? gate0 : gate1;
+              const int pos0 = (h & 1) * 16, kg0 = cq * 8 + h * 2;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < 2; ++j) {
                 uint4 o;
-                o.x = relu_gate2(gb, j * 8 + 0, __uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
-                o.y = relu_gate2(gb, j * 8 + 2, __uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
-                o.z = relu_gate2(gb, j * 8 + 4, __uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
-                o.w = relu_gate2(gb, j * 8 + 6, __uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-                sts_v4(bufX_t + (cg * 4 + j) * PLANE + q * 16, o);
-                if (tile_ok) *reinterpret_cast<uint4*>(dyo + stash_off(q, cg * 4 + j, 32)) = o;
+                o.x = relu_gate2(gb, pos0 + j * 8 + 0, __uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+                o.y = relu_gate2(gb, pos0 + j * 8 + 2, __uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+                o.z = relu_gate2(gb, pos0 + j * 8 + 4, __uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+                o.w = relu_gate2(gb, pos0 + j * 8 + 6, __uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+                sts_v4(bufX_t + (kg0 + j) * PLANE + q * 16, o);
+                if (tile_ok) *reinterpret_cast<uint4*>(dyo + stash_off(q, kg0 + j, 32)) = o;
               }
             };
-            uint32_t va[32], vb[32];
-            tc::tmem_ld32(taddr + (2 * cq) * 32, va);
-            tc::tmem_ld32(taddr + (2 * cq + 1) * 32, vb);
+            uint32_t va[16], vb[16];
+            const uint32_t tcol = taddr + cq * 64;
+            tc::tmem_ld16(tcol, va);
             tc::tmem_ld_wait();
-            block(va, 2 * cq, gate0);
-            block(vb, 2 * cq + 1, gate1);
+            tc::tmem_ld16(tcol + 16, vb);
+            half(va, 0);
+            tc::tmem_ld_wait();
+            tc::tmem_ld16(tcol + 32, va);
+            half(vb, 1);
+            tc::tmem_ld_wait();
+            tc::tmem_ld16(tcol + 48, vb);
+            half(va, 2);
+            tc::tmem_ld_wait();
+            half(vb, 3);
           } else if (jb.kind == BK_SIGMA_INJECT) {
             // d relu(sigma.0) pre-activation = g_sigma * w_sigma2 gated by the forward gate bits; the accumulator
             // (gradient that arrived through sh.0) stays in TMEM and the next job accumulates onto it.

@@ -28,6 +28,7 @@
 #else
 #define MC_TRACE(x)
 #endif
+#define EPI_TRACE(k) MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && s == 2 && lane == 0 && (warp == 0 || warp == 15)) a.dbg[8 * 32 + (warp ? 16 : 0) + t * 8 + (k)] = clock64();)
 
 namespace mlptc {
 
@@ -486,16 +487,18 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
           float dot = 0.f;
           uint32_t* gate_out = st_tile ? reinterpret_cast<uint32_t*>(a.stash_bits + ((size_t)tile * a.n_slots + st.stash_slot) * BITS_BYTES + q * 32)
                                        : nullptr;
-          // one 32-column block of the accumulator (bias already in it): ReLU, bf16, -> next A operand (smem) / stash /
-          // sigma dot
-          auto block = [&](const uint32_t (&v)[32], int cg) {
-            uint32_t gbits = 0;
+          // 16 accumulator columns (bias already in them): ReLU, bf16 -> next A operand (smem) / stash / sigma dot.
+          // This warp owns columns [64 cq, 64 cq + 64) = 32-column blocks 2cq and 2cq+1, walked in four halves with
+          // the TMEM load of the next half in flight while one is processed.
+          uint32_t sbits = 0;
+          auto half = [&](const uint32_t (&v)[16], int h) {
+            const int col0 = cq * 64 + h * 16;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
               uint32_t w[4];
               if (!to_smem) {       // sigma.0: the fp32 activations feed the sigma.2 dot product
-                const float4 s0 = *reinterpret_cast<const float4*>(w2s + cg * 32 + j * 8);
-                const float4 s1 = *reinterpret_cast<const float4*>(w2s + cg * 32 + j * 8 + 4);
+                const float4 s0 = *reinterpret_cast<const float4*>(w2s + col0 + j * 8);
+                const float4 s1 = *reinterpret_cast<const float4*>(w2s + col0 + j * 8 + 4);
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = fmaxf(__uint_as_float(v[j * 8 + i]), 0.f);
@@ -508,40 +511,46 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
                 for (int i = 0; i < 4; ++i)
                   w[i] = tc::pack_bf16_relu(__uint_as_float(v[j * 8 + 2 * i]), __uint_as_float(v[j * 8 + 2 * i + 1]));
               }
-              const int kg = cg * 4 + j;
+              const int kg = col0 / 8 + j;
               if (to_smem) st_shared_v4(act_t + kg * PLANE + q * 16, w[0], w[1], w[2], w[3]);
-              if (TRAIN) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) gbits |= tc::gate_bits(w[i], j * 4 + i);
-                if (st_tile) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w[0], w[1], w[2], w[3]);
+              if (TRAIN && st_tile) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (TRAIN) {
+              sbits |= tc::sign_bits16(v, h & 1);
+              if (h & 1) {
+                if (gate_out) gate_out[2 * cq + (h >> 1)] = ~sbits;     // gate = accumulator > 0
+                sbits = 0;
               }
             }
-            if (TRAIN && gate_out) gate_out[cg] = gbits;
           };
-          // this warp owns the 32-column blocks 2cq and 2cq+1
-          if (TRAIN) {
-            // training variant: one buffer (the extra stash/gate state would spill at 96 registers, and with the
-            // whole L1 carved out as shared memory a spill costs an L2 round trip)
-            uint32_t va[32];
-#pragma unroll 1
-            for (int cg = 2 * cq; cg < 2 * cq + 2; ++cg) {
-              tc::tmem_ld32(taddr + cg * 32, va);
-              tc::tmem_ld_wait();
-              block(va, cg);
-            }
-          } else {
-            uint32_t va[32], vb[32];
-            tc::tmem_ld32(taddr + (2 * cq) * 32, va);
-            tc::tmem_ld32(taddr + (2 * cq + 1) * 32, vb);
+          EPI_TRACE(0)
+          {
+            uint32_t va[16], vb[16];
+            const uint32_t tcol = taddr + cq * 64;
+            tc::tmem_ld16(tcol, va);
             tc::tmem_ld_wait();
-            block(va, 2 * cq);
-            block(vb, 2 * cq + 1);
+            tc::tmem_ld16(tcol + 16, vb);
+            EPI_TRACE(1)
+            half(va, 0);
+            tc::tmem_ld_wait();
+            tc::tmem_ld16(tcol + 32, va);
+            half(vb, 1);
+            EPI_TRACE(2)
+            tc::tmem_ld_wait();
+            tc::tmem_ld16(tcol + 48, vb);
+            half(va, 2);
+            EPI_TRACE(3)
+            tc::tmem_ld_wait();
+            half(vb, 3);
+            EPI_TRACE(4)
           }
           if (!to_smem) sig_dot[t] = dot;
           tc::fence_proxy_async();
+          EPI_TRACE(5)
           tc::tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_remote(a_ready_leader + t * 8);
+          EPI_TRACE(6)
           MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && warp == 0 && lane == 0) a.dbg[(6 + t) * 32 + s] = clock64();)
         }
         par ^= 1;
@@ -718,18 +727,12 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
       for (int e = 0; e < 8; ++e) printf(" %s=%lld", names[e], h[e * 32 + s] ? h[e * 32 + s] - t0 : -1);
       printf(" wait_w0=%lld\n", h[7 * 32 + 16 + s]);
     }
-    printf("step 2 producer(CTA0) after-empty-wait:");
-    for (int c = 0; c < 8; ++c) printf(" %lld", h[9 * 32 + c] ? h[9 * 32 + c] - t0 : -1);
-    printf("\nstep 2 relay(CTA1) local-full seen:");
-    for (int c = 0; c < 8; ++c) printf(" %lld", h[9 * 32 + 8 + c] ? h[9 * 32 + 8 + c] - t0 : -1);
-    printf("\nstep 2 leader own-full seen:");
-    for (int c = 0; c < 8; ++c) printf(" %lld", h[9 * 32 + 16 + c] ? h[9 * 32 + 16 + c] - t0 : -1);
-    printf("\n");
-    for (int t = 0; t < 2; ++t) {
-      printf("step 2 slot %d chunks (after wait / after commit):", t);
-      for (int c = 0; c < 8; ++c) printf(" %lld", h[8 * 32 + t * 16 + c] ? h[8 * 32 + t * 16 + c] - t0 : -1);
-      printf("\n");
-    }
+    for (int w = 0; w < 2; ++w)
+      for (int t = 0; t < 2; ++t) {
+        printf("step 2 epilogue warp %d slot %d (woke, ld0 done, blk0 done, ld1 done, blk1 done, proxy fence, arrived):", w ? 15 : 0, t);
+        for (int k = 0; k < 7; ++k) printf(" %lld", h[8 * 32 + w * 16 + t * 8 + k] ? h[8 * 32 + w * 16 + t * 8 + k] - t0 : -1);
+        printf("\n");
+      }
   }
   return 0;
 }

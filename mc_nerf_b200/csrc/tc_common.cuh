@@ -279,6 +279,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // relu + round-to-nearest bf16 pack in ONE instruction (negative / NaN inputs clamp to +0)
@@ -291,6 +301,18 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
 // flag(lo) -> bit k, flag(hi) -> bit 16+k.  (x != 0  <=>  x + 0x7FFF carries into bit 15 of its half.)
 __device__ __forceinline__ uint32_t gate_bits(uint32_t packed, int k) {
   return ((packed + 0x7FFF7FFFu) >> (15 - k)) & (0x00010001u << k);
+}
+// ReLU gate flags straight from 16 fp32 accumulators (sign bits): element 2k -> bit k, element 2k+1 -> bit 16+k of
+// the half word `half` (0: columns 0-15 of the block -> k = 0..7, 1: columns 16-31 -> k = 8..15).  One funnel shift
+// per element; the caller ORs the halves and inverts once ("positive" = sign bit clear).
+__device__ __forceinline__ uint32_t sign_bits16(const uint32_t (&v)[16], int half) {
+  uint32_t hi = 0, lo = 0;
+#pragma unroll
+  for (int i = 7; i >= 0; --i) {
+    hi = __funnelshift_l(v[2 * i + 1], hi, 1);     // ends with element 2i+1 at bit i
+    lo = __funnelshift_l(v[2 * i], lo, 1);         // element 2i at bit i
+  }
+  return ((hi << 16) | lo) << (8 * half);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
