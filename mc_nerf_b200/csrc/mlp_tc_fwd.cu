@@ -215,16 +215,21 @@ struct FwdArgs {
 constexpr int FSTAGE = 4;
 struct __align__(16) SmemBars {
   uint64_t w_full[FSTAGE], w_empty[FSTAGE], a_ready[2], acc_full[2];
+  uint64_t st_full[2], st_done[2];      // training: activation tile of slot t is complete / has been copied to the stash
   uint32_t tmem_base;
 };
 constexpr int ONES_BYTES = 256;
 constexpr int W2_FLOATS = 264;         // w_sigma2[256], b_sigma2, pad
-constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + FSTAGE * STAGE_BYTES + ONES_BYTES + W2_FLOATS * 4 + 128;
+constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + FSTAGE * STAGE_BYTES + ONES_BYTES + W2_FLOATS * 4 + 256;
+static_assert(sizeof(SmemBars) <= 256 && SMEM_FWD <= 232448, "shared memory budget");
 // 18 warps: 16 epilogue warps (TMEM lane quarter = warp % 4, column quarter = warp / 4) that serve BOTH tile slots in
 // turn - the slot whose accumulator just completed gets all 16, four per scheduler, which is what hides the
 // TMEM-load / pack / store latency of one warp - plus 1 weight producer and 1 MMA issuer / relay.
-constexpr int FWD_THREADS = 576;
-constexpr int W_PROD = 16, W_MMA = 17;
+// Training adds 2 stash warps: they copy each finished activation tile shared memory -> HBM stash while the next
+// layer's MMAs read the same tile, so the 64 KB of stores per tile-layer leave the epilogue's critical path (issued by
+// the epilogue warps themselves they stretched it from ~2900 to ~4700 cycles).  20 warps keep the 96-register budget.
+constexpr int FWD_THREADS = 576, FWD_THREADS_TRAIN = 640;
+constexpr int W_PROD = 16, W_MMA = 17, W_STASH0 = 18;
 
 __constant__ float cC0 = 0.28209479177387814f;
 __constant__ float cC1 = 0.4886025119029199f;
@@ -282,7 +287,7 @@ __device__ __forceinline__ void encode_row(const FwdArgs& a, int row_g, bool val
 }
 
 template <bool TRAIN>
-__global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(TRAIN ? FWD_THREADS_TRAIN : FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_constant__ FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;                                   // [2][ACT_BYTES]
   uint8_t* enc = smem + 2 * ACT_BYTES;                   // [2][ENC_BYTES]
@@ -304,6 +309,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
     for (int i = 0; i < FSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], crank == 0 ? 2 : 1); tc::mbar_init(&bars->w_empty[i], 1); }
     // a_ready (leader's copy is the one waited on): one arrive per epilogue warp of BOTH CTAs
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 32); tc::mbar_init(&bars->acc_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->st_full[i], 16); tc::mbar_init(&bars->st_done[i], 2); }
     tc::mbar_init_fence();
   }
   if (warp == W_MMA) tc::tmem_alloc2(&bars->tmem_base, 512);
@@ -409,13 +415,52 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
           }
         }
     }
+  } else if (TRAIN && warp >= W_STASH0) {
+    // ------------------------------------------------------------------ stash warps: activation tile smem -> HBM
+    // warp-item = (plane p, 32-row block rb): 512 contiguous bytes on both sides; the two warps split the 128 items
+    const int sw = warp - W_STASH0;
+    uint32_t spar[2] = {0, 0};
+    for (int it = 0; it < n_iter; ++it) {
+      const int pair = blockIdx.x + it * gridDim.x;
+      for (int s = 0; s < n_steps; ++s) {
+        const Step& st = a.plan.s[s];
+        if (st.epi != EPI_RELU || st.stash_slot < 0) continue;
+        for (int t = 0; t < 2; ++t) {
+          const int tile = 2 * pair + t;
+          tc::mbar_wait(&bars->st_full[t], spar[t]);
+          spar[t] ^= 1;
+          if (tile < n_tiles) {
+            uint8_t* dst = a.stash + ((size_t)tile * a.n_slots + st.stash_slot) * ACT_BYTES;
+            const uint32_t src = tc::smem_u32(act + t * ACT_BYTES);
+#pragma unroll 1
+            for (int i0 = sw * 64; i0 < sw * 64 + 64; i0 += 8) {
+              uint4 v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int item = i0 + u, p = item >> 2, row = (item & 3) * 32 + lane;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+                             : "r"(src + p * PLANE + row * 16));
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int item = i0 + u, p = item >> 2, row = (item & 3) * 32 + lane;
+                *reinterpret_cast<uint4*>(dst + stash_off(row, p, 32)) = v[u];
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bars->st_done[t]);
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ input stage + epilogues (both slots)
     const int lq = warp & 3, cq = warp >> 2;          // TMEM lane quarter, accumulator column quarter
     const int q = lq * 32 + lane;                     // row in tile == TMEM lane
     const uint32_t act0 = tc::smem_u32(act), enc0 = tc::smem_u32(enc);
     const uint32_t a_ready_leader = tc::mapa(tc::smem_u32(&bars->a_ready[0]), 0);
-    uint32_t par = 0;
+    uint32_t par = 0, stpar = 0;
     for (int it = 0; it < n_iter; ++it) {
       const int pair = blockIdx.x + it * gridDim.x;
       if (cq < 2) {       // warps 0-3 encode the rows of slot 0, warps 4-7 those of slot 1
@@ -484,6 +529,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
                                  ? a.stash + ((size_t)tile * a.n_slots + st.stash_slot) * ACT_BYTES
                                  : nullptr;
           const bool to_smem = st.epi == EPI_RELU;
+          const bool direct_stash = TRAIN && !to_smem;          // sigma.0: its tile never exists in shared memory
+          if (TRAIN && to_smem) {                                // the stash warps are done copying the previous tile
+            tc::mbar_wait(&bars->st_done[t], (stpar >> t & 1) ^ 1);
+            stpar ^= 1u << t;
+          }
           float dot = 0.f;
           uint32_t* gate_out = st_tile ? reinterpret_cast<uint32_t*>(a.stash_bits + ((size_t)tile * a.n_slots + st.stash_slot) * BITS_BYTES + q * 32)
                                        : nullptr;
@@ -513,7 +563,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
               }
               const int kg = col0 / 8 + j;
               if (to_smem) st_shared_v4(act_t + kg * PLANE + q * 16, w[0], w[1], w[2], w[3]);
-              if (TRAIN && st_tile) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w[0], w[1], w[2], w[3]);
+              if (direct_stash && st_tile) *reinterpret_cast<uint4*>(st_tile + stash_off(q, kg, 32)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
             if (TRAIN) {
               sbits |= tc::sign_bits16(v, h & 1);
@@ -549,7 +599,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_tc_fwd_k(const __grid_cons
           EPI_TRACE(5)
           tc::tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive_remote(a_ready_leader + t * 8);
+          if (lane == 0) {
+            tc::mbar_arrive_remote(a_ready_leader + t * 8);
+            if (TRAIN && to_smem) tc::mbar_arrive(&bars->st_full[t]);
+          }
           EPI_TRACE(6)
           MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && warp == 0 && lane == 0) a.dbg[(6 + t) * 32 + s] = clock64();)
         }
@@ -704,7 +757,7 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   if (grid > sms) grid = sms & ~1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(FWD_THREADS);
+  cfg.blockDim = dim3(stash ? FWD_THREADS_TRAIN : FWD_THREADS);
   cfg.dynamicSmemBytes = SMEM_FWD;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
