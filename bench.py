@@ -203,7 +203,7 @@ def run_ours(args):
         traffic, traffic_src = None, None
         try:   # DRAM bytes per MLP evaluation from the committed ncu --set full capture (dram__bytes_read+write)
             summ = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
-            per_eval = sum(k["dram_bytes_per_eval"] for k in summ["kernels"].values())
+            per_eval = sum(k["dram_bytes_per_eval"] for n, k in summ["kernels"].items() if n != "mlp_tc_fwd_k<0>")   # <0> = inference variant
             traffic = round(per_eval * evals / 1e9, 3)
             traffic_src = "GB per step = ncu dram bytes/evaluation (fwd+bwd-chain+wgrad, profiles/r01_ncu_summary.json) x evaluations"
         except Exception:
