@@ -133,7 +133,7 @@ def run_ours(args):
     dev_batch = tuple(t.to(device) for t in batch)
     host_batch = tuple(t.pin_memory() for t in batch)
 
-    def step(data, read_loss):
+    def eager_step(data, read_loss):
         opt.zero_grad()
         loss_dict, _, _, _ = net(data, 25, STAGE, RATIO)
         loss = loss_fn(loss_dict, STAGE)
@@ -141,6 +141,19 @@ def run_ours(args):
         sync_grads()
         opt.step()
         return loss.item() if read_loss else loss
+
+    use_graph = args.graph and not (world > 1 and args.allreduce == "ddp")
+    if use_graph:      # forward + loss + backward replayed from one CUDA graph (mc_nerf_b200/graph.py); the gradient
+        from mc_nerf_b200.graph import GraphedTrainStep          # all-reduce and RAdam.step stay eager launches
+        gstep = GraphedTrainStep(model, loss_fn)
+
+        def step(data, read_loss):
+            loss = gstep(data, 25, STAGE, RATIO)
+            sync_grads()
+            opt.step()
+            return loss.item() if read_loss else loss
+    else:
+        step = eager_step
 
     def barrier():
         if world > 1:
@@ -169,10 +182,8 @@ def run_ours(args):
     sampler = ClockSampler(local, period=float(os.environ.get('MCNERF_CLOCK_PERIOD', '0.05'))) if rank == 0 and os.environ.get('MCNERF_NO_CLOCKS') is None else None
     if sampler:
         sampler.start()
-    n0 = lib().launch_count()
     ms, last = timed(dev_batch, False, args.steps)
     host_issue_ms = timed.host_ms
-    launches = lib().launch_count() - n0
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
         step(host_batch, True)
@@ -185,11 +196,14 @@ def run_ours(args):
     # per-kernel device time of the dominant kernels (CUDA events on the launching stream), 3 extra steps
     roof = None
     L = lib()
+    # (eager launches: the per-kernel events need host-side launches; no graph replay may follow an eager step)
     if rank == 0:
         L.profile_begin()
+    n0 = L.launch_count()
     for _ in range(3):                 # every rank steps (the step contains the gradient all-reduce)
-        step(dev_batch, False)
+        eager_step(dev_batch, False)
     barrier()
+    launches = (L.launch_count() - n0) // 3 * args.steps     # the graph replays exactly the eager step's kernels
     if rank == 0:
         prof = L.profile_end()
         from mc_nerf_b200 import render
@@ -233,7 +247,9 @@ def run_ours(args):
                                 parallelism=(f"dp{world}: one camera's {args.rays}-ray batch per rank, {args.allreduce} NCCL "
                                              "all-reduce of MLP+camera grads") if world > 1 else "single GPU",
                                 l2="per-step working set (activation stash > 3 GB) exceeds the 126 MB L2; no flush needed",
-                                precision=args.precision),
+                                precision=args.precision,
+                                issue=("CUDA-graph replay of forward+loss+backward per step (GraphedTrainStep); "
+                                       "gradient all-reduce and RAdam.step launched eagerly") if use_graph else "eager launches"),
                     e2e=dict(value=round(e2e, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                              ms_per_step=round(ms_e2e / args.steps, 3)),
                     gpu_launches=int(launches), host_issue_ms_per_step=round(host_issue_ms, 3), clocks=clocks, roofline=roof, cpu_baseline=cpu,
@@ -299,6 +315,8 @@ def main():
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--allreduce", default="flat", choices=["flat", "ddp"])
+    ap.add_argument("--no-graph", dest="graph", action="store_false", default=os.environ.get("MCNERF_BENCH_GRAPH", "1") != "0",
+                    help="issue every step with eager launches instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,70 @@
+"""CUDA-graph replay of the train step's device work: forward + loss + backward captured once, replayed per step.
+
+The reference's loop (main.py:78-92) issues ~100 kernel launches per step from Python; on a B200 the kernels of one
+4096-ray step take 3.9 ms while PyTorch needs ~3.1 ms of host time to issue them, so the host bounds multi-GPU
+scaling and the end-to-end rate.  GraphedTrainStep keeps the reference's objects (MC_Model, MC_NeRF_Loss, the
+optimiser) and replaces only HOW the launches are issued:
+
+    step = GraphedTrainStep(model, loss_fn)
+    for data in loader:                                   # data exactly as main.py hands it to the model
+        loss = step(data, epoch, epoch_type, cur_ratio)   # copies inputs, replays the graph; .grad is populated
+        optimizer.step()                                  # (gradient all-reduce first when distributed)
+
+What is baked into a captured graph and therefore part of its cache key: epoch, epoch_type, cur_ratio (they select the
+stage and the BARF frequency weights) and the input shapes.  Random draws are NOT baked: torch's CUDA generator is
+graph-aware, every replay consumes fresh Philox offsets in the reference's draw order.  The camera id is a device
+tensor, so one graph serves all cameras.  Gradients are produced by the graph into static buffers (the usual
+whole-network-capture contract): do not call optimizer.zero_grad() between replays, and do not accumulate.
+Drop every reference to losses / outputs of earlier EAGER steps of the same model before the first graphed step: a live
+eager autograd graph keeps its AccumulateGrad nodes bound to the default stream, which breaks the capture.
+Configurations whose forward needs the host (the reference's 128-samples-per-ray cap with its CPU randperm, active
+when samples*scale > 128) cannot be captured and raise.
+"""
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, loss_fn, warmup=3):
+        self.model, self.loss_fn, self.warmup = model, loss_fn, warmup
+        self._graphs = {}
+
+    def _eager(self, static, key):
+        epoch, epoch_type, ratio = key[:3]
+        loss_dict, _, _, _ = self.model(static, epoch, epoch_type, ratio)
+        loss = self.loss_fn(loss_dict, epoch_type)
+        loss.backward()
+        return loss
+
+    def _capture(self, data, key):
+        m = self.model
+        if m.sys_param["samples"] * m.sys_param["scale"] > 128:
+            raise RuntimeError("GraphedTrainStep: samples*scale > 128 activates the reference's host-side sample cap "
+                               "(CPU randperm + synchronisation); that step cannot be captured in a CUDA graph")
+        dev = torch.device(m.device)
+        static = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev).copy_(t) for t in data)
+        params = [p for p in m.parameters()]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                for p in params:
+                    p.grad = None
+                self._eager(static, key)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for p in params:
+            p.grad = None
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss = self._eager(static, key)
+        return g, static, loss
+
+    def __call__(self, data, epoch, epoch_type, cur_ratio):
+        key = (epoch, epoch_type, float(cur_ratio), tuple(tuple(t.shape) for t in data))
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = self._capture(data, key)
+        g, static, loss = ent
+        for s, t in zip(static, data):
+            s.copy_(t, non_blocking=True)
+        g.replay()
+        return loss

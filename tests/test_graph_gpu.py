@@ -1,0 +1,98 @@
+"""CUDA-graph replay of forward + loss + backward (mc_nerf_b200/graph.py) against the eager step.
+With the random draws pinned (the same device tensors returned on every call) graph replay must reproduce the
+eager loss and gradients; with torch's generator it must draw fresh numbers on every replay."""
+import pytest
+import torch
+
+from mc_nerf_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+STAGE = "GLOBAL_OPTIM_EPOCH"
+
+
+class FixedRNG:
+    """torch.randn / randperm / Tensor.uniform_ return the same device tensors on every call (cyclic queues)."""
+
+    def __init__(self, rng):
+        self.seq = dict(randn=[rng["noise_c"], rng["noise_sel"], rng["noise_f"]], randperm=[rng["perm"]],
+                        uniform=[rng["jitter"]])
+        self.seq = {k: [t.to(DEV) for t in v] for k, v in self.seq.items()}
+        self.pos = dict(randn=0, randperm=0, uniform=0)
+
+    def _next(self, kind):
+        t = self.seq[kind][self.pos[kind] % len(self.seq[kind])]
+        self.pos[kind] += 1
+        return t
+
+    def __enter__(self):
+        self._saved = (torch.randn, torch.randperm, torch.Tensor.uniform_)
+        me = self
+        torch.randn = lambda *size, **kw: me._next("randn").clone()
+        torch.randperm = lambda n, **kw: me._next("randperm").clone()
+        torch.Tensor.uniform_ = lambda self_t, a=0.0, b=1.0: self_t.copy_(me._next("uniform"))
+        return self
+
+    def __exit__(self, *a):
+        torch.randn, torch.randperm, torch.Tensor.uniform_ = self._saved
+
+
+def build(seed=0):
+    from mc_nerf_b200.model import MC_Model, MC_NeRF_Loss
+    sp = syn.make_sys_param(n_cam=6, img_h=24, img_w=32, batch=256, samples=16, scale=2, device=DEV, with_images=False)
+    sp["mlp_precision"] = "bf16"
+    torch.manual_seed(seed)
+    m = MC_Model(sp).to(DEV)
+    with torch.no_grad():
+        for k, v in syn.init_camera_weights(sp).items():
+            getattr(m, k).copy_(v)
+    return sp, m, MC_NeRF_Loss(sp)
+
+
+def grads(m):
+    return {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+
+def test_graph_replay_matches_eager_step():
+    from mc_nerf_b200.graph import GraphedTrainStep
+    # two identically initialised models: the graphed one must never have run an eager backward (an eager autograd
+    # graph pins its AccumulateGrad nodes to the default stream, see graph.py)
+    sp, m, loss_fn = build()
+    _, m_e, loss_fn_e = build()
+    rng = syn.draw_step_rng(sp, 256, seed=5)
+    batch = tuple(t.to(DEV) for t in syn.make_train_batch(sp, img_id=2, seed=3))
+    with FixedRNG(rng):
+        step = GraphedTrainStep(m, loss_fn)
+        loss_g = step(batch, 25, STAGE, 0.5)
+        g_g = grads(m)
+        loss_t = loss_fn_e(m_e(batch, 25, STAGE, 0.5)[0], STAGE)
+        loss_t.backward()
+        loss_e, g_e = loss_t.detach().clone(), grads(m_e)
+        assert abs(loss_g.item() - loss_e.item()) <= 1e-6 * abs(loss_e.item())
+        assert set(g_g) == set(g_e)
+        for k in g_e:     # ray-gradient atomics reorder: tiny differences in the camera-parameter gradients only
+            assert torch.allclose(g_g[k], g_e[k], rtol=1e-4, atol=1e-7), k
+        # inputs are re-read on replay: another camera / image gives another loss, the first one comes back
+        other = tuple(t.to(DEV) for t in syn.make_train_batch(sp, img_id=4, seed=9))
+        loss_o = step(other, 25, STAGE, 0.5).item()
+        assert abs(loss_o - loss_e.item()) > 1e-6
+        assert abs(step(batch, 25, STAGE, 0.5).item() - loss_e.item()) <= 1e-6 * abs(loss_e.item())
+
+
+def test_graph_replay_draws_fresh_random_numbers():
+    from mc_nerf_b200.graph import GraphedTrainStep
+    sp, m, loss_fn = build(1)
+    batch = tuple(t.to(DEV) for t in syn.make_train_batch(sp, img_id=1, seed=3))
+    step = GraphedTrainStep(m, loss_fn)
+    losses = {round(step(batch, 25, STAGE, 0.5).item(), 7) for _ in range(4)}
+    assert len(losses) > 1          # new pixels / jitter / noise on every replay
+
+
+def test_graph_rejects_host_side_sample_cap():
+    from mc_nerf_b200.graph import GraphedTrainStep
+    from mc_nerf_b200.model import MC_Model, MC_NeRF_Loss
+    sp = syn.make_sys_param(n_cam=4, img_h=16, img_w=16, batch=64, samples=64, scale=4, device=DEV, with_images=False)
+    m = MC_Model(sp).to(DEV)
+    batch = tuple(t.to(DEV) for t in syn.make_train_batch(sp, img_id=1, seed=3))
+    with pytest.raises(RuntimeError, match="cap"):
+        GraphedTrainStep(m, MC_NeRF_Loss(sp))(batch, 25, STAGE, 0.5)
