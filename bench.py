@@ -100,6 +100,7 @@ def build_workload(device, rank, precision, rays=RAYS, img=IMG):
     sp = syn.make_sys_param(n_cam=N_CAM, img_h=img, img_w=img, batch=rays, samples=SC, scale=SCALE, device=device,
                             with_images=False)
     sp["mlp_precision"] = precision
+    sp["pixel_sampler"] = "device"                    # the package default (synthetic.py pins "randperm" for replay tests)
     torch.manual_seed(42 + rank)                      # reference main.py:273-277
     model = MC_Model(sp).to(device)
     with torch.no_grad():

@@ -195,6 +195,24 @@ int mcnerf_gather_fine(const float* g_dense, const int32_t* sel_idx, int n_sel, 
  * g_c = 2(rgb_c-gt)/(3B)*grad_scale, g_f likewise.  gt_idx (may be NULL) gathers gt rows. */
 int mcnerf_rgb_loss(const float* rgb_c, const float* rgb_f, const float* gt, const int32_t* gt_idx, int n_rays,
                     float grad_scale, float* loss, float* g_c, float* g_f, void* stream);
+/* ref: model/loss.py:15-58 (MC_NeRF_Loss.forward of the stages that render).  ONE single-block launch:
+ *   l_px  = mean(((px_x-gt_x)/W)^2) + mean(((px_y-gt_y)/H)^2) over the n_pts reprojected calibration points
+ *           (px == NULL: no reprojection term), divided by (l_px.detach() + 1e-8) when normalise != 0;
+ *   l_rgb = mean((rgb_c-gt)^2) + mean((rgb_f-gt)^2) over n_rays*3 elements (rgb_f may be NULL);
+ *   out3  = {l_px[/norm] + l_rgb, l_px, l_rgb};  g_c, g_f [n_rays,3], g_px [n_pts,2] = d out3[0] / d input. */
+int mcnerf_train_loss(const float* rgb_c, const float* rgb_f, const float* gt, int n_rays, const float* px,
+                      const float* px_gt, int n_pts, int img_w, int img_h, int normalise, float* out3,
+                      float* g_c, float* g_f, float* g_px, void* stream);
+
+/* ref: model/mc_nerf.py:327-345 (generate_rand_rays: torch.randperm(H*W)[:batch]).  The first min(batch, n)
+ * entries of a uniform random permutation of [0, n) without sorting all n keys: Philox4x32-10 keyed by the two
+ * device-side int64 `seed` words, threshold filter, one-block sort of the few thousand survivors.
+ * workspace: mcnerf_sample_pixels_workspace() bytes, ZEROED once by the caller before the first call (the kernels
+ * leave it zeroed).  out_idx int64 [min(batch,n)]; out_idx32 (optional) the same values as int32. */
+int mcnerf_sample_pixels_workspace(int n, int batch, size_t* bytes);
+int mcnerf_sample_pixels(int n, int batch, const int64_t* seed, void* workspace, int64_t* out_idx,
+                         int32_t* out_idx32, void* stream);
+
 /* ref: model/net_utils.py:10-101 (RAdam.step) on one flat buffer.  The host evaluates the scalar schedule
  * (N_sma, step_size - incl. the 10-slot cache semantics) and passes it in:
  *   mode 1 (N_sma >= 5): p -= wd*lr*p ; p -= step_size*lr * m/(sqrt(v)+eps)

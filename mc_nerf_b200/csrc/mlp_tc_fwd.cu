@@ -144,42 +144,55 @@ struct PackArgs {
 };
 
 __global__ void __launch_bounds__(256) pack_all_k(const __grid_constant__ PackArgs a) {
+  // work unit: one 16-byte group of 8 consecutive k (matrix jobs) or one float (bias jobs)
   const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gi >= a.prefix[a.n_jobs]) return;
   int job = 0;
   while (gi >= a.prefix[job + 1]) ++job;
   const PackJob& pj = a.j[job];
-  const int64_t i = gi - a.prefix[job];
+  const int64_t t = gi - a.prefix[job];
   if (pj.is_bias) {
-    a.bias[pj.dst_off + i] = i < pj.n_valid ? pj.src[i] : 0.f;
+    a.bias[pj.dst_off + t] = t < pj.n_valid ? pj.src[t] : 0.f;
     return;
   }
   const int N = pj.N;
-  const int j = (int)(i & 7);
-  const int64_t t = i >> 3;
-  const int n = (int)(t % N);
-  const int k = (int)(t / N) * 8 + j;
-  int ks = k, ns = n;
-  bool ok = true;
-  if (pj.pad_k) { if (k == 63) ok = false; else if (k > 63) ks = k - 1; }
-  if (pj.pad_n) { if (n == 63) ok = false; else if (n > 63) ns = n - 1; }
-  if (ns >= pj.n_valid || ks >= pj.k_valid) ok = false;
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>((pj.dst_sel == 0 ? a.wf : a.wb) + pj.dst_off);
-  int64_t di = i;
+  const int n = (int)(t % N), kgi = (int)(t / N);
+  uint4* dst = reinterpret_cast<uint4*>((pj.dst_sel == 0 ? a.wf : a.wb) + pj.dst_off);
+  float v[8];
+  int64_t dg = t;                                                    // destination group index (16-byte units)
   if (pj.pair == 2) {
-    const int NH = N / 2, kgi = (int)(t / N);                      // K = 16: kgi in {0, 1}
-    di = (((int64_t)(n / NH) * 2 + kgi) * NH + n % NH) * 8 + j;
-    float b = n < pj.n_valid ? pj.src[n] : 0.f, v = 0.f;
+    const int NH = N / 2;                                            // K = 16: kgi in {0, 1}
+    dg = ((int64_t)(n / NH) * 2 + kgi) * NH + n % NH;
+    const float b = n < pj.n_valid ? pj.src[n] : 0.f;
     const float hi = __bfloat162float(__float2bfloat16(b));
-    if (k == 0) v = hi; else if (k == 1) v = b - hi;
-    dst[di] = __float2bfloat16(v);
-    return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (kgi == 0) { v[0] = hi; v[1] = b - hi; }
+  } else {
+    if (pj.pair) {
+      const int NH = N / 2, kgc = pj.K >= KC2 ? KC2 / 8 : pj.K / 8;   // k-groups per chunk
+      dg = (((int64_t)(kgi / kgc) * 2 + n / NH) * kgc + (kgi % kgc)) * NH + n % NH;
+    }
+    int ns = n;
+    bool n_ok = true;
+    if (pj.pad_n) { if (n == 63) n_ok = false; else if (n > 63) ns = n - 1; }
+    if (ns >= pj.n_valid) n_ok = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kgi * 8 + j;
+      int ks = k;
+      bool ok = n_ok;
+      if (pj.pad_k) { if (k == 63) ok = false; else if (k > 63) ks = k - 1; }
+      if (ks >= pj.k_valid) ok = false;
+      v[j] = ok ? pj.src[ns * pj.sn + ks * pj.sk] : 0.f;
+    }
   }
-  if (pj.pair) {
-    const int kgi = (int)(t / N), NH = N / 2, kgc = pj.K >= KC2 ? KC2 / 8 : pj.K / 8;   // k-groups per chunk
-    di = ((((int64_t)(kgi / kgc) * 2 + n / NH) * kgc + (kgi % kgc)) * NH + n % NH) * 8 + j;
-  }
-  dst[di] = __float2bfloat16(ok ? pj.src[ns * pj.sn + ks * pj.sk] : 0.f);
+  uint4 w;
+  w.x = tc::pack_bf16(v[0], v[1]);
+  w.y = tc::pack_bf16(v[2], v[3]);
+  w.z = tc::pack_bf16(v[4], v[5]);
+  w.w = tc::pack_bf16(v[6], v[7]);
+  dst[dg] = w;
 }
 
 // ----------------------------------------------------------------------------------------- forward kernel
@@ -655,7 +668,7 @@ extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb
     j.k_valid = k_valid; j.is_bias = is_bias; j.dst_off = dst_off; j.dst_sel = dst_sel; j.pair = 1;
     if (dst_sel == 3) { j.dst_sel = 0; j.pair = 2; }
     a.prefix[nj] = tot;
-    tot += (int64_t)N * K;
+    tot += is_bias ? (int64_t)N * K : (int64_t)N * K / 8;      // work units (see pack_all_k)
     ++nj;
   };
   for (int s = 0; s < L.fwd.n_steps; ++s) {

@@ -1,6 +1,7 @@
 """MC_NeRF_Loss with the reference's interface (ref: model/loss.py).  Tiny tensors ([B,3] renders and
-110x5 reprojected calibration points): plain torch ops on the device; the renderer's backward is seeded by
-the gradient of this loss."""
+110x5 reprojected calibration points).  The rendering stages on the GPU use one fused kernel (loss value + its
+gradients, libmcnerf `mcnerf_train_loss`); the camera-only stage and CPU tensors keep the plain torch expression."""
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -15,8 +16,15 @@ class MC_NeRF_Loss(nn.Module):
         self.img_w = sys_param["data_img_w"]
 
     def forward(self, loss_dict, epoch_type):
-        total = 0.0
         self.global_step += 1
+        if ("rgb" in loss_dict and "extr" not in loss_dict and epoch_type != "CAM_PARAM_EPOCH"
+                and loss_dict["rgb"][0].is_cuda and loss_dict["rgb"][0].dtype == torch.float32):
+            # rendering stages on the GPU: the whole expression below, forward and backward, is one kernel
+            from .. import ops
+            rgb_c, rgb_f, gt = loss_dict["rgb"]
+            px, px_gt = loss_dict["intr"] if "intr" in loss_dict else (None, None)
+            return ops.TrainLossFn.apply(rgb_c, rgb_f, gt, px, px_gt, self.img_w, self.img_h, True)
+        total = 0.0
         if "intr" in loss_dict:
             l_intr = self.get_reproject_loss(loss_dict["intr"])
             # stage 1 uses the raw value, later stages normalise it by its own magnitude (ref: model/loss.py:20-23)

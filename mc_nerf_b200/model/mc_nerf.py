@@ -102,6 +102,7 @@ class MC_Model(nn.Module):
             self.opt_idx = 0
         else:
             glob = epoch_type == "GLOBAL_OPTIM_EPOCH"    # ref: :73-83 (global) / :85-95 (fine tune)
+            self.nerf.prefetch_weights()                 # bf16 weight images pack while the camera kernels run
             self.nerf.emmbedding_xyz.barf_mode = glob
             self.intr_adj, self.pose_adj, self.calib_pose_adj = self.add_weights2param(True, glob, True)
             reproj = self.get_reproject_pixels(intr_wpts, self.intr_adj, self.calib_pose_adj)
@@ -157,12 +158,27 @@ class MC_Model(nn.Module):
         """randperm(H*W)[:batch] exactly as generate_rand_rays draws it (ref: :327-345), but only the selected
         rays are generated, straight from (camera, pixel)."""
         n = self.img_h * self.img_w
-        rand_idx = torch.randperm(n, device=self.device)[:self.batch]
+        rand_idx, rand_idx32 = self._choose_pixels(n)
         cam = self._cam_index(img_id, rand_idx.shape[0])
         rays_o, rays_d = ops.RaygenFn.apply(self.inverse_intrinsic(self.intr_adj), self.pose_adj, cam,
-                                            rand_idx.to(torch.int32), rand_idx.shape[0], self.img_w)
+                                            rand_idx32, rand_idx.shape[0], self.img_w)
         self.count_rays += 1
         return rays_d, rays_o, rand_idx
+
+    def _choose_pixels(self, n):
+        """-> (int64, int32) pixel indices = randperm(n)[:batch].  sys_param["pixel_sampler"]:
+        "device" (default): libmcnerf's threshold-and-sort sampler (same distribution, 2 launches instead of the
+        8-pass radix sort of all n keys; seeded from torch's CUDA generator, so torch.manual_seed governs it and it is
+        CUDA-graph safe);  "randperm": torch.randperm itself, draw for draw as the reference (replay tests)."""
+        if self.sys_param.get("pixel_sampler", "device") == "device" and torch.device(self.device).type == "cuda":
+            ws = self.__dict__.get("_pixel_ws")
+            if ws is None or ws[0] != (n, self.batch):
+                ws = self.__dict__["_pixel_ws"] = ((n, self.batch), ops.sample_pixels_workspace(n, self.batch, self.device))
+            if ws[1] is not None:
+                seed = torch.randint(-(1 << 62), 1 << 62, (2,), device=self.device, dtype=torch.int64)
+                return ops.sample_pixels(n, self.batch, seed, ws[1])
+        rand_idx = torch.randperm(n, device=self.device)[:self.batch]
+        return rand_idx, rand_idx.to(torch.int32)
 
     def generate_rand_rays(self, rays_d, rays_o, rand=True):
         """API-compatible subset selection on pre-generated rays.  ref: model/mc_nerf.py:327-345."""
@@ -386,6 +402,12 @@ class NeRF_Model(nn.Module):
             return self.render_rays_train(rays_d, rays_o, cur_epoch, step_r, only_coarse=False)
         rays_d, rays_o = args
         return self.render_rays_test(rays_d, rays_o, self.nerf_coarse, self.nerf_fine)
+
+    def prefetch_weights(self):
+        """start deriving the tensor-core weight images on a side stream (see render.prefetch_weights)"""
+        if torch.device(self.device).type == "cuda":
+            render.prefetch_weights(self.render_cfg, self.nerf_coarse.param_dict(), self.nerf_fine.param_dict(),
+                                    need_bwd=torch.is_grad_enabled())
 
     # ------------------------------------------------------------------ fused render paths
     def render_rays_train(self, rays_d, rays_o, cur_epoch, step_r, only_coarse=False, rng=None, cap_perm=None):

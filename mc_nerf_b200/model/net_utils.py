@@ -111,6 +111,9 @@ class RAdam(Optimizer):
                            (ctypes.c_int64 * n)(*[p.numel() for p, _ in items]),
                            float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
                            float(group["weight_decay"]), float(step_size), mode, 1.0, stream)
+                # the kernel wrote the parameters through raw pointers: bump their version counters as an in-place
+                # torch op would, so that derived caches (the packed bf16 weight images) and autograd notice
+                torch.autograd.graph.increment_version([p for p, _ in items])
         return loss
 
 

@@ -65,6 +65,60 @@ def barf_band_weights(step_r, barf_start, barf_end, n_freqs):
     w = (1 - (alpha - k).clamp_(min=0, max=1).mul_(torch.pi).cos_()) / 2
     return [float(x) for x in w]
 
+# --------------------------------------------------------------------------- loss + pixel choice
+
+
+class TrainLossFn(torch.autograd.Function):
+    """Total loss of a rendering stage in ONE launch: normalised reprojection term + coarse/fine MSE, with the
+    gradients produced by the same kernel.  ref: model/loss.py:15-58."""
+
+    @staticmethod
+    def forward(ctx, rgb_c, rgb_f, gt, px, px_gt, img_w, img_h, normalise):
+        rc, g = _f32(rgb_c), _f32(gt)
+        rf = _f32(rgb_f) if rgb_f is not None else None
+        pxc = _f32(px) if px is not None else None
+        pgt = _f32(px_gt).to(rc.device) if px is not None else None
+        n, n_pts = rc.shape[0], (pxc.numel() // 2 if pxc is not None else 0)
+        if rc.shape != g.shape or (rf is not None and rf.shape != g.shape) or rc.dim() != 2 or rc.shape[1] != 3:
+            raise _lib.McnerfError(f"TrainLossFn: renders {tuple(rc.shape)} / ground truth {tuple(g.shape)} mismatch")
+        out = torch.empty(3, device=rc.device)
+        grads = torch.empty(6 * n + 2 * n_pts, device=rc.device)        # g_c | g_f | g_px in one buffer
+        g_c, g_f, g_px = grads[:3 * n], grads[3 * n:6 * n], grads[6 * n:]
+        lib().call("mcnerf_train_loss", _p(rc), _p(rf), _p(g), n, _p(pxc), _p(pgt), n_pts, int(img_w), int(img_h),
+                   int(bool(normalise)), _p(out), _p(g_c), _p(g_f) if rf is not None else None,
+                   _p(g_px) if pxc is not None else None, _stream())
+        ctx.save_for_backward(grads)
+        ctx.meta = (n, rgb_f is not None, tuple(px.shape) if px is not None else None)
+        ctx.parts = out                       # (total, raw reprojection loss, rgb loss) for logging
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, go):
+        (grads,) = ctx.saved_tensors
+        n, has_f, px_shape = ctx.meta
+        g = grads * go                        # one launch for all three gradients
+        return (g[:3 * n].view(n, 3), g[3 * n:6 * n].view(n, 3) if has_f else None, None,
+                g[6 * n:].view(px_shape) if px_shape is not None else None, None, None, None, None)
+
+
+def sample_pixels_workspace(n, batch, device):
+    """zeroed workspace for sample_pixels, or None when the batch is too large for the one-block sort."""
+    sz = ctypes.c_size_t()
+    if lib().cdll.mcnerf_sample_pixels_workspace(int(n), int(batch), ctypes.byref(sz)) != 0:
+        return None
+    return torch.zeros(sz.value, dtype=torch.uint8, device=device)
+
+
+def sample_pixels(n, batch, seed, workspace):
+    """first min(batch, n) entries of a random permutation of [0, n): (int64 [m], int32 [m]).
+    ref: model/mc_nerf.py:327-345."""
+    m = min(int(n), int(batch))
+    idx64 = torch.empty(m, dtype=torch.int64, device=seed.device)
+    idx32 = torch.empty(m, dtype=torch.int32, device=seed.device)
+    lib().call("mcnerf_sample_pixels", int(n), int(batch), _p(seed, torch.int64), _p(workspace, torch.uint8),
+               _p(idx64, torch.int64), _p(idx32, torch.int32), _stream())
+    return idx64, idx32
+
 # --------------------------------------------------------------------------- camera
 
 
@@ -399,10 +453,32 @@ class TcWeights:
     def __init__(self):
         self.key = None
         self.wf = self.wb = self.bias = None
+        self.ready = None            # event of a pack issued ahead of time on a side stream (prefetch)
+
+    def prefetch(self, ps, tensors, need_bwd, side):
+        """Issue the pack on `side` (forked from the current stream) so that it overlaps the step's camera / pixel /
+        RNG launches; the next get() on the main stream waits for it instead of packing."""
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)        # everything issued so far (last backward reads wb, RAdam writes the weights)
+        with torch.cuda.stream(side):
+            self.get(ps, tensors, need_bwd)
+            self.ready = (side.record_event(), tuple((t.data_ptr(), t._version) for t in tensors.values()))
 
     def get(self, ps, tensors, need_bwd=True):
         key = tuple((t.data_ptr(), t._version) for t in tensors.values())
-        if key != self.key or (need_bwd and self.wb is None):
+        if self.ready is not None:
+            event, packed_key = self.ready
+            self.ready = None
+            torch.cuda.current_stream().wait_event(event)
+            if packed_key == key and (not need_bwd or self.wb is not None):
+                return self
+        # Under CUDA-graph capture the host-side version check would be frozen into the graph (a replay after
+        # optimizer.step() would read stale images): always record the pack launch, and forget the key so that the
+        # next eager call re-packs too.
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing:
+            key = None
+        if capturing or key != self.key or (need_bwd and self.wb is None):
             dev = next(iter(tensors.values())).device
             sz = [ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()]
             lib().call("mcnerf_mlp_tc_pack_sizes", ctypes.byref(ps), *[ctypes.byref(x) for x in sz])

@@ -61,6 +61,30 @@ def _tc_weights(ps, tensors, need_bwd):
     return tcw.get(ps, tensors, need_bwd)
 
 
+_SIDE = {}         # device index -> side stream for the weight packs
+
+
+def prefetch_weights(cfg, params_c, params_f, need_bwd=True):
+    """Start packing both networks' bf16 images on a side stream (no-op for networks on the fp32 path).  Call at the
+    top of a train step; render() picks the images up where it would otherwise pack them."""
+    for net, params in ((cfg.coarse, params_c), (cfg.fine, params_f)):
+        if not use_tc(cfg, net):
+            continue
+        tensors = {k: ops._f32(params[k]) for k in ops.param_names(net[0])}
+        first = next(iter(tensors.values()))
+        if not first.is_cuda:
+            continue
+        side = _SIDE.get(first.device.index)
+        if side is None:
+            side = _SIDE[first.device.index] = torch.cuda.Stream(device=first.device)
+        ps = ops.make_mlp_params(tensors, net[0], net[1], net[2], in_ch=cfg.in_ch)
+        key = first.data_ptr()
+        tcw = _TC_CACHE.get(key)
+        if tcw is None:
+            tcw = _TC_CACHE[key] = ops.TcWeights()
+        tcw.prefetch(ps, tensors, need_bwd, side)
+
+
 def use_tc(cfg, net):
     """bf16 tcgen05 path when asked for and the network shape is one the tensor-core kernels implement."""
     depth, width, skips = net

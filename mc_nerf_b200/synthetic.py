@@ -107,7 +107,7 @@ def se3_log(Rt):
 def make_sys_param(n_cam=N_CAM_BALL, img_h=100, img_w=100, batch=1024, samples=64, scale=2,
                    coarse=(8, 256, (4,)), fine=(8, 256, (4,)), emb_freqs=10, deg=2, device="cpu",
                    mode=0, near=1.0, far=8.0, seed=4, with_images=True, barf_start=20 / 52, barf_end=36 / 52,
-                   weight_thresh=1e-3):
+                   weight_thresh=1e-3, pixel_sampler="randperm"):
     """The flat `sys_param` dict every reference constructor reads (SURVEY.md §5 'Config')."""
     w2c, fov = ball_rig(n_cam, seed=seed)
     K = fov_to_intrinsics(fov, img_h, img_w)
@@ -118,7 +118,7 @@ def make_sys_param(n_cam=N_CAM_BALL, img_h=100, img_w=100, batch=1024, samples=6
     else:
         valid_rgbs = torch.zeros(n_cam, 1, 3)
     return dict(
-        mode=mode, device_type=device, distributed=False, batch=batch,
+        mode=mode, device_type=device, distributed=False, batch=batch, pixel_sampler=pixel_sampler,
         data_img_h=img_h, data_img_w=img_w, res_h=img_h, res_w=img_w,
         data_numb=[n_cam, n_cam, n_cam],
         intr_mat=[K, K.clone(), K.clone()], intr_mat_inv=[Kinv, Kinv.clone(), Kinv.clone()],

@@ -332,3 +332,38 @@ def cfg_from_sys_param(sp):
                 barf_start=sp["barf_start"], barf_end=sp["barf_end"], img_h=sp["data_img_h"], img_w=sp["data_img_w"],
                 coarse=(sp["coarse_MLP_depth"], sp["coarse_MLP_width"], tuple(sp["coarse_MLP_skip"])),
                 fine=(sp["fine_MLP_depth"], sp["fine_MLP_width"], tuple(sp["fine_MLP_skip"])))
+
+
+# --------------------------------------------------------------------------- pixel choice (checker of the device sampler)
+
+
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., SC'11) on numpy uint64 lanes holding 32-bit words."""
+    import numpy as np
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85, np.uint64(0xFFFFFFFF)
+    k0, k1 = int(k0), int(k1)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def sample_pixels(n, batch, seed0, seed1):
+    """randperm(n)[:batch] (model/mc_nerf.py:327-345) as the device sampler DEFINES its permutation: pixel i gets the
+    composite key (64 - ceil(log2 n) random Philox bits | i) and the permutation is the argsort of ALL n composites.
+    The kernel (mcnerf_sample_pixels) must return exactly the head of this full sort without performing it."""
+    import numpy as np
+    bits = 1
+    while (1 << bits) < n:
+        bits += 1
+    s0, s1 = int(seed0) & 0xFFFFFFFFFFFFFFFF, int(seed1) & 0xFFFFFFFFFFFFFFFF
+    i = np.arange(n, dtype=np.uint64)
+    z = np.zeros(n, dtype=np.uint64)
+    r0, r1, _, _ = _philox4x32_10(i, z, z + np.uint64(s1 & 0xFFFFFFFF), z + np.uint64(s1 >> 32),
+                                  s0 & 0xFFFFFFFF, s0 >> 32)
+    r = ((r0 << np.uint64(32)) | r1) >> np.uint64(bits)
+    comp = (r << np.uint64(bits)) | i
+    order = np.sort(comp)[:min(n, batch)]
+    return (order & np.uint64((1 << bits) - 1)).astype(np.int64)

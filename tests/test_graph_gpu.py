@@ -79,6 +79,45 @@ def test_graph_replay_matches_eager_step():
         assert abs(step(batch, 25, STAGE, 0.5).item() - loss_e.item()) <= 1e-6 * abs(loss_e.item())
 
 
+def test_graph_replay_follows_weight_updates():
+    """The packed bf16 weight images are derived INSIDE the graph: a replay after the fp32 parameters changed (what
+    optimizer.step() does) must render with the new weights, exactly as an eager step does."""
+    from mc_nerf_b200.graph import GraphedTrainStep
+    from mc_nerf_b200.model import RAdam
+    sp, m, loss_fn = build()
+    _, m_e, loss_fn_e = build()
+    rng = syn.draw_step_rng(sp, 256, seed=5)
+    batch = tuple(t.to(DEV) for t in syn.make_train_batch(sp, img_id=2, seed=3))
+
+    def perturb(model):
+        with torch.no_grad():
+            for name, p in model.nerf.named_parameters():      # a change the renders cannot miss
+                p.mul_(1.5)
+                if name.endswith("bias"):
+                    p.add_(0.25)
+
+    with FixedRNG(rng):
+        step = GraphedTrainStep(m, loss_fn)
+        before = step(batch, 25, STAGE, 0.5).item()
+        perturb(m)
+        after = step(batch, 25, STAGE, 0.5).item()
+        opt = RAdam(list(m.nerf.parameters()), lr=5e-3)      # MLP weights only: the normalised
+            # reprojection term makes the camera parameters' first step large and sensitive to summation order
+        opt.step()                                  # consumes the replay's gradients, moves every parameter
+        after_opt = step(batch, 25, STAGE, 0.5).item()
+        perturb(m_e)
+        loss = loss_fn_e(m_e(batch, 25, STAGE, 0.5)[0], STAGE)
+        loss.backward()
+        opt_e = RAdam(list(m_e.nerf.parameters()), lr=5e-3)
+        opt_e.step()
+        after_opt_e = loss_fn_e(m_e(batch, 25, STAGE, 0.5)[0], STAGE).item()
+    assert abs(after - before) > 1e-3 * abs(before), (before, after)        # the replay saw the new weights
+    assert abs(after - loss.item()) <= 1e-5 * abs(after)
+    assert abs(after_opt_e - loss.item()) > 1e-5 * abs(after_opt_e)         # the eager render re-packed its weights too
+    assert abs(after_opt - after_opt_e) <= 1e-4 * abs(after_opt_e), (after, after_opt, after_opt_e)
+    assert abs(after_opt - after) > 10 * abs(after_opt - after_opt_e)        # the optimiser's step is what moved it
+
+
 def test_graph_replay_draws_fresh_random_numbers():
     from mc_nerf_b200.graph import GraphedTrainStep
     sp, m, loss_fn = build(1)

@@ -177,7 +177,9 @@ def test_radam_matches_reference_trajectory():
     for step, grads in enumerate(fx["grads"]):
         for t, g in zip(p, grads):
             t.grad = g.to(DEV)
+        versions = [t._version for t in p]
         opt.step()
+        assert all(t._version > v for t, v in zip(p, versions))     # raw-pointer update is visible to version checks
         if step in fx["traj"]:
             for t, ref in zip(p, fx["traj"][step]):
                 close(t, ref, rtol=2e-5, atol=1e-7)

@@ -153,3 +153,18 @@ def test_cfg1_train_step():
         net, pname = k.split(".", 2)[1:]
         p = (pc if net == "nerf_coarse" else pf)[pname]
         assert abs(float(p.grad.norm()) - n) <= 2e-3 * max(n, 1e-6), k
+
+
+def test_philox_known_answers_and_sampler_oracle_properties():
+    """The pixel-sampler checker: Philox4x32-10 against the Random123 known-answer vectors, and the oracle's
+    permutation head is a set of distinct in-range indices that changes with the seed."""
+    import numpy as np
+    z = np.zeros(1, dtype=np.uint64)
+    f = np.full(1, 0xFFFFFFFF, dtype=np.uint64)
+    assert [int(x[0]) for x in orc._philox4x32_10(z, z, z, z, 0, 0)] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert [int(x[0]) for x in orc._philox4x32_10(f, f, f, f, 0xFFFFFFFF, 0xFFFFFFFF)] == \
+        [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    a, b = orc.sample_pixels(10000, 512, 1, 2), orc.sample_pixels(10000, 512, 1, 3)
+    assert a.shape == (512,) and len(np.unique(a)) == 512 and a.min() >= 0 and a.max() < 10000
+    assert not np.array_equal(a, b)
+    assert sorted(orc.sample_pixels(37, 100, 5, 6).tolist()) == list(range(37))
