@@ -33,6 +33,10 @@ METRIC = "train_rays_per_sec_64c_128f"
 UNIT = "rays/s"
 N_CAM, IMG, RAYS, SC, SCALE = 110, 800, 4096, 64, 2
 MACS_PER_EVAL = 629248          # GEMM MACs per MLP evaluation (8x256, skip[4], sigma + SH-27 heads)
+# Bytes the weight-gradient kernel must read per MLP evaluation: every (dY, X) operand pair once, bf16, per 128-row
+# tile: layer 0: 64+16 KB; six plain trunk layers: 128 KB each; skip layer: (64+16) + 128; sigma.0, sh.0: 128 each;
+# sh.2, sigma.2: 64 + 8 (head-gradient tile) each  ->  1456 KB / 128 rows
+WGRAD_BYTES_PER_EVAL = 1456 * 1024 // 128
 STAGE, RATIO = "GLOBAL_OPTIM_EPOCH", 0.5
 
 
@@ -223,7 +227,27 @@ def run_ours(args):
             traffic_src = "GB per step = ncu dram bytes/evaluation (fwd+bwd-chain+wgrad, profiles/r01_ncu_summary.json) x evaluations"
         except Exception:
             pass
-        roof = dict(bound="tensor", achieved=round(ach, 2), peak=peaks["tensor"], unit="TFLOP/s",
+        per_kernel = []
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))["kernels"]
+        except Exception:
+            ncu = {}
+        for label, ncu_name, bound in (("mcnerf_mlp_tc_fwd", "mlp_tc_fwd_k<1>", "tensor"),
+                                       ("mcnerf_mlp_tc_bwd[chain]", "mlp_tc_bwd_k", "tensor"),
+                                       ("mcnerf_mlp_tc_bwd[wgrad]", "mlp_tc_wgrad_k", "hbm")):
+            if label not in prof:
+                continue
+            k_ms = prof[label] / 3
+            if bound == "tensor":
+                a_k, pk, unit = 2.0 * MACS_PER_EVAL * evals / (k_ms / 1e3) / 1e12, peaks["tensor"], "TFLOP/s"
+            else:
+                a_k, pk, unit = WGRAD_BYTES_PER_EVAL * evals / (k_ms / 1e3) / 1e9, peaks["hbm"], "GB/s"
+            tr = ncu.get(ncu_name, {}).get("dram_bytes_per_eval")
+            per_kernel.append(dict(kernel=ncu_name, entry=label, bound=bound, achieved=round(a_k, 1), peak=pk, unit=unit,
+                                   frac=round(a_k / pk, 4), ms_per_step=round(k_ms, 3), launches_per_step=2,
+                                   traffic=round(tr * evals / 1e9, 3) if tr else None, traffic_unit="GB per step",
+                                   share_of_step=round(k_ms / (ms / args.steps), 3)))
+        roof = dict(bound="tensor", achieved=round(ach, 2), peak=peaks["tensor"], unit="TFLOP/s", kernels=per_kernel,
                     frac=round(ach / peaks["tensor"], 4), traffic=traffic, traffic_unit="GB", traffic_source=traffic_src,
                     peak_source=peaks["src"],
                     kernel="mcnerf_mlp_* (fwd+bwd, coarse+fine)", kernel_ms_per_step=round(mlp_ms, 3),

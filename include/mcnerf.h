@@ -266,6 +266,10 @@ int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, const float* b
                       const float* out4, const float* g_out4, const void* stash, void* workspace,
                       const mcnerf_mlp_grads* g, float* g_rays_o, float* g_rays_d, float* g_x_enc,
                       float* g_dirs_rows, void* stream);
+/* Measurement aid (bench.py's per-kernel CUDA-event timing): select which phases the next mcnerf_mlp_tc_bwd calls
+ * launch - bit 0: data-gradient chain (+ ray gradients), bit 1: weight/bias gradients.  Default 3 (both); the two
+ * phases of one backward may be issued as two calls (1 then 2) with identical arguments.  Process-global. */
+int mcnerf_mlp_tc_bwd_phases(int mask);
 
 /* ------------------------------------------------------------------ tensor-core self test
  * One 128xN tcgen05 tile: D = A B^T (mn_major = 0: A [128,K], B [N,K] bf16, K-major operands) or

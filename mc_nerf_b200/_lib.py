@@ -119,7 +119,10 @@ class _Lib:
         self._prof = None
         return out
 
-    def call(self, name, *args):
+    def profiling(self):
+        return getattr(self, "_prof", None) is not None
+
+    def call(self, name, *args, label=None):
         """Call an int-returning entry; raise McnerfError(mcnerf_last_error()) on failure."""
         if getattr(self, "_prof", None) is not None:
             import torch
@@ -127,7 +130,7 @@ class _Lib:
             e0.record()
             rc = getattr(self.cdll, name)(*args)
             e1.record()
-            self._prof.append((name, e0, e1))
+            self._prof.append((label or name, e0, e1))
         else:
             rc = getattr(self.cdll, name)(*args)
         if rc != 0:

@@ -438,6 +438,14 @@ extern "C" size_t mcnerf_mlp_tc_bwd_workspace(const mcnerf_mlp_params* p, int n_
   return stash_tiles(n_rows) * ((size_t)(p->depth + 2) * ACT_BYTES + HEAD_BYTES) + mlp_tc_wgrad_scratch_bytes(WG_MAX_CTAS);
 }
 
+// Measurement aid: which phases mcnerf_mlp_tc_bwd launches (bit 0: data-gradient chain, bit 1: weight gradients).
+static int g_bwd_phases = 3;
+extern "C" int mcnerf_mlp_tc_bwd_phases(int mask) {
+  MC_ARG(mask >= 1 && mask <= 3);
+  g_bwd_phases = mask;
+  return 0;
+}
+
 extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, const float* bias,
                                  const mcnerf_tc_input* in, const float* out4, const float* g_out4, const void* stash,
                                  void* workspace, const mcnerf_mlp_grads* g, float* g_rays_o, float* g_rays_d,
@@ -480,7 +488,7 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  {
+  if (g_bwd_phases & 1) {
     int grid = n_pairs < sms ? n_pairs : sms;
     grid = (grid + 1) & ~1;                                  // whole clusters of 2
     if (grid > sms) grid = sms & ~1;
@@ -495,8 +503,9 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_bwd_k, a));
+    MC_LAUNCHED();
   }
-  MC_LAUNCHED();
+  if (!(g_bwd_phases & 2)) return 0;
   // weight gradients (tcgen05, reduction over all rows) and bias gradients (column sums of the dY stash)
   MC_ARG(sms <= WG_MAX_CTAS);
   float* scratch = (float*)(a.dy_head + tiles * HEAD_BYTES);

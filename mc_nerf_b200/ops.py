@@ -535,6 +535,16 @@ def tc_bwd_workspace(ps, n_rows, device):
 
 def mlp_tc_bwd(ps, tcw, tcin, out4, g_out4, stash, workspace, grads_struct, g_rays_o=None, g_rays_d=None,
                g_x_enc=None, g_dirs_rows=None):
-    lib().call("mcnerf_mlp_tc_bwd", ctypes.byref(ps), _p(tcw.wb, torch.uint8), _p(tcw.bias), ctypes.byref(tcin),
-               _p(out4), _p(g_out4), _p(stash, torch.uint8), _p(workspace, torch.uint8), ctypes.byref(grads_struct),
-               _p(g_rays_o), _p(g_rays_d), _p(g_x_enc), _p(g_dirs_rows), _stream())
+    args = (ctypes.byref(ps), _p(tcw.wb, torch.uint8), _p(tcw.bias), ctypes.byref(tcin),
+            _p(out4), _p(g_out4), _p(stash, torch.uint8), _p(workspace, torch.uint8), ctypes.byref(grads_struct),
+            _p(g_rays_o), _p(g_rays_d), _p(g_x_enc), _p(g_dirs_rows), _stream())
+    if lib().profiling():        # per-kernel timing: the chain and the weight-gradient kernels as two calls
+        try:
+            lib().cdll.mcnerf_mlp_tc_bwd_phases(1)
+            lib().call("mcnerf_mlp_tc_bwd", *args, label="mcnerf_mlp_tc_bwd[chain]")
+            lib().cdll.mcnerf_mlp_tc_bwd_phases(2)
+            lib().call("mcnerf_mlp_tc_bwd", *args, label="mcnerf_mlp_tc_bwd[wgrad]")
+        finally:
+            lib().cdll.mcnerf_mlp_tc_bwd_phases(3)
+        return
+    lib().call("mcnerf_mlp_tc_bwd", *args)
