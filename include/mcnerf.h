@@ -213,6 +213,13 @@ int mcnerf_sample_pixels_workspace(int n, int batch, size_t* bytes);
 int mcnerf_sample_pixels(int n, int batch, const int64_t* seed, void* workspace, int64_t* out_idx,
                          int32_t* out_idx32, void* stream);
 
+/* dst_j[r*dst_ld_j + c] = src_j[r*src_ld_j + c] for r < rows_j, c < cols_j, j < n_jobs, in one launch per 64 jobs.
+ * Used to zero-pad the parameters of a network narrower than 256 into 256-wide shadows for the tensor-core path
+ * (zero rows/columns leave the arithmetic of ref: model/net_block.py:67-78 unchanged) and to cut the valid blocks
+ * back out of the 256-wide gradients.  All seven arrays are HOST arrays of length n_jobs. */
+int mcnerf_copy_blocks(int n_jobs, const float* const* src, float* const* dst, const int* rows, const int* cols,
+                       const int* src_ld, const int* dst_ld, void* stream);
+
 /* ref: model/net_utils.py:10-101 (RAdam.step) on one flat buffer.  The host evaluates the scalar schedule
  * (N_sma, step_size - incl. the 10-slot cache semantics) and passes it in:
  *   mode 1 (N_sma >= 5): p -= wd*lr*p ; p -= step_size*lr * m/(sqrt(v)+eps)

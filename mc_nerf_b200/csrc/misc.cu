@@ -269,6 +269,30 @@ pixel_pick_k(int n, int n_out, const int64_t* __restrict__ seed, int idx_bits, u
   if (tid == 0) *count = 0;       // ready for the next call (and the next graph replay)
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// dst[r*dst_ld + c] = src[r*src_ld + c] for the top-left rows x cols block of up to 64 matrices in one launch:
+// zero-pads a narrow network's parameters into 256-wide shadows (tensor-core path for widths < 256) and cuts the
+// valid blocks back out of the 256-wide gradients.
+constexpr int COPY_MAX_JOBS = 64;
+struct CopyBlocks {
+  int n;
+  const float* src[COPY_MAX_JOBS];
+  float* dst[COPY_MAX_JOBS];
+  int rows[COPY_MAX_JOBS], cols[COPY_MAX_JOBS], src_ld[COPY_MAX_JOBS], dst_ld[COPY_MAX_JOBS];
+  int blk_prefix[COPY_MAX_JOBS + 1];
+};
+
+__global__ void copy_blocks_k(const __grid_constant__ CopyBlocks a) {
+  int job = 0;
+  while ((int)blockIdx.x >= a.blk_prefix[job + 1]) ++job;
+  const int i = ((int)blockIdx.x - a.blk_prefix[job]) * blockDim.x + threadIdx.x;
+  const int cols = a.cols[job];
+  if (i >= a.rows[job] * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  a.dst[job][(size_t)r * a.dst_ld[job] + c] = a.src[job][(size_t)r * a.src_ld[job] + c];
+}
+
 }  // namespace
 
 extern "C" int mcnerf_rgb_loss(const float* rgb_c, const float* rgb_f, const float* gt, const int32_t* gt_idx,
@@ -385,5 +409,29 @@ extern "C" int mcnerf_sample_pixels(int n, int batch, const int64_t* seed, void*
   pixel_pick_k<<<1, 1024, 0, (cudaStream_t)stream>>>(n, n_out, seed, bits, tau, shift, cap, cand, cand + cap, count,
                                                      out_idx, out_idx32);
   MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcnerf_copy_blocks(int n_jobs, const float* const* src, float* const* dst, const int* rows,
+                                  const int* cols, const int* src_ld, const int* dst_ld, void* stream) {
+  MC_ARG(n_jobs >= 0);
+  if (n_jobs == 0) return 0;
+  MC_ARG(src && dst && rows && cols && src_ld && dst_ld);
+  for (int base = 0; base < n_jobs; base += COPY_MAX_JOBS) {
+    CopyBlocks a;
+    a.n = n_jobs - base < COPY_MAX_JOBS ? n_jobs - base : COPY_MAX_JOBS;
+    int blocks = 0;
+    for (int t = 0; t < a.n; ++t) {
+      const int j = base + t;
+      MC_ARG(src[j] && dst[j] && rows[j] > 0 && cols[j] > 0 && src_ld[j] >= cols[j] && dst_ld[j] >= cols[j]);
+      a.src[t] = src[j]; a.dst[t] = dst[j]; a.rows[t] = rows[j]; a.cols[t] = cols[j];
+      a.src_ld[t] = src_ld[j]; a.dst_ld[t] = dst_ld[j];
+      a.blk_prefix[t] = blocks;
+      blocks += cdiv((int64_t)rows[j] * cols[j], 256);
+    }
+    for (int t = a.n; t <= COPY_MAX_JOBS; ++t) a.blk_prefix[t] = blocks;
+    copy_blocks_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    MC_LAUNCHED();
+  }
   return 0;
 }

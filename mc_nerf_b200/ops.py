@@ -442,6 +442,69 @@ class ScatterFineFn(torch.autograd.Function):
 # --------------------------------------------------------------------------- bf16 tcgen05 MLP path
 
 
+TC_WIDTH = 256        # hidden width the tcgen05 kernels are built for
+
+
+class PaddedNet:
+    """256-wide zero-padded fp32 shadow of a network narrower than 256 (e.g. the reference's default 4x128 coarse net).
+    Zero rows/columns change nothing in the arithmetic (a padded unit has pre-activation 0, output 0, gradient 0), so
+    the tensor-core kernels run the shadow and the valid blocks of its gradients are the network's gradients.
+    One launch copies every parameter into its shadow, one launch cuts every gradient back out."""
+
+    def __init__(self, tensors, depth, width, in_ch):
+        self.names = param_names(depth)
+        dev = next(iter(tensors.values())).device
+        wide_shapes = {}
+        for name in self.names:
+            shape = list(tensors[name].shape)
+            head_out = name in ("sigma.2.weight", "sigma.2.bias", "sh.2.weight", "sh.2.bias")
+            if not head_out:
+                shape[0] = TC_WIDTH                                  # output features (weights and biases)
+            if len(shape) == 2 and name != TRUNK.format(1, "weight"):   # input features: hidden, or encoding + hidden
+                shape[1] = TC_WIDTH + (shape[1] - width)
+            wide_shapes[name] = tuple(shape)
+        total = sum(int(torch.Size(sh).numel()) for sh in wide_shapes.values())
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.wide, off = {}, 0
+        for name in self.names:
+            n = int(torch.Size(wide_shapes[name]).numel())
+            self.wide[name] = self.flat[off:off + n].view(wide_shapes[name])
+            off += n
+        self.narrow_shapes = {name: tuple(tensors[name].shape) for name in self.names}
+        self.key = None
+
+    def _copy(self, src, dst, shapes):
+        n = len(self.names)
+        vp, ip = ctypes.c_void_p * n, ctypes.c_int * n
+        rows = [shapes[k][0] if len(shapes[k]) == 2 else 1 for k in self.names]
+        cols = [shapes[k][-1] for k in self.names]
+        lib().call("mcnerf_copy_blocks", n, vp(*[src[k].data_ptr() for k in self.names]),
+                   vp(*[dst[k].data_ptr() for k in self.names]), ip(*rows), ip(*cols),
+                   ip(*[src[k].shape[-1] for k in self.names]), ip(*[dst[k].shape[-1] for k in self.names]), _stream())
+
+    def refresh(self, tensors):
+        """bring the shadow up to date with the parameters (after optimizer.step(); always under graph capture)"""
+        key = tuple((t.data_ptr(), t._version) for t in tensors.values())
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing or key != self.key:
+            self._copy(tensors, self.wide, self.narrow_shapes)
+            torch.autograd.graph.increment_version(list(self.wide.values()))     # the packed images are now stale
+            self.key = None if capturing else key
+        return self.wide
+
+    def unpad(self, wide_grads):
+        """valid blocks of the 256-wide gradients as views of one contiguous buffer in parameter order"""
+        total = sum(int(torch.Size(sh).numel()) for sh in self.narrow_shapes.values())
+        flat = torch.empty(total, dtype=torch.float32, device=self.flat.device)
+        out, off = {}, 0
+        for name in self.names:
+            n = int(torch.Size(self.narrow_shapes[name]).numel())
+            out[name] = flat[off:off + n].view(self.narrow_shapes[name])
+            off += n
+        self._copy(wide_grads, out, self.narrow_shapes)
+        return out
+
+
 def tc_supported(ps):
     return bool(lib().cdll.mcnerf_mlp_tc_supported(ctypes.byref(ps)))
 

@@ -10,6 +10,7 @@ ref: model/mc_nerf.py:598-736.  Random draws (jitter, three noise tensors) are e
 caller decides where they come from (torch's generator in the reference's draw order, or fixtures in tests).
 """
 import ctypes
+import os
 
 import torch
 
@@ -68,7 +69,7 @@ def prefetch_weights(cfg, params_c, params_f, need_bwd=True):
     """Start packing both networks' bf16 images on a side stream (no-op for networks on the fp32 path).  Call at the
     top of a train step; render() picks the images up where it would otherwise pack them."""
     for net, params in ((cfg.coarse, params_c), (cfg.fine, params_f)):
-        if not use_tc(cfg, net):
+        if not use_tc(cfg, net) or net[1] != ops.TC_WIDTH:      # padded shadows are refreshed and packed in line
             continue
         tensors = {k: ops._f32(params[k]) for k in ops.param_names(net[0])}
         first = next(iter(tensors.values()))
@@ -86,10 +87,30 @@ def prefetch_weights(cfg, params_c, params_f, need_bwd=True):
 
 
 def use_tc(cfg, net):
-    """bf16 tcgen05 path when asked for and the network shape is one the tensor-core kernels implement."""
+    """bf16 tcgen05 path when asked for and the network shape is one the tensor-core kernels implement: width 256
+    natively, narrower networks through a zero-padded 256-wide shadow (ops.PaddedNet)."""
     depth, width, skips = net
-    return (cfg.precision == "bf16" and width == 256 and cfg.n_freqs == 10 and 2 <= depth <= 12
+    if width != ops.TC_WIDTH and os.environ.get("MCNERF_TC_PAD", "1") == "0":      # A/B switch for measurements
+        return False
+    return (cfg.precision == "bf16" and 8 <= width <= ops.TC_WIDTH and cfg.n_freqs == 10 and 2 <= depth <= 12
             and len([s for s in skips if 0 < s < depth]) <= 1)
+
+
+_PAD_CACHE = {}    # (data_ptr of the first weight) -> ops.PaddedNet
+
+
+def _tc_view(cfg, net, tensors):
+    """-> (net the kernels see, tensors the kernels see, PaddedNet or None)"""
+    depth, width, skips = net
+    if not use_tc(cfg, net) or width == ops.TC_WIDTH:
+        return net, tensors, None
+    key = next(iter(tensors.values())).data_ptr()
+    pad = _PAD_CACHE.get(key)
+    if pad is None or pad.narrow_shapes != {k: tuple(v.shape) for k, v in tensors.items()}:
+        if len(_PAD_CACHE) > 16:
+            _PAD_CACHE.clear()
+        pad = _PAD_CACHE[key] = ops.PaddedNet(tensors, depth, width, cfg.in_ch)
+    return (depth, ops.TC_WIDTH, skips), pad.refresh(tensors), pad
 
 
 def _branch_fwd(cfg, net, tensors, rays_o, rays_d, jitter, S, band_w, sel_idx, n_rows, n_rows_dev, train=True):
@@ -164,7 +185,9 @@ def select_and_cap(cfg, out_c, noise_sel, jitter, B, train, cap_perm=None):
     if train and cfg.Sf > 128:
         n = int(n_sel.item())                      # the reference synchronises here too
         if n > B * 128:
-            perm = cap_perm if cap_perm is not None else torch.randperm(n)     # CPU generator, as the reference
+            # the reference draws this permutation with the CPU generator (~40 ms for the default config's 3.4 M
+            # selected samples); the same uniform B*128-subset is drawn on the device here
+            perm = cap_perm if cap_perm is not None else torch.randperm(n, device=dev)
             keep = perm[:B * 128].to(dev)
             sel_idx = sel_idx[:n][keep].contiguous()
             n_rows, n_rows_dev = B * 128, None
@@ -185,9 +208,11 @@ class RenderFn(torch.autograd.Function):
         tf = {k: ops._f32(v) for k, v in zip(ops.param_names(cfg.fine[0]), params[nc:])}
         jitter = ops._f32(rng["jitter"]).reshape(-1) if (train and rng.get("jitter") is not None) else None
         noise_c, noise_sel, noise_f = (ops._f32(rng[k]) for k in ("noise_c", "noise_sel", "noise_f"))
+        net_c, run_c, pad_c = _tc_view(cfg, cfg.coarse, tc)       # what the kernels see (narrow nets: 256-wide shadow)
+        net_f, run_f, pad_f = _tc_view(cfg, cfg.fine, tf)
         # coarse
         need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
-        out_c, saved_c = _branch_fwd(cfg, cfg.coarse, tc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
+        out_c, saved_c = _branch_fwd(cfg, net_c, run_c, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
                                      need_grad)
         cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
         rgb_c = torch.empty(B, 3, device=dev)
@@ -198,7 +223,7 @@ class RenderFn(torch.autograd.Function):
         LAST["n_rows"], LAST["n_rows_dev"] = n_rows, n_rows_dev
         # fine
         if n_rows > 0:
-            out_sel, saved_f = _branch_fwd(cfg, cfg.fine, tf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx,
+            out_sel, saved_f = _branch_fwd(cfg, net_f, run_f, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx,
                                            n_rows, n_rows_dev, need_grad)
         else:
             out_sel, saved_f = torch.empty(0, 4, device=dev), None
@@ -212,7 +237,8 @@ class RenderFn(torch.autograd.Function):
         lib().call("mcnerf_composite_fwd", _p(dense), _p(noise_f), _p(rays_d), _p(jitter), None, B,
                    ctypes.byref(cf), _p(rgb_f), _p(depth_f), _p(opa_f), None, _stream())
         ctx.cfg, ctx.band_w, ctx.n_rows = cfg, band_w, n_rows
-        ctx.tc, ctx.tf = tc, tf
+        ctx.tc, ctx.tf = run_c, run_f
+        ctx.nets, ctx.pads = (net_c, net_f), (pad_c, pad_f)
         ctx.saved = (rays_d, rays_o, jitter, noise_c, noise_f, out_c, saved_c, sel_idx, n_rows_dev, dense, saved_f,
                      out_sel)
         ctx.mark_non_differentiable(depth_f, opa_f)
@@ -224,6 +250,7 @@ class RenderFn(torch.autograd.Function):
         rays_d, rays_o, jitter, noise_c, noise_f, out_c, saved_c, sel_idx, n_rows_dev, dense, saved_f, out_sel = ctx.saved
         B, dev = rays_d.shape[0], rays_d.device
         tc, tf = ctx.tc, ctx.tf
+        (net_c, net_f), (pad_c, pad_f) = ctx.nets, ctx.pads
         gc, gf = _flat_zero_grads(tc), _flat_zero_grads(tf)
         g_o = torch.zeros_like(rays_o)
         g_d = torch.zeros_like(rays_d)
@@ -235,15 +262,19 @@ class RenderFn(torch.autograd.Function):
             g_sel = torch.empty(n_rows, 4, device=dev)
             lib().call("mcnerf_gather_fine", _p(g_dense), _p(sel_idx, torch.int32), n_rows,
                        _p(n_rows_dev, torch.int32), _p(g_sel), _stream())
-            _branch_bwd(cfg, cfg.fine, tf, gf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx, n_rows, n_rows_dev,
+            _branch_bwd(cfg, net_f, tf, gf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx, n_rows, n_rows_dev,
                         saved_f, out_sel, g_sel, g_o, g_d)
         if g_rgb_c is not None:
             cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
             g_out_c = torch.empty_like(out_c)
             lib().call("mcnerf_composite_bwd", _p(out_c), _p(noise_c), _p(jitter), None, B, ctypes.byref(cc),
                        _p(ops._f32(g_rgb_c)), _p(g_out_c), _stream())
-            _branch_bwd(cfg, cfg.coarse, tc, gc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
+            _branch_bwd(cfg, net_c, tc, gc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
                         saved_c, out_c, g_out_c, g_o, g_d)
+        if pad_c is not None:
+            gc = pad_c.unpad(gc)
+        if pad_f is not None:
+            gf = pad_f.unpad(gf)
         pg = [gc[k] for k in ops.param_names(cfg.coarse[0])] + [gf[k] for k in ops.param_names(cfg.fine[0])]
         return (None, None, None, None, None, g_d, g_o) + tuple(pg)
 
