@@ -154,6 +154,8 @@ def run_ours(args):
 
         def step(data, read_loss):
             loss = gstep(data, 25, STAGE, RATIO)
+            if not data[0].is_cuda:
+                gstep.prefetch(data)          # e2e: the next step's H2D upload overlaps this step's graph
             sync_grads()
             opt.step()
             return loss.item() if read_loss else loss

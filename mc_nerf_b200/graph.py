@@ -10,6 +10,9 @@ optimiser) and replaces only HOW the launches are issued:
         loss = step(data, epoch, epoch_type, cur_ratio)   # copies inputs, replays the graph; .grad is populated
         optimizer.step()                                  # (gradient all-reduce first when distributed)
 
+`step.prefetch(next_data)` right after a call uploads the next step's (pinned) inputs on a side stream while the graph
+runs.
+
 What is baked into a captured graph and therefore part of its cache key: epoch, epoch_type, cur_ratio (they select the
 stage and the BARF frequency weights) and the input shapes.  Random draws are NOT baked: torch's CUDA generator is
 graph-aware, every replay consumes fresh Philox offsets in the reference's draw order.  The camera id is a device
@@ -27,6 +30,28 @@ class GraphedTrainStep:
     def __init__(self, model, loss_fn, warmup=3):
         self.model, self.loss_fn, self.warmup = model, loss_fn, warmup
         self._graphs = {}
+        self._staged = None       # (ids of the host tensors, device staging copies, upload-done event)
+        self._consumed = None     # event: the last staging -> static copy has been issued on the main stream
+        self._copy_stream = None
+
+    def prefetch(self, data):
+        """Start uploading the NEXT step's inputs (pinned host tensors) on a side stream while the current step runs;
+        the next __call__ with the same tensors only pays a device-to-device copy into the graph's static inputs."""
+        dev = torch.device(self.model.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        side = self._copy_stream
+        if self._staged is None or any(s.shape != t.shape or s.dtype != t.dtype for s, t in zip(self._staged[1], data)):
+            bufs = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in data)
+        else:
+            bufs = self._staged[1]
+        if self._consumed is not None:
+            side.wait_event(self._consumed)            # the previous contents have been handed to the graph
+        with torch.cuda.stream(side):
+            for b, t in zip(bufs, data):
+                b.copy_(t, non_blocking=True)
+            done = side.record_event()
+        self._staged = (tuple(id(t) for t in data), bufs, done)
 
     def _eager(self, static, key):
         epoch, epoch_type, ratio = key[:3]
@@ -64,7 +89,16 @@ class GraphedTrainStep:
         if ent is None:
             ent = self._graphs[key] = self._capture(data, key)
         g, static, loss = ent
-        for s, t in zip(static, data):
-            s.copy_(t, non_blocking=True)
+        staged = self._staged
+        if staged is not None and staged[0] == tuple(id(t) for t in data):
+            main = torch.cuda.current_stream()
+            main.wait_event(staged[2])
+            for s, b in zip(static, staged[1]):
+                s.copy_(b, non_blocking=True)
+            self._consumed = main.record_event()
+            self._staged = (None, staged[1], None)      # keep the buffers, forget the contents
+        else:
+            for s, t in zip(static, data):
+                s.copy_(t, non_blocking=True)
         g.replay()
         return loss

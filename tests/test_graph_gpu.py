@@ -135,3 +135,25 @@ def test_graph_rejects_host_side_sample_cap():
     batch = tuple(t.to(DEV) for t in syn.make_train_batch(sp, img_id=1, seed=3))
     with pytest.raises(RuntimeError, match="cap"):
         GraphedTrainStep(m, MC_NeRF_Loss(sp))(batch, 25, STAGE, 0.5)
+
+
+def test_prefetched_inputs_give_the_same_step():
+    from mc_nerf_b200.graph import GraphedTrainStep
+    sp, m, loss_fn = build(2)
+    rng = syn.draw_step_rng(sp, 256, seed=5)
+    host_a = tuple(t.pin_memory() for t in syn.make_train_batch(sp, img_id=2, seed=3))
+    host_b = tuple(t.pin_memory() for t in syn.make_train_batch(sp, img_id=4, seed=9))
+    with FixedRNG(rng):
+        step = GraphedTrainStep(m, loss_fn)
+        la = step(host_a, 25, STAGE, 0.5).item()          # direct upload
+        lb = step(host_b, 25, STAGE, 0.5).item()
+        assert la != lb
+        step.prefetch(host_b)
+        assert step(host_b, 25, STAGE, 0.5).item() == lb   # staged upload, same inputs -> same loss
+        step.prefetch(host_a)
+        assert step(host_a, 25, STAGE, 0.5).item() == la
+        step.prefetch(host_a)                              # staged A, asked for B: the staging is ignored
+        assert step(host_b, 25, STAGE, 0.5).item() == lb
+        for _ in range(3):                                 # steady state: prefetch right after every call
+            assert step(host_a, 25, STAGE, 0.5).item() == la
+            step.prefetch(host_a)
