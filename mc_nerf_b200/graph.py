@@ -20,8 +20,8 @@ tensor, so one graph serves all cameras.  Gradients are produced by the graph in
 whole-network-capture contract): do not call optimizer.zero_grad() between replays, and do not accumulate.
 Drop every reference to losses / outputs of earlier EAGER steps of the same model before the first graphed step: a live
 eager autograd graph keeps its AccumulateGrad nodes bound to the default stream, which breaks the capture.
-Configurations whose forward needs the host (the reference's 128-samples-per-ray cap with its CPU randperm, active
-when samples*scale > 128) cannot be captured and raise.
+The reference's 128-samples-per-ray cap (samples*scale > 128) is drawn on the device (render.select_and_cap), so those
+configurations capture as well.
 """
 import torch
 
@@ -62,9 +62,6 @@ class GraphedTrainStep:
 
     def _capture(self, data, key):
         m = self.model
-        if m.sys_param["samples"] * m.sys_param["scale"] > 128:
-            raise RuntimeError("GraphedTrainStep: samples*scale > 128 activates the reference's host-side sample cap "
-                               "(CPU randperm + synchronisation); that step cannot be captured in a CUDA graph")
         dev = torch.device(m.device)
         static = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev).copy_(t) for t in data)
         params = [p for p in m.parameters()]

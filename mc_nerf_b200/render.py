@@ -183,16 +183,23 @@ def select_and_cap(cfg, out_c, noise_sel, jitter, B, train, cap_perm=None):
     sel_idx, offs, n_sel = ops.select_fine(w_sel, w_max, cfg.scale, cfg.thresh)
     n_rows, n_rows_dev = B * cfg.Sf, n_sel
     if train and cfg.Sf > 128:
-        n = int(n_sel.item())                      # the reference synchronises here too
-        if n > B * 128:
-            # the reference draws this permutation with the CPU generator (~40 ms for the default config's 3.4 M
-            # selected samples); the same uniform B*128-subset is drawn on the device here
-            perm = cap_perm if cap_perm is not None else torch.randperm(n, device=dev)
-            keep = perm[:B * 128].to(dev)
-            sel_idx = sel_idx[:n][keep].contiguous()
-            n_rows, n_rows_dev = B * 128, None
-        else:
-            n_rows, n_rows_dev = n, None
+        K = B * 128
+        if cap_perm is not None:                   # test hook: an explicit permutation of the n selected samples
+            n = int(n_sel.item())                  # (host synchronisation, as in the reference)
+            if n > K:
+                sel_idx = sel_idx[:n][cap_perm[:K].to(dev)].contiguous()
+                n_rows, n_rows_dev = K, None
+            else:
+                n_rows, n_rows_dev = n, None
+        elif sel_idx.shape[0] > K:
+            # The reference synchronises, draws torch.randperm(n) on the CPU (~40 ms for the shipped config's 3.4 M
+            # selected samples) and keeps the first K.  Same uniform K-subset without leaving the device: one uniform
+            # key per capacity slot, slots beyond the device-side count n pushed to the end, argsort, first K.
+            # (When n <= K all n samples survive, in shuffled row order - which no result depends on.)
+            keys = torch.rand(sel_idx.shape[0], device=dev)
+            keys.masked_fill_(torch.arange(sel_idx.shape[0], device=dev, dtype=torch.int32) >= n_sel, 2.0)
+            sel_idx = sel_idx[torch.argsort(keys)[:K]].contiguous()
+            n_rows, n_rows_dev = K, torch.clamp(n_sel, max=K)
     return sel_idx, n_rows, n_rows_dev, w_sel
 
 

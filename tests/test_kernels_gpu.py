@@ -271,3 +271,43 @@ def test_reprojection_golden_and_backward(mods):
     orc.reproject(r["wpts"], Kc, Rc).backward(g)
     close(K.grad, Kc.grad, rtol=1e-4, atol=1e-3)
     close(Rt.grad, Rc.grad, rtol=1e-4, atol=1e-2)
+
+
+def test_device_side_sample_cap_keeps_a_uniform_subset():
+    """ref: model/mc_nerf.py:630-632 - more than 128*B selected fine samples in training: keep a uniformly random
+    subset of exactly 128*B.  Drawn on the device (render.select_and_cap) without the reference's host round trip."""
+    from mc_nerf_b200 import render
+    B, Sc, scale = 64, 64, 4
+    K = B * 128
+    cfg = render.RenderCfg(1.0, 8.0, Sc, scale, 10, True, -20.0, 1e-3, (8, 256, (4,)), (8, 256, (4,)))
+    g = torch.Generator().manual_seed(3)
+    out_c = torch.randn(B * Sc, 4, generator=g)
+    out_c[:, 0] = -2.0              # thin uniform medium: transmittance stays high, most samples pass the threshold
+    noise = torch.randn(B, Sc, generator=g).to(DEV)
+    jitter = (torch.rand(B, generator=g) * 0.1).to(DEV)
+    out_c = out_c.to(DEV)
+    all_idx, n_all, n_all_dev, _ = render.select_and_cap(cfg, out_c, noise, jitter, B, train=False)
+    n = int(n_all_dev.item())
+    assert n > K and n_all == B * Sc * scale
+    pool = all_idx[:n].cpu()
+    first_half = 0.0
+    draws = []
+    for _ in range(6):
+        idx, n_rows, n_dev, _ = render.select_and_cap(cfg, out_c, noise, jitter, B, train=True)
+        kept = idx[:K].cpu()
+        assert n_rows == K and int(n_dev.item()) == K and idx.shape[0] == K
+        assert len(torch.unique(kept)) == K and bool(torch.isin(kept, pool).all())
+        first_half += float((kept < pool[n // 2]).float().mean())      # pool is ascending: median split
+        draws.append(kept)
+    assert abs(first_half / 6 - 0.5) < 0.02
+    assert not torch.equal(draws[0], draws[1])
+    # fewer than 128*B selected: everything survives (row order is free)
+    sparse = out_c.clone()
+    sparse[:, 0] = -30.0
+    sparse[::7, 0] = 5.0
+    all2, _, n2_dev, _ = render.select_and_cap(cfg, sparse, noise, jitter, B, train=False)
+    n2 = int(n2_dev.item())
+    assert 0 < n2 <= K
+    idx2, n_rows2, n_dev2, _ = render.select_and_cap(cfg, sparse, noise, jitter, B, train=True)
+    assert n_rows2 == K and int(n_dev2.item()) == n2
+    assert torch.equal(torch.sort(idx2[:n2]).values, all2[:n2])
