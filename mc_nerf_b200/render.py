@@ -207,7 +207,7 @@ class RenderFn(torch.autograd.Function):
     """(rays_d, rays_o, *coarse params, *fine params) -> rgb_c, rgb_f, depth_f, opacity_f  (all [B,*])."""
 
     @staticmethod
-    def forward(ctx, cfg, train, band_w, rng, cap_perm, rays_d, rays_o, *params):
+    def forward(ctx, cfg, train, need_grad, band_w, rng, cap_perm, rays_d, rays_o, *params):
         rays_d, rays_o = ops._f32(rays_d), ops._f32(rays_o)
         B, dev = rays_d.shape[0], rays_d.device
         nc = len(ops.param_names(cfg.coarse[0]))
@@ -218,7 +218,9 @@ class RenderFn(torch.autograd.Function):
         net_c, run_c, pad_c = _tc_view(cfg, cfg.coarse, tc)       # what the kernels see (narrow nets: 256-wide shadow)
         net_f, run_f, pad_f = _tc_view(cfg, cfg.fine, tf)
         # coarse
-        need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
+        # need_grad: decided by render() - grad mode is always off inside Function.forward, and ctx.needs_input_grad
+        # stays True for parameters under torch.no_grad(), which would run the stash-writing training kernels in the
+        # demo / validation renders
         out_c, saved_c = _branch_fwd(cfg, net_c, run_c, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
                                      need_grad)
         cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
@@ -283,7 +285,7 @@ class RenderFn(torch.autograd.Function):
         if pad_f is not None:
             gf = pad_f.unpad(gf)
         pg = [gc[k] for k in ops.param_names(cfg.coarse[0])] + [gf[k] for k in ops.param_names(cfg.fine[0])]
-        return (None, None, None, None, None, g_d, g_o) + tuple(pg)
+        return (None, None, None, None, None, None, g_d, g_o) + tuple(pg)
 
 
 def draw_rng(cfg, B, device, train):
@@ -303,4 +305,5 @@ def render(cfg, params_c, params_f, rays_d, rays_o, train, band_w=None, rng=None
     if rng is None:
         rng = draw_rng(cfg, rays_d.shape[0], rays_d.device, train)
     plist = [params_c[k] for k in ops.param_names(cfg.coarse[0])] + [params_f[k] for k in ops.param_names(cfg.fine[0])]
-    return RenderFn.apply(cfg, train, band_w, rng, cap_perm, rays_d, rays_o, *plist)
+    need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in [rays_d, rays_o] + plist)
+    return RenderFn.apply(cfg, train, need_grad, band_w, rng, cap_perm, rays_d, rays_o, *plist)

@@ -332,3 +332,26 @@ def test_reference_default_config_shapes_mixed_paths(padded, monkeypatch):
     for k, v in pfr.items():
         gk = named[f"nerf.nerf_fine.{k}"].grad
         assert ((gk.cpu() - v.grad).norm() / v.grad.norm().clamp_min(1e-12)).item() < 0.15, k
+
+
+def test_no_grad_render_uses_the_inference_kernels(monkeypatch):
+    """Under torch.no_grad() (demo, validation) the parameters still have requires_grad=True; the renderer must not
+    take that for a training pass: no activation stash may be allocated or written."""
+    from mc_nerf_b200 import ops
+    sp_kw = dict(n_cam=4, img_h=16, img_w=16, batch=256, samples=16, scale=2)
+    sp0 = syn.make_sys_param(**sp_kw)
+    cfg = orc.cfg_from_sys_param(sp0)
+    pc, pf = orc.init_mlp_params(*cfg["coarse"], seed=1), orc.init_mlp_params(*cfg["fine"], seed=2)
+    sp, m = build_model(sp_kw, syn.init_camera_weights(sp0), pc, pf, precision="bf16")
+    g = torch.Generator().manual_seed(1)
+    rd = torch.nn.functional.normalize(torch.randn(256, 3, generator=g), dim=-1).to(DEV)
+    ro = (torch.randn(256, 3, generator=g) * 0.2).to(DEV)
+    rgb_train, _ = m.nerf.render_rays_train(rd, ro, 25, 1.0)          # training pass: stash allowed
+    assert rgb_train.requires_grad
+
+    def no_stash(*a, **k):
+        raise AssertionError("activation stash requested in an inference render")
+    monkeypatch.setattr(ops, "tc_stash", no_stash)
+    with torch.no_grad():
+        rgb, depth, opa = m.nerf.render_rays_test(rd, ro, m.nerf.nerf_coarse, m.nerf.nerf_fine)
+    assert rgb.shape == (256, 3) and not rgb.requires_grad and bool(torch.isfinite(rgb).all())

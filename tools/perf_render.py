@@ -33,3 +33,21 @@ with torch.no_grad():
     dt = (time.perf_counter() - t0) / views
 print(f"demo render {img}x{img}, chunk {batch}: {dt*1e3:.1f} ms/view  {img*img/dt/1e6:.2f} Mrays/s  "
       f"(110 views: {110*dt:.1f} s)")
+
+from mc_nerf_b200._lib import lib
+L = lib()
+with torch.no_grad():
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    L.profile_begin()
+    demo(torch.tensor([5]))
+    torch.cuda.synchronize()
+    calls = [(n, e0.elapsed_time(e1)) for n, e0, e1 in L._prof if n == "mcnerf_mlp_tc_fwd"]
+    prof = L.profile_end()
+    wall = time.perf_counter() - t0
+print("one profiled view: wall %.1f ms; kernel ms by entry: " % (wall * 1e3)
+      + ", ".join(f"{k.replace('mcnerf_', '')} {v:.2f}" for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:8])
+      + f"; sum {sum(prof.values()):.1f}")
+from mc_nerf_b200 import render
+print("mlp_tc_fwd calls of the view (ms):", " ".join(f"{ms:.2f}" for _, ms in calls),
+      "| fine rows selected in the last chunk:", int(render.LAST["n_rows_dev"].item()), "of capacity", render.LAST["n_rows"])
