@@ -99,7 +99,7 @@ __host__ __device__ inline size_t stash_tiles(int n_rows) {
   return t + (t & 1);
 }
 constexpr int HEAD_BYTES = TM * 32 * 2;      // 8 KB: head-gradient tile [128 x 32] bf16 (g_sh 0..26, g_sigma at 31)
-constexpr int BITS_BYTES = TM * 32;          // 4 KB: ReLU gate bits of one tile-layer [128 rows][8 x u32]
+constexpr int BITS_BYTES = TM * 32;          // 4 KB: ReLU gate bits of one tile-layer [8 x 32-column block][128 rows] u32
 
 // Tile images in HBM (activation stash, dY stash, head tile) are stored as two 64-row halves, each a contiguous
 // [k-group plane][64 rows][16 B] block, so that the weight-gradient kernel fetches one half of ALL planes with a

@@ -18,7 +18,7 @@ struct BwdArgs {
   int sig2_off;
   int n_slots;              // D + 2
   const uint8_t* stash_bits;  // forward ReLU gate bits [tile][n_slots][BITS_BYTES]
-  const float* stash_sh;    // [row][SH_LD]
+  const float* stash_sh;    // [tile][SH_LD/4 float4 groups][128 rows] float4
   uint8_t* dy;              // [tile][n_slots][ACT_BYTES]
   uint8_t* dy_head;         // [tile][HEAD_BYTES]
   const float* g_out4;      // [rows,4]
@@ -233,11 +233,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
           const float Y[9] = {bC0, -bC1 * y, bC1 * zz, -bC1 * x, bC2[0] * x * y, bC2[1] * y * zz,
                               bC2[2] * (2.f * zz * zz - x * x - y * y), bC2[3] * x * zz, bC2[4] * (x * x - y * y)};
           const float gc[3] = {g.y * o.y * (1.f - o.y), g.z * o.z * (1.f - o.z), g.w * o.w * (1.f - o.w)};
-          const float4* shp = reinterpret_cast<const float4*>(a.stash_sh + (size_t)row_g * SH_LD);
+          const float4* shp = reinterpret_cast<const float4*>(a.stash_sh) + (size_t)(row_g >> 7) * (TM * SH_LD / 4) + (row_g & (TM - 1));
           float sh[28];
 #pragma unroll
           for (int i = 0; i < 7; ++i) {
-            float4 v = shp[i];
+            float4 v = shp[i * TM];            // [tile][float4 group][row] (mlp_tc_fwd.cu)
             sh[4 * i] = v.x; sh[4 * i + 1] = v.y; sh[4 * i + 2] = v.z; sh[4 * i + 3] = v.w;
           }
           float comb[9];
@@ -289,9 +289,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
           // forward ReLU gate bits of this row for this warp's two 32-column blocks, fetched BEFORE waiting
           uint32_t gate0 = 0, gate1 = 0;
           if (tile_ok && jb.mask_slot >= 0) {
-            const uint2 gg = *reinterpret_cast<const uint2*>(a.stash_bits + ((size_t)tile * a.n_slots + jb.mask_slot) * BITS_BYTES +
-                                                              q * 32 + cq * 8);
-            gate0 = gg.x; gate1 = gg.y;
+            const uint32_t* gb = reinterpret_cast<const uint32_t*>(a.stash_bits + ((size_t)tile * a.n_slots + jb.mask_slot) * BITS_BYTES) + q;
+            gate0 = gb[(2 * cq) * TM]; gate1 = gb[(2 * cq + 1) * TM];      // [32-column block][row] (mlp_tc_fwd.cu)
           }
           tc::mbar_wait(&bars->acc_full[t], par);
           tc::tcgen05_fence_after();

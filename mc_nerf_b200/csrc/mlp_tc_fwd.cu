@@ -214,7 +214,7 @@ struct FwdArgs {
   float* out4;
   uint8_t* stash;        // [tile][n_slots][ACT_BYTES] or null
   uint8_t* stash_enc;    // [tile][ENC_BYTES]
-  float* stash_sh;       // [row][SH_LD]
+  float* stash_sh;       // [tile][SH_LD/4 float4 groups][128 rows] float4
   uint8_t* stash_bits;   // [tile][n_slots][BITS_BYTES] ReLU gate bits
   int n_slots;
 };
@@ -530,10 +530,11 @@ __global__ void __launch_bounds__(TRAIN ? FWD_THREADS_TRAIN : FWD_THREADS, 1) ml
               }
               reinterpret_cast<float4*>(a.out4)[row_g] = make_float4(sigma_raw, c[0], c[1], c[2]);
               if (TRAIN) {
-                float4* dst = reinterpret_cast<float4*>(a.stash_sh + (size_t)row_g * SH_LD);
+                // per tile [float4 group i][row]: a warp's 32 rows write 512 contiguous bytes per store
+                float4* dst = reinterpret_cast<float4*>(a.stash_sh) + (size_t)(row_g >> 7) * (TM * SH_LD / 4) + (row_g & (TM - 1));
 #pragma unroll
                 for (int i = 0; i < 7; ++i)
-                  dst[i] = make_float4(sh[4 * i], sh[4 * i + 1], sh[4 * i + 2], i < 6 ? sh[4 * i + 3] : 0.f);
+                  dst[i * TM] = make_float4(sh[4 * i], sh[4 * i + 1], sh[4 * i + 2], i < 6 ? sh[4 * i + 3] : 0.f);
               }
             }
             continue;
@@ -548,7 +549,8 @@ __global__ void __launch_bounds__(TRAIN ? FWD_THREADS_TRAIN : FWD_THREADS, 1) ml
             stpar ^= 1u << t;
           }
           float dot = 0.f;
-          uint32_t* gate_out = st_tile ? reinterpret_cast<uint32_t*>(a.stash_bits + ((size_t)tile * a.n_slots + st.stash_slot) * BITS_BYTES + q * 32)
+          // gate words are stored [32-column block w][row]: a warp's 32 rows write one contiguous 128-byte line
+          uint32_t* gate_out = st_tile ? reinterpret_cast<uint32_t*>(a.stash_bits + ((size_t)tile * a.n_slots + st.stash_slot) * BITS_BYTES) + q
                                        : nullptr;
           // 16 accumulator columns (bias already in them): ReLU, bf16 -> next A operand (smem) / stash / sigma dot.
           // This warp owns columns [64 cq, 64 cq + 64) = 32-column blocks 2cq and 2cq+1, walked in four halves with
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__(TRAIN ? FWD_THREADS_TRAIN : FWD_THREADS, 1) ml
             if (TRAIN) {
               sbits |= tc::sign_bits16(v, h & 1);
               if (h & 1) {
-                if (gate_out) gate_out[2 * cq + (h >> 1)] = ~sbits;     // gate = accumulator > 0
+                if (gate_out) gate_out[(2 * cq + (h >> 1)) * TM] = ~sbits;     // gate = accumulator > 0
                 sbits = 0;
               }
             }
