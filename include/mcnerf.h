@@ -84,6 +84,8 @@ typedef struct {
   int S;            /* samples per ray on this grid (coarse: Sc, fine: Sc*scale) */
   int n_freqs;      /* L */
   float band_w[MCNERF_MAX_FREQS];
+  const float* band_w_dev;   /* optional: L floats in DEVICE memory that override band_w[] when non-NULL, so that a
+                                captured CUDA graph follows a moving BARF window (the struct itself is baked in) */
 } mcnerf_sampling;
 
 int mcnerf_encode_rays_fwd(const float* rays_o, const float* rays_d, const float* jitter /*[n_rays] or NULL*/,

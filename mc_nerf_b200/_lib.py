@@ -19,7 +19,7 @@ _fp = ctypes.c_void_p
 
 class Sampling(ctypes.Structure):
     _fields_ = [("near_", ctypes.c_float), ("far_", ctypes.c_float), ("S", ctypes.c_int),
-                ("n_freqs", ctypes.c_int), ("band_w", ctypes.c_float * MAX_FREQS)]
+                ("n_freqs", ctypes.c_int), ("band_w", ctypes.c_float * MAX_FREQS), ("band_w_dev", ctypes.c_void_p)]
 
 
 class MlpParams(ctypes.Structure):

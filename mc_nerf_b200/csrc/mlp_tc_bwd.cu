@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
   uint8_t* wst = small + 2 * HEAD_BYTES;                   // [BSTAGE][STAGE_BYTES]
   float* w2s = reinterpret_cast<float*>(wst + BSTAGE * STAGE_BYTES);     // w_sigma2 [256] (no L1 left: keep it on chip)
   BwdBars* bars = reinterpret_cast<BwdBars*>(w2s + 256);
+  static_assert(sizeof(BwdBars) <= 128, "BwdBars must leave room for the band weights");
+  float* bw_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);      // 10 BARF band weights
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   const int n_tiles = (rows + TM - 1) / TM;
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
   }
   if (warp == BW_MMA) tc::tmem_alloc2(&bars->tmem_base, 512);
   if (tid < 256) w2s[tid] = a.bias[a.sig2_off + tid];
+  if (tid < 10) bw_s[tid] = a.smp.band_w_dev ? a.smp.band_w_dev[tid] : a.smp.band_w[tid];   // see mlp_tc_fwd.cu
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::cluster_sync();
@@ -387,7 +390,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
                   float g = d[c], f = 1.f;
 #pragma unroll
                   for (int kf = 0; kf < 10; ++kf) {
-                    g += a.smp.band_w[kf] * f * (d[3 + c * 20 + kf] * cs - d[3 + c * 20 + 10 + kf] * sn);
+                    const float bw = bw_s[kf];
+                    g += bw * f * (d[3 + c * 20 + kf] * cs - d[3 + c * 20 + 10 + kf] * sn);
                     const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
                     sn = s2; cs = c2; f *= 2.f;
                   }

@@ -232,7 +232,7 @@ struct __align__(16) SmemBars {
   uint32_t tmem_base;
 };
 constexpr int ONES_BYTES = 256;
-constexpr int W2_FLOATS = 264;         // w_sigma2[256], b_sigma2, pad
+constexpr int W2_FLOATS = 280;         // w_sigma2[256], b_sigma2, pad to 264, then the 10 BARF band weights (+ pad)
 constexpr int SMEM_FWD = 2 * ACT_BYTES + 2 * ENC_BYTES + FSTAGE * STAGE_BYTES + ONES_BYTES + W2_FLOATS * 4 + 256;
 static_assert(sizeof(SmemBars) <= 256 && SMEM_FWD <= 232448, "shared memory budget");
 // 18 warps: 16 epilogue warps (TMEM lane quarter = warp % 4, column quarter = warp / 4) that serve BOTH tile slots in
@@ -259,7 +259,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
 // Encode one row (sample) into 64 bf16 features and store them as 8 planes of the enc tile image
 // (and optionally to the global stash image).  L = 10 frequencies.
 __device__ __forceinline__ void encode_row(const FwdArgs& a, int row_g, bool valid, uint32_t enc_smem, int q,
-                                           uint8_t* stash_enc_tile) {
+                                           uint8_t* stash_enc_tile, const float* bw_s) {
   float f[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) f[i] = 0.f;
@@ -280,8 +280,9 @@ __device__ __forceinline__ void encode_row(const FwdArgs& a, int row_g, bool val
         sincosf(xc, &sn, &cs);
 #pragma unroll
         for (int kf = 0; kf < 10; ++kf) {
-          f[3 + c * 20 + kf] = sn * a.smp.band_w[kf];
-          f[3 + c * 20 + 10 + kf] = cs * a.smp.band_w[kf];
+          const float bw = bw_s[kf];
+          f[3 + c * 20 + kf] = sn * bw;
+          f[3 + c * 20 + 10 + kf] = cs * bw;
           float s2 = 2.f * sn * cs;            // angle doubling: error grows 2x per octave (<= 5e-5 at 2^9),
           float c2 = 1.f - 2.f * sn * sn;      // far below the bf16 rounding of the feature
           sn = s2;
@@ -327,6 +328,9 @@ __global__ void __launch_bounds__(TRAIN ? FWD_THREADS_TRAIN : FWD_THREADS, 1) ml
   }
   if (warp == W_MMA) tc::tmem_alloc2(&bars->tmem_base, 512);
   for (int i = tid; i < 257; i += blockDim.x) w2s[i] = a.bias[a.sig2_off + i];
+  // BARF band weights: from the device buffer when given (CUDA-graph replays follow a moving window), else the
+  // launch-time values; kept in shared memory so that the input stage pays no global round trip per row
+  if (tid < 10) w2s[264 + tid] = a.smp.band_w_dev ? a.smp.band_w_dev[tid] : a.smp.band_w[tid];
   if (tid < 128)   // core matrix 0: 8 rows x (1, 1, 0, 0, 0, 0, 0, 0); core matrix 1: zeros
     reinterpret_cast<__nv_bfloat16*>(ones)[tid] = __float2bfloat16((tid < 64 && (tid & 7) < 2) ? 1.f : 0.f);
   tc::fence_proxy_async();
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(TRAIN ? FWD_THREADS_TRAIN : FWD_THREADS, 1) ml
       if (cq < 2) {       // warps 0-3 encode the rows of slot 0, warps 4-7 those of slot 1
         const int tile = 2 * pair + cq, row_g = tile * TM + q;
         uint8_t* st_enc = (TRAIN && tile < n_tiles) ? a.stash_enc + (size_t)tile * ENC_BYTES : nullptr;
-        encode_row(a, row_g, tile < n_tiles && row_g < rows, enc0 + cq * ENC_BYTES, q, st_enc);
+        encode_row(a, row_g, tile < n_tiles && row_g < rows, enc0 + cq * ENC_BYTES, q, st_enc, w2s + 264);
       }
       tc::fence_proxy_async();
       tc::tcgen05_fence_before();

@@ -152,7 +152,7 @@ __global__ void encode_points_fwd_k(const float* __restrict__ x, int n, mcnerf_s
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 3 * n) return;
   int m = t / 3, c = t - 3 * m;
-  encode_coord(x[t], smp.n_freqs, smp.band_w, enc + (size_t)m * ld, c);
+  encode_coord(x[t], smp.n_freqs, (smp.band_w_dev ? smp.band_w_dev : smp.band_w), enc + (size_t)m * ld, c);
 }
 
 __global__ void encode_points_bwd_k(const float* __restrict__ x, int n, mcnerf_sampling smp,
@@ -160,7 +160,7 @@ __global__ void encode_points_bwd_k(const float* __restrict__ x, int n, mcnerf_s
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= 3 * n) return;
   int m = t / 3, c = t - 3 * m;
-  gx[t] = encode_coord_bwd(x[t], smp.n_freqs, smp.band_w, genc + (size_t)m * ld, c);
+  gx[t] = encode_coord_bwd(x[t], smp.n_freqs, (smp.band_w_dev ? smp.band_w_dev : smp.band_w), genc + (size_t)m * ld, c);
 }
 
 __device__ __forceinline__ float sample_z(const mcnerf_sampling& smp, int k, float jit) {
@@ -179,7 +179,7 @@ __global__ void encode_rays_fwd_k(const float* __restrict__ ro, const float* __r
   int ray = flat / smp.S, k = flat - ray * smp.S;
   float z = sample_z(smp, k, jitter ? jitter[ray] : 0.f);
   float xc = ro[3 * ray + c] + rd[3 * ray + c] * z;
-  encode_coord(xc, smp.n_freqs, smp.band_w, enc + (size_t)m * ld, c);
+  encode_coord(xc, smp.n_freqs, (smp.band_w_dev ? smp.band_w_dev : smp.band_w), enc + (size_t)m * ld, c);
 }
 
 // One thread per row: gradient wrt the sample position, then a segmented warp reduction over rows that
@@ -202,7 +202,7 @@ __global__ void encode_rays_bwd_k(const float* __restrict__ ro, const float* __r
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float xc = ro[3 * ray + c] + rd[3 * ray + c] * z;
-      float g = encode_coord_bwd(xc, smp.n_freqs, smp.band_w, genc + (size_t)m * ld, c);
+      float g = encode_coord_bwd(xc, smp.n_freqs, (smp.band_w_dev ? smp.band_w_dev : smp.band_w), genc + (size_t)m * ld, c);
       v[c] = g;
       v[3 + c] = g * z;
     }
@@ -284,7 +284,7 @@ extern "C" int mcnerf_encode_rays_bwd(const float* rays_o, const float* rays_d, 
 
 static int points_sampling(int n_freqs, const float* band_w_host, mcnerf_sampling* s) {
   MC_ARG(n_freqs >= 1 && n_freqs <= MCNERF_MAX_FREQS);
-  s->near_ = 0.f; s->far_ = 1.f; s->S = 2; s->n_freqs = n_freqs;
+  s->near_ = 0.f; s->far_ = 1.f; s->S = 2; s->n_freqs = n_freqs; s->band_w_dev = nullptr;
   for (int k = 0; k < MCNERF_MAX_FREQS; ++k) s->band_w[k] = (band_w_host && k < n_freqs) ? band_w_host[k] : 1.f;
   return 0;
 }

@@ -13,9 +13,11 @@ optimiser) and replaces only HOW the launches are issued:
 `step.prefetch(next_data)` right after a call uploads the next step's (pinned) inputs on a side stream while the graph
 runs.
 
-What is baked into a captured graph and therefore part of its cache key: epoch, epoch_type, cur_ratio (they select the
-stage and the BARF frequency weights) and the input shapes.  Random draws are NOT baked: torch's CUDA generator is
-graph-aware, every replay consumes fresh Philox offsets in the reference's draw order.  The camera id is a device
+What is baked into a captured graph and therefore part of its cache key: epoch_type (the stage) and the input shapes.
+cur_ratio is NOT baked: the BARF frequency weights it selects are kept in a device buffer (NeRF_Model.set_band_weights)
+that the captured kernels read, so one graph serves the whole stage although cur_ratio changes every step.
+Random draws are NOT baked: torch's CUDA generator is graph-aware, every replay consumes fresh Philox offsets in the
+reference's draw order.  The camera id is a device
 tensor, so one graph serves all cameras.  Gradients are produced by the graph into static buffers (the usual
 whole-network-capture contract): do not call optimizer.zero_grad() between replays, and do not accumulate.
 Drop every reference to losses / outputs of earlier EAGER steps of the same model before the first graphed step: a live
@@ -54,7 +56,7 @@ class GraphedTrainStep:
         self._staged = (tuple(id(t) for t in data), bufs, done)
 
     def _eager(self, static, key):
-        epoch, epoch_type, ratio = key[:3]
+        epoch_type, epoch, ratio = key[0], self._call[0], self._call[1]
         loss_dict, _, _, _ = self.model(static, epoch, epoch_type, ratio)
         loss = self.loss_fn(loss_dict, epoch_type)
         loss.backward()
@@ -81,7 +83,14 @@ class GraphedTrainStep:
         return g, static, loss
 
     def __call__(self, data, epoch, epoch_type, cur_ratio):
-        key = (epoch, epoch_type, float(cur_ratio), tuple(tuple(t.shape) for t in data))
+        # cur_ratio moves every step (main.py:80): the BARF weights it selects live in a device buffer the captured
+        # kernels read, refreshed here; `epoch` is not used by the render (ref: model/mc_nerf.py:598-646)
+        nerf = self.model.nerf
+        if nerf.__dict__.get("_band_w_dev") is None:
+            nerf.use_device_band_weights(True)
+        nerf.set_band_weights(cur_ratio if epoch_type == "GLOBAL_OPTIM_EPOCH" else 1)
+        self._call = (epoch, float(cur_ratio))
+        key = (epoch_type, tuple(tuple(t.shape) for t in data))
         ent = self._graphs.get(key)
         if ent is None:
             ent = self._graphs[key] = self._capture(data, key)

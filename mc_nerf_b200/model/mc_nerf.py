@@ -403,6 +403,26 @@ class NeRF_Model(nn.Module):
         rays_d, rays_o = args
         return self.render_rays_test(rays_d, rays_o, self.nerf_coarse, self.nerf_fine)
 
+    def use_device_band_weights(self, enable=True):
+        """Keep the BARF window weights in a device buffer that the kernels read at run time instead of baking them
+        into every launch - what a captured CUDA graph needs to follow `cur_ratio` (graph.GraphedTrainStep).  The
+        caller then calls set_band_weights(step_r) before each training render."""
+        if enable:
+            self.__dict__["_band_w_dev"] = torch.ones(16, dtype=torch.float32, device=self.device)
+            self.__dict__["_band_w_host"] = torch.ones(16, dtype=torch.float32).pin_memory()
+        else:
+            self.__dict__["_band_w_dev"] = None
+
+    def set_band_weights(self, step_r):
+        """fill the device buffer with the window weights of `step_r` (independent of the current barf_mode flag,
+        which MC_Model.forward only sets when it runs)"""
+        if self.__dict__.get("_band_w_dev") is None:
+            return
+        emb = self.emmbedding_xyz
+        w = ops.barf_band_weights(float(step_r), emb.barf_start, emb.barf_end, emb.n_freqs)
+        self._band_w_host[:len(w)] = torch.tensor(w, dtype=torch.float32)
+        self._band_w_dev.copy_(self._band_w_host, non_blocking=True)
+
     def prefetch_weights(self):
         """start deriving the tensor-core weight images on a side stream (see render.prefetch_weights)"""
         if torch.device(self.device).type == "cuda":
@@ -415,6 +435,8 @@ class NeRF_Model(nn.Module):
         if only_coarse:
             return self._coarse_only(rays_d, rays_o, step_r)
         band_w = self.emmbedding_xyz.band_weights(step_r)
+        if band_w is not None and self.__dict__.get("_band_w_dev") is not None:
+            band_w = self._band_w_dev          # device-side weights, filled by set_band_weights(step_r) for this step
         rgb_c, rgb_f, _, _ = render.render(self.render_cfg, self.nerf_coarse.param_dict(), self.nerf_fine.param_dict(),
                                            rays_d, rays_o, True, band_w, rng, cap_perm)
         return rgb_c, rgb_f

@@ -44,10 +44,18 @@ def _f32(t):
 
 
 def make_sampling(near, far, S, n_freqs, band_w=None):
+    """band_w: None (all ones), a sequence of floats (baked into the struct), or a float32 CUDA tensor of >= n_freqs
+    weights that the kernels read at run time (CUDA-graph replays with a moving BARF window)."""
     s = Sampling()
     s.near_, s.far_, s.S, s.n_freqs = float(near), float(far), int(S), int(n_freqs)
+    dynamic = torch.is_tensor(band_w)
     for k in range(_lib.MAX_FREQS):
-        s.band_w[k] = float(band_w[k]) if (band_w is not None and k < n_freqs) else 1.0
+        s.band_w[k] = float(band_w[k]) if (band_w is not None and not dynamic and k < n_freqs) else 1.0
+    if dynamic:
+        if band_w.numel() < n_freqs:
+            raise _lib.McnerfError("band weight tensor shorter than n_freqs")
+        s.band_w_dev = _p(band_w).value
+        s._keep = band_w
     return s
 
 
@@ -472,6 +480,7 @@ class PaddedNet:
             off += n
         self.narrow_shapes = {name: tuple(tensors[name].shape) for name in self.names}
         self.key = None
+        self.cache = {}               # derived data of the shadow itself (its packed bf16 images)
 
     def _copy(self, src, dst, shapes):
         n = len(self.names)
@@ -545,7 +554,8 @@ class TcWeights:
             dev = next(iter(tensors.values())).device
             sz = [ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()]
             lib().call("mcnerf_mlp_tc_pack_sizes", ctypes.byref(ps), *[ctypes.byref(x) for x in sz])
-            if self.wf is None:
+            if self.wf is None or self.wf.device != dev:
+                self.wb = None
                 self.wf = torch.empty(sz[0].value, dtype=torch.uint8, device=dev)
                 self.bias = torch.empty(sz[2].value // 4, dtype=torch.float32, device=dev)
             if need_bwd and self.wb is None:

@@ -49,16 +49,21 @@ class RenderCfg:
                          (sp["fine_MLP_depth"], sp["fine_MLP_width"], tuple(sp["fine_MLP_skip"])), precision)
 
 
-_TC_CACHE = {}     # (data_ptr of the first weight) -> ops.TcWeights (packed bf16 images, refreshed on version change)
+def _owner_cache(params):
+    """Derived-data cache of ONE network (packed bf16 weight images, zero-padded shadow), stored on its first Parameter
+    so that it lives and dies with the network.  (A global cache keyed by device address would hand a newly created
+    network the images of a freed one that happened to occupy the same memory with the same version counters.)"""
+    owner = next(iter(params.values()))
+    cache = owner.__dict__.get("_mcnerf_cache")
+    if cache is None:
+        cache = owner.__dict__["_mcnerf_cache"] = {}
+    return cache
 
 
-def _tc_weights(ps, tensors, need_bwd):
-    key = next(iter(tensors.values())).data_ptr()
-    tcw = _TC_CACHE.get(key)
+def _tc_weights(ps, tensors, need_bwd, cache):
+    tcw = cache.get("tcw")
     if tcw is None:
-        if len(_TC_CACHE) > 16:
-            _TC_CACHE.clear()
-        tcw = _TC_CACHE[key] = ops.TcWeights()
+        tcw = cache["tcw"] = ops.TcWeights()
     return tcw.get(ps, tensors, need_bwd)
 
 
@@ -79,10 +84,10 @@ def prefetch_weights(cfg, params_c, params_f, need_bwd=True):
         if side is None:
             side = _SIDE[first.device.index] = torch.cuda.Stream(device=first.device)
         ps = ops.make_mlp_params(tensors, net[0], net[1], net[2], in_ch=cfg.in_ch)
-        key = first.data_ptr()
-        tcw = _TC_CACHE.get(key)
+        cache = _owner_cache(params)
+        tcw = cache.get("tcw")
         if tcw is None:
-            tcw = _TC_CACHE[key] = ops.TcWeights()
+            tcw = cache["tcw"] = ops.TcWeights()
         tcw.prefetch(ps, tensors, need_bwd, side)
 
 
@@ -96,24 +101,20 @@ def use_tc(cfg, net):
             and len([s for s in skips if 0 < s < depth]) <= 1)
 
 
-_PAD_CACHE = {}    # (data_ptr of the first weight) -> ops.PaddedNet
-
-
-def _tc_view(cfg, net, tensors):
-    """-> (net the kernels see, tensors the kernels see, PaddedNet or None)"""
+def _tc_view(cfg, net, tensors, cache):
+    """-> (net the kernels see, tensors the kernels see, PaddedNet or None, cache of the tensors the kernels see)"""
     depth, width, skips = net
     if not use_tc(cfg, net) or width == ops.TC_WIDTH:
-        return net, tensors, None
-    key = next(iter(tensors.values())).data_ptr()
-    pad = _PAD_CACHE.get(key)
-    if pad is None or pad.narrow_shapes != {k: tuple(v.shape) for k, v in tensors.items()}:
-        if len(_PAD_CACHE) > 16:
-            _PAD_CACHE.clear()
-        pad = _PAD_CACHE[key] = ops.PaddedNet(tensors, depth, width, cfg.in_ch)
-    return (depth, ops.TC_WIDTH, skips), pad.refresh(tensors), pad
+        return net, tensors, None, cache
+    pad = cache.get("pad")
+    if pad is None or pad.narrow_shapes != {k: tuple(v.shape) for k, v in tensors.items()} \
+            or pad.flat.device != next(iter(tensors.values())).device:
+        pad = cache["pad"] = ops.PaddedNet(tensors, depth, width, cfg.in_ch)
+    return (depth, ops.TC_WIDTH, skips), pad.refresh(tensors), pad, pad.cache
 
 
-def _branch_fwd(cfg, net, tensors, rays_o, rays_d, jitter, S, band_w, sel_idx, n_rows, n_rows_dev, train=True):
+def _branch_fwd(cfg, net, tensors, rays_o, rays_d, jitter, S, band_w, sel_idx, n_rows, n_rows_dev, train=True,
+                cache=None):
     """encode + MLP for one branch.  Returns (out4 [n_rows,4], saved-for-backward tuple)."""
     depth, width, skips = net
     dev = rays_o.device
@@ -122,7 +123,7 @@ def _branch_fwd(cfg, net, tensors, rays_o, rays_d, jitter, S, band_w, sel_idx, n
     if use_tc(cfg, net):
         # fused sampling + encoding + MLP + SH head, bf16 tcgen05 (mlp_tc_fwd.cu)
         ps = ops.make_mlp_params(tensors, depth, width, skips, in_ch=cfg.in_ch)
-        tcw = _tc_weights(ps, tensors, train)
+        tcw = _tc_weights(ps, tensors, train, cache if cache is not None else {})
         tin = ops.make_tc_input_rays(rays_o, rays_d, jitter, smp, sel_idx, n_rows, n_rows_dev)
         out4 = torch.empty(n_rows, 4, device=dev)
         stash = ops.tc_stash(ps, n_rows, dev) if train else None
@@ -245,7 +246,7 @@ class RenderFn(torch.autograd.Function):
     """(rays_d, rays_o, *coarse params, *fine params) -> rgb_c, rgb_f, depth_f, opacity_f  (all [B,*])."""
 
     @staticmethod
-    def forward(ctx, cfg, train, need_grad, band_w, rng, cap_perm, rays_d, rays_o, *params):
+    def forward(ctx, cfg, caches, train, need_grad, band_w, rng, cap_perm, rays_d, rays_o, *params):
         rays_d, rays_o = ops._f32(rays_d), ops._f32(rays_o)
         B, dev = rays_d.shape[0], rays_d.device
         nc = len(ops.param_names(cfg.coarse[0]))
@@ -253,14 +254,14 @@ class RenderFn(torch.autograd.Function):
         tf = {k: ops._f32(v) for k, v in zip(ops.param_names(cfg.fine[0]), params[nc:])}
         jitter = ops._f32(rng["jitter"]).reshape(-1) if (train and rng.get("jitter") is not None) else None
         noise_c, noise_sel, noise_f = (ops._f32(rng[k]) for k in ("noise_c", "noise_sel", "noise_f"))
-        net_c, run_c, pad_c = _tc_view(cfg, cfg.coarse, tc)       # what the kernels see (narrow nets: 256-wide shadow)
-        net_f, run_f, pad_f = _tc_view(cfg, cfg.fine, tf)
+        net_c, run_c, pad_c, cache_c = _tc_view(cfg, cfg.coarse, tc, caches[0])    # what the kernels see (narrow nets:
+        net_f, run_f, pad_f, cache_f = _tc_view(cfg, cfg.fine, tf, caches[1])      # the 256-wide shadow)
         # coarse
         # need_grad: decided by render() - grad mode is always off inside Function.forward, and ctx.needs_input_grad
         # stays True for parameters under torch.no_grad(), which would run the stash-writing training kernels in the
         # demo / validation renders
         out_c, saved_c = _branch_fwd(cfg, net_c, run_c, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
-                                     need_grad)
+                                     need_grad, cache_c)
         cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
         rgb_c = torch.empty(B, 3, device=dev)
         lib().call("mcnerf_composite_fwd", _p(out_c), _p(noise_c), _p(rays_d), _p(jitter), None, B,
@@ -271,7 +272,7 @@ class RenderFn(torch.autograd.Function):
         # fine
         if n_rows > 0:
             out_sel, saved_f = _branch_fwd(cfg, net_f, run_f, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx,
-                                           n_rows, n_rows_dev, need_grad)
+                                           n_rows, n_rows_dev, need_grad, cache_f)
         else:
             out_sel, saved_f = torch.empty(0, 4, device=dev), None
         dense = torch.empty(B * cfg.Sf, 4, device=dev)
@@ -332,7 +333,7 @@ class RenderFn(torch.autograd.Function):
         if pad_f is not None:
             gf = pad_f.unpad(gf)
         pg = [gc[k] for k in ops.param_names(cfg.coarse[0])] + [gf[k] for k in ops.param_names(cfg.fine[0])]
-        return (None, None, None, None, None, None, g_d, g_o) + tuple(pg)
+        return (None, None, None, None, None, None, None, g_d, g_o) + tuple(pg)
 
 
 def draw_rng(cfg, B, device, train):
@@ -353,4 +354,5 @@ def render(cfg, params_c, params_f, rays_d, rays_o, train, band_w=None, rng=None
         rng = draw_rng(cfg, rays_d.shape[0], rays_d.device, train)
     plist = [params_c[k] for k in ops.param_names(cfg.coarse[0])] + [params_f[k] for k in ops.param_names(cfg.fine[0])]
     need_grad = torch.is_grad_enabled() and any(t.requires_grad for t in [rays_d, rays_o] + plist)
-    return RenderFn.apply(cfg, train, need_grad, band_w, rng, cap_perm, rays_d, rays_o, *plist)
+    caches = (_owner_cache(params_c), _owner_cache(params_f))
+    return RenderFn.apply(cfg, caches, train, need_grad, band_w, rng, cap_perm, rays_d, rays_o, *plist)

@@ -163,3 +163,22 @@ def test_prefetched_inputs_give_the_same_step():
         for _ in range(3):                                 # steady state: prefetch right after every call
             assert step(host_a, 25, STAGE, 0.5).item() == la
             step.prefetch(host_a)
+
+
+def test_one_graph_follows_the_barf_schedule():
+    """cur_ratio changes every step (ref: main.py:80); the BARF weights it selects are read from a device buffer, so the
+    same captured graph must reproduce the eager step at every ratio - and the epoch number - without a new capture."""
+    from mc_nerf_b200.graph import GraphedTrainStep
+    sp, m, loss_fn = build(3)
+    _, m_e, loss_fn_e = build(3)
+    rng = syn.draw_step_rng(sp, 256, seed=5)
+    batch = tuple(t.to(DEV) for t in syn.make_train_batch(sp, img_id=2, seed=3))
+    ratios = [0.40, 0.45, 0.52, 0.60, 0.75]          # inside the BARF window (20/52 .. 36/52) and past its end
+    with FixedRNG(rng):
+        step = GraphedTrainStep(m, loss_fn)
+        got = [step(batch, 20 + i, STAGE, r).item() for i, r in enumerate(ratios)]
+        assert len(step._graphs) == 1
+        want = [loss_fn_e(m_e(batch, 20 + i, STAGE, r)[0], STAGE).item() for i, r in enumerate(ratios)]
+    assert len(set(round(x, 6) for x in want[:4])) == 4          # the window really moves the loss
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 2e-6 * abs(b), (got, want)
