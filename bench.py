@@ -279,6 +279,7 @@ def run_ours(args):
                                        "gradient all-reduce and RAdam.step launched eagerly") if use_graph else "eager launches"),
                     e2e=dict(value=round(e2e, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                              ms_per_step=round(ms_e2e / args.steps, 3)),
+                    allreduce_collectives_per_step=getattr(sync_grads, "n_collectives", None),
                     gpu_launches=int(launches), host_issue_ms_per_step=round(host_issue_ms, 3), clocks=clocks, roofline=roof, cpu_baseline=cpu,
                     loss=float(last.item()) if torch.is_tensor(last) else float(last))
         print(json.dumps(line), flush=True)

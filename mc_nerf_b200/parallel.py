@@ -49,6 +49,7 @@ class FlatGradAllReduce:
                 p.grad = torch.zeros_like(p)
         grads = [p.grad for p in self.params]
         singles = []
+        self.n_collectives = 0
         for first, count, numel in self._runs(grads):
             g0 = grads[first]
             if count > 1 and g0.is_contiguous():
@@ -56,12 +57,14 @@ class FlatGradAllReduce:
                                                                                 (numel,))
                 dist.all_reduce(alias, op=dist.ReduceOp.SUM)
                 alias.mul_(1.0 / n)
+                self.n_collectives += 1
             else:
                 singles += grads[first:first + count]
         if singles:
             flat = torch.cat([g.reshape(-1) for g in singles])
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
             flat.mul_(1.0 / n)
+            self.n_collectives += 1
             torch._foreach_copy_(singles, [c.view_as(g) for c, g in zip(flat.split([g.numel() for g in singles]), singles)])
 
 
