@@ -279,10 +279,7 @@ int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, const float* b
  * launch - bit 0: data-gradient chain (+ ray gradients), bit 1: weight/bias gradients.  Default 3 (both); the two
  * phases of one backward may be issued as two calls (1 then 2) with identical arguments.  Process-global. */
 int mcnerf_mlp_tc_bwd_phases(int mask);
-/* CTA budgets of the next mcnerf_mlp_tc_bwd calls (0 = one CTA per SM): chain kernel (even: CTA pairs) and
- * weight-gradient kernel.  With the phases above this lets a caller run one network's HBM-bound weight-gradient
- * kernel and the other network's tensor-bound chain kernel concurrently on disjoint SMs (two streams). */
-int mcnerf_mlp_tc_bwd_ctas(int chain_ctas, int wgrad_ctas);
+
 
 /* ------------------------------------------------------------------ tensor-core self test
  * One 128xN tcgen05 tile: D = A B^T (mn_major = 0: A [128,K], B [N,K] bf16, K-major operands) or

@@ -441,17 +441,6 @@ extern "C" size_t mcnerf_mlp_tc_bwd_workspace(const mcnerf_mlp_params* p, int n_
   return stash_tiles(n_rows) * ((size_t)(p->depth + 2) * ACT_BYTES + HEAD_BYTES) + mlp_tc_wgrad_scratch_bytes(WG_MAX_CTAS);
 }
 
-// CTA budgets of the two backward kernels (0 = all SMs): lets the HBM-bound weight-gradient kernel of one network
-// and the tensor-bound chain kernel of the other run side by side on disjoint SMs (two streams).
-namespace mlptc { extern int g_wgrad_cta_limit; }
-static int g_chain_cta_limit = 0;
-extern "C" int mcnerf_mlp_tc_bwd_ctas(int chain_ctas, int wgrad_ctas) {
-  MC_ARG(chain_ctas >= 0 && wgrad_ctas >= 0 && chain_ctas % 2 == 0);
-  g_chain_cta_limit = chain_ctas;
-  g_wgrad_cta_limit = wgrad_ctas;
-  return 0;
-}
-
 // Measurement aid: which phases mcnerf_mlp_tc_bwd launches (bit 0: data-gradient chain, bit 1: weight gradients).
 static int g_bwd_phases = 3;
 extern "C" int mcnerf_mlp_tc_bwd_phases(int mask) {
@@ -504,7 +493,6 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (g_bwd_phases & 1) {
     int grid = n_pairs < sms ? n_pairs : sms;
-    if (g_chain_cta_limit > 0 && grid > g_chain_cta_limit) grid = g_chain_cta_limit;
     grid = (grid + 1) & ~1;                                  // whole clusters of 2
     if (grid > sms) grid = sms & ~1;
     cudaLaunchConfig_t cfg = {};

@@ -12,8 +12,6 @@
 
 namespace mlptc {
 
-int g_wgrad_cta_limit = 0;     // 0: one CTA per SM (see mcnerf_mlp_tc_bwd_ctas)
-
 
 constexpr int WG_ROWS = 64;                          // rows per stage
 constexpr int WG_PLANE = WG_ROWS * 16;               // 1 KB: one k-group plane of a 64-row half tile
@@ -261,7 +259,6 @@ int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const u
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (g_wgrad_cta_limit > 0 && g_wgrad_cta_limit < sms) sms = g_wgrad_cta_limit;   // share the GPU with a concurrent kernel
   WArgs a;
   a.plan = L.wg;
   a.n_slots = D + 2;

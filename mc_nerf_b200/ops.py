@@ -607,19 +607,10 @@ def tc_bwd_workspace(ps, n_rows, device):
 
 
 def mlp_tc_bwd(ps, tcw, tcin, out4, g_out4, stash, workspace, grads_struct, g_rays_o=None, g_rays_d=None,
-               g_x_enc=None, g_dirs_rows=None, phase=3, chain_ctas=0, wgrad_ctas=0):
+               g_x_enc=None, g_dirs_rows=None):
     args = (ctypes.byref(ps), _p(tcw.wb, torch.uint8), _p(tcw.bias), ctypes.byref(tcin),
             _p(out4), _p(g_out4), _p(stash, torch.uint8), _p(workspace, torch.uint8), ctypes.byref(grads_struct),
             _p(g_rays_o), _p(g_rays_d), _p(g_x_enc), _p(g_dirs_rows), _stream())
-    if phase != 3 or chain_ctas or wgrad_ctas:     # one phase on a CTA budget (render.py overlaps two networks)
-        try:
-            lib().cdll.mcnerf_mlp_tc_bwd_phases(phase)
-            lib().cdll.mcnerf_mlp_tc_bwd_ctas(chain_ctas, wgrad_ctas)
-            lib().call("mcnerf_mlp_tc_bwd", *args)
-        finally:
-            lib().cdll.mcnerf_mlp_tc_bwd_phases(3)
-            lib().cdll.mcnerf_mlp_tc_bwd_ctas(0, 0)
-        return
     if lib().profiling():        # per-kernel timing: the chain and the weight-gradient kernels as two calls
         try:
             lib().cdll.mcnerf_mlp_tc_bwd_phases(1)

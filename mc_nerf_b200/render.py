@@ -163,44 +163,6 @@ def _branch_bwd(cfg, net, tensors, grads, rays_o, rays_d, jitter, S, band_w, sel
                _p(g_rays_o), _p(g_rays_d), _stream())
 
 
-def _overlap_chain_ctas():
-    """CTAs given to the coarse network's chain kernel while the fine network's weight-gradient kernel runs on the
-    rest of the GPU (0 = run the four backward kernels one after the other).  env MCNERF_BWD_OVERLAP."""
-    return int(os.environ.get("MCNERF_BWD_OVERLAP", "0"))
-
-
-def _tc_bwd_overlapped(cfg, nets, tensors, grads, rays_o, rays_d, jitter, band_w, sel_idx, n_rows, n_rows_dev,
-                       saved_c, saved_f, out_c, out_sel, g_out_c, g_sel, g_o, g_d, chain_ctas):
-    """Backward of both tensor-core networks with the fine network's weight-gradient kernel (HBM-bound) and the coarse
-    network's chain kernel (tensor-bound) side by side on disjoint SMs:
-        main: chain_f | wgrad_f on (SMs - chain_ctas)       | wgrad_c
-        side:         | chain_c on chain_ctas CTAs (pairs)   |"""
-    (net_c, net_f), (tc, tf), (gc, gf) = nets, tensors, grads
-    B, dev = rays_o.shape[0], rays_o.device
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    ps_f = ops.make_mlp_params(tf, net_f[0], net_f[1], net_f[2], in_ch=cfg.in_ch)
-    ps_c = ops.make_mlp_params(tc, net_c[0], net_c[1], net_c[2], in_ch=cfg.in_ch)
-    gs_f = ops.fill_mlp_struct(MlpGrads(), gf, net_f[0])
-    gs_c = ops.fill_mlp_struct(MlpGrads(), gc, net_c[0])
-    _, tcw_f, tin_f, stash_f = saved_f
-    _, tcw_c, tin_c, stash_c = saved_c
-    ws_f = ops.tc_bwd_workspace(ps_f, n_rows, dev)              # both workspaces belong to the main stream
-    ws_c = ops.tc_bwd_workspace(ps_c, B * cfg.Sc, dev)
-    main = torch.cuda.current_stream()
-    side = _SIDE.get(dev.index)
-    if side is None:
-        side = _SIDE[dev.index] = torch.cuda.Stream(device=dev)
-    ops.mlp_tc_bwd(ps_f, tcw_f, tin_f, out_sel, g_sel, stash_f, ws_f, gs_f, g_rays_o=g_o, g_rays_d=g_d, phase=1)
-    side.wait_stream(main)
-    ops.mlp_tc_bwd(ps_f, tcw_f, tin_f, out_sel, g_sel, stash_f, ws_f, gs_f, g_rays_o=g_o, g_rays_d=g_d, phase=2,
-                   wgrad_ctas=sms - chain_ctas)
-    with torch.cuda.stream(side):
-        ops.mlp_tc_bwd(ps_c, tcw_c, tin_c, out_c, g_out_c, stash_c, ws_c, gs_c, g_rays_o=g_o, g_rays_d=g_d, phase=1,
-                       chain_ctas=chain_ctas)
-    main.wait_stream(side)
-    ops.mlp_tc_bwd(ps_c, tcw_c, tin_c, out_c, g_out_c, stash_c, ws_c, gs_c, g_rays_o=g_o, g_rays_d=g_d, phase=2)
-
-
 def _flat_zero_grads(*nets):
     """zero gradients for every tensor of the given networks as views of ONE zero-filled buffer, in parameter order
     (1 fill instead of 48, and the gradient all-reduce sees a single contiguous run: parallel.FlatGradAllReduce)."""
@@ -306,10 +268,6 @@ class RenderFn(torch.autograd.Function):
         gc, gf = _flat_zero_grads(tc, tf)
         g_o = torch.zeros_like(rays_o)
         g_d = torch.zeros_like(rays_d)
-        chain_ctas = _overlap_chain_ctas()
-        overlap = (chain_ctas > 0 and g_rgb_f is not None and g_rgb_c is not None and n_rows > 0
-                   and saved_c[0] == "tc" and saved_f is not None and saved_f[0] == "tc" and not lib().profiling())
-        g_sel = g_out_c = None
         if g_rgb_f is not None and n_rows > 0:
             cf = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sf, cfg.white_back)
             g_dense = torch.empty_like(dense)
@@ -318,20 +276,15 @@ class RenderFn(torch.autograd.Function):
             g_sel = torch.empty(n_rows, 4, device=dev)
             lib().call("mcnerf_gather_fine", _p(g_dense), _p(sel_idx, torch.int32), n_rows,
                        _p(n_rows_dev, torch.int32), _p(g_sel), _stream())
-            if not overlap:
-                _branch_bwd(cfg, net_f, tf, gf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx, n_rows, n_rows_dev,
-                            saved_f, out_sel, g_sel, g_o, g_d)
+            _branch_bwd(cfg, net_f, tf, gf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx, n_rows, n_rows_dev,
+                        saved_f, out_sel, g_sel, g_o, g_d)
         if g_rgb_c is not None:
             cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
             g_out_c = torch.empty_like(out_c)
             lib().call("mcnerf_composite_bwd", _p(out_c), _p(noise_c), _p(jitter), None, B, ctypes.byref(cc),
                        _p(ops._f32(g_rgb_c)), _p(g_out_c), _stream())
-            if not overlap:
-                _branch_bwd(cfg, net_c, tc, gc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
-                            saved_c, out_c, g_out_c, g_o, g_d)
-        if overlap:
-            _tc_bwd_overlapped(cfg, (net_c, net_f), (tc, tf), (gc, gf), rays_o, rays_d, jitter, band_w, sel_idx, n_rows,
-                               n_rows_dev, saved_c, saved_f, out_c, out_sel, g_out_c, g_sel, g_o, g_d, chain_ctas)
+            _branch_bwd(cfg, net_c, tc, gc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
+                        saved_c, out_c, g_out_c, g_o, g_d)
         if pad_c is not None:
             gc = pad_c.unpad(gc)
         if pad_f is not None:
