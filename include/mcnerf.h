@@ -215,6 +215,10 @@ int mcnerf_sample_pixels_workspace(int n, int batch, size_t* bytes);
 int mcnerf_sample_pixels(int n, int batch, const int64_t* seed, void* workspace, int64_t* out_idx,
                          int32_t* out_idx32, void* stream);
 
+/* dst[0..n) = host_values[0..n), n <= 16, passed by value in a one-block launch: stream-ordered refresh of a few
+ * device-side scalars (mcnerf_sampling.band_w_dev) with no staging buffer for the host to race with. */
+int mcnerf_store_floats(float* dst, const float* host_values, int n, void* stream);
+
 /* dst_j[r*dst_ld_j + c] = src_j[r*src_ld_j + c] for r < rows_j, c < cols_j, j < n_jobs, in one launch per 64 jobs.
  * Used to zero-pad the parameters of a network narrower than 256 into 256-wide shadows for the tensor-core path
  * (zero rows/columns leave the arithmetic of ref: model/net_block.py:67-78 unchanged) and to cut the valid blocks

@@ -293,6 +293,15 @@ __global__ void copy_blocks_k(const __grid_constant__ CopyBlocks a) {
   a.dst[job][(size_t)r * a.dst_ld[job] + c] = a.src[job][(size_t)r * a.src_ld[job] + c];
 }
 
+
+// dst[0..n) = values passed BY VALUE in the launch (n <= 16): a stream-ordered way to refresh a few device-side
+// scalars (the BARF band weights read by captured graphs) without a pinned staging buffer that the host could
+// overwrite before the copy engine reads it.
+struct FloatPack { float v[16]; };
+__global__ void store_floats_k(float* __restrict__ dst, FloatPack p, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = p.v[threadIdx.x];
+}
+
 }  // namespace
 
 extern "C" int mcnerf_rgb_loss(const float* rgb_c, const float* rgb_f, const float* gt, const int32_t* gt_idx,
@@ -433,5 +442,14 @@ extern "C" int mcnerf_copy_blocks(int n_jobs, const float* const* src, float* co
     copy_blocks_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
     MC_LAUNCHED();
   }
+  return 0;
+}
+
+extern "C" int mcnerf_store_floats(float* dst, const float* host_values, int n, void* stream) {
+  MC_ARG(dst && host_values && n >= 1 && n <= 16);
+  FloatPack p;
+  for (int i = 0; i < 16; ++i) p.v[i] = i < n ? host_values[i] : 0.f;
+  store_floats_k<<<1, 32, 0, (cudaStream_t)stream>>>(dst, p, n);
+  MC_LAUNCHED();
   return 0;
 }

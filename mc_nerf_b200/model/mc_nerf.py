@@ -409,7 +409,6 @@ class NeRF_Model(nn.Module):
         caller then calls set_band_weights(step_r) before each training render."""
         if enable:
             self.__dict__["_band_w_dev"] = torch.ones(16, dtype=torch.float32, device=self.device)
-            self.__dict__["_band_w_host"] = torch.ones(16, dtype=torch.float32).pin_memory()
         else:
             self.__dict__["_band_w_dev"] = None
 
@@ -420,8 +419,7 @@ class NeRF_Model(nn.Module):
             return
         emb = self.emmbedding_xyz
         w = ops.barf_band_weights(float(step_r), emb.barf_start, emb.barf_end, emb.n_freqs)
-        self._band_w_host[:len(w)] = torch.tensor(w, dtype=torch.float32)
-        self._band_w_dev.copy_(self._band_w_host, non_blocking=True)
+        ops.store_floats(self._band_w_dev, w)          # values travel in the launch itself: stream-ordered, no staging
 
     def prefetch_weights(self):
         """start deriving the tensor-core weight images on a side stream (see render.prefetch_weights)"""

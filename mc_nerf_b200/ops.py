@@ -65,6 +65,12 @@ def make_composite_cfg(near, far, S, white_back):
     return c
 
 
+def store_floats(dst, values):
+    """dst[:len(values)] = values (<= 16 Python floats), stream-ordered, values passed by value in the launch"""
+    n = len(values)
+    lib().call("mcnerf_store_floats", _p(dst), (ctypes.c_float * n)(*[float(v) for v in values]), n, _stream())
+
+
 def barf_band_weights(step_r, barf_start, barf_end, n_freqs):
     """Host-side evaluation of the 10 BARF window weights (ref: model/net_block.py:26-29).
     Returned as Python floats computed in fp32 the way torch does it."""
