@@ -41,13 +41,15 @@ struct BwdArgs {
 constexpr int BSTAGE = 5;
 struct __align__(16) BwdBars {
   uint64_t w_full[BSTAGE], w_empty[BSTAGE], a_ready[2], acc_full[2];
+  uint64_t st_full[2], st_done[2];      // dY tile of slot t is complete in shared memory / has been copied to the dY stash
   uint32_t tmem_base;
 };
 constexpr int SMEM_BWD = 2 * ACT_BYTES + 2 * HEAD_BYTES + BSTAGE * STAGE_BYTES + 1024 + 256;
-// 18 warps: 16 epilogue warps (TMEM lane quarter = warp % 4, accumulator column quarter = warp / 4) serving both tile
-// slots in turn, 1 weight producer, 1 MMA issuer (leader) / relay (peer).
-constexpr int BWD_THREADS = 576;
-constexpr int BW_PROD = 16, BW_MMA = 17;
+// 20 warps: 16 epilogue warps (TMEM lane quarter = warp % 4, accumulator column quarter = warp / 4) serving both tile
+// slots in turn, 1 weight producer, 1 MMA issuer (leader) / relay (peer), 2 stash warps that copy every finished dY
+// tile shared memory -> HBM while the next job's MMAs read it (as in the forward kernel).
+constexpr int BWD_THREADS = 640;
+constexpr int BW_PROD = 16, BW_MMA = 17, BW_STASH0 = 18;
 
 __constant__ float bC0 = 0.28209479177387814f;
 __constant__ float bC1 = 0.4886025119029199f;
@@ -93,8 +95,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
   uint8_t* wst = small + 2 * HEAD_BYTES;                   // [BSTAGE][STAGE_BYTES]
   float* w2s = reinterpret_cast<float*>(wst + BSTAGE * STAGE_BYTES);     // w_sigma2 [256] (no L1 left: keep it on chip)
   BwdBars* bars = reinterpret_cast<BwdBars*>(w2s + 256);
-  static_assert(sizeof(BwdBars) <= 128, "BwdBars must leave room for the band weights");
-  float* bw_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 128);      // 10 BARF band weights
+  static_assert(sizeof(BwdBars) <= 192, "BwdBars must leave room for the band weights");
+  float* bw_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 192);      // 10 BARF band weights
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.n_rows) : a.n_rows;
   const int n_tiles = (rows + TM - 1) / TM;
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
   if (tid == 0) {
     for (int i = 0; i < BSTAGE; ++i) { tc::mbar_init(&bars->w_full[i], crank == 0 ? 2 : 1); tc::mbar_init(&bars->w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->a_ready[i], 32); /* epilogue warps of both CTAs */ tc::mbar_init(&bars->acc_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->st_full[i], 16); tc::mbar_init(&bars->st_done[i], 2); }
     tc::mbar_init_fence();
   }
   if (warp == BW_MMA) tc::tmem_alloc2(&bars->tmem_base, 512);
@@ -194,13 +197,52 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
           }
         }
     }
+  } else if (warp >= BW_STASH0) {
+    // ---- stash warps: dY tile shared memory -> HBM.  warp-item = (plane p, 32-row block): 512 contiguous bytes on
+    // both sides; the two warps split the 128 items of a tile.
+    const int sw = warp - BW_STASH0;
+    uint32_t spar[2] = {0, 0};
+    for (int it = 0; it < n_iter; ++it) {
+      const int pair = blockIdx.x + it * gridDim.x;
+      for (int jn = 0; jn < n_jobs; ++jn) {
+        const BJob& jb = a.plan.j[jn];
+        if (jb.kind != BK_MASK_STORE) continue;
+        for (int t = 0; t < 2; ++t) {
+          const int tile = 2 * pair + t;
+          tc::mbar_wait(&bars->st_full[t], spar[t]);
+          spar[t] ^= 1;
+          if (tile < n_tiles) {
+            uint8_t* dst = a.dy + ((size_t)tile * a.n_slots + jb.dy_slot) * ACT_BYTES;
+            const uint32_t src = tc::smem_u32(bufX + t * ACT_BYTES);
+#pragma unroll 1
+            for (int i0 = sw * 64; i0 < sw * 64 + 64; i0 += 8) {
+              uint4 v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int item = i0 + u, p = item >> 2, row = (item & 3) * 32 + lane;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+                             : "r"(src + p * PLANE + row * 16));
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int item = i0 + u, p = item >> 2, row = (item & 3) * 32 + lane;
+                *reinterpret_cast<uint4*>(dst + stash_off(row, p, 32)) = v[u];
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bars->st_done[t]);
+        }
+      }
+    }
   } else {
     const int lq = warp & 3, cq = warp >> 2;           // TMEM lane quarter, accumulator column quarter
     const int q = lq * 32 + lane;                      // row in tile == TMEM lane
     const uint32_t bufX0 = tc::smem_u32(bufX), small0 = tc::smem_u32(small);
     const uint32_t a_ready_leader = tc::mapa(tc::smem_u32(&bars->a_ready[0]), 0);
     const float* w2 = w2s;
-    uint32_t par = 0;
+    uint32_t par = 0, stpar = 0, st_pending = 0;       // stash handshake: parity / "a copy of slot t's tile is in flight"
     for (int it = 0; it < n_iter; ++it) {
       const int pair = blockIdx.x + it * gridDim.x;
       // per-slot row state of this thread (row q of slot t): needed by the column-split epilogues below
@@ -297,8 +339,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
           }
           tc::mbar_wait(&bars->acc_full[t], par);
           tc::tcgen05_fence_after();
+          if ((st_pending >> t & 1u) && (jb.kind == BK_MASK_STORE || jb.kind == BK_SIGMA_INJECT || jb.kind == BK_RELOAD_SKIP)) {
+            tc::mbar_wait(&bars->st_done[t], stpar >> t & 1u);     // the stash warps are done reading the tile about to
+            stpar ^= 1u << t;                                      // be overwritten
+            st_pending &= ~(1u << t);
+          }
           if (jb.kind == BK_MASK_STORE) {
-            uint8_t* dyo = dy_tile + (size_t)jb.dy_slot * ACT_BYTES;
             // this warp owns accumulator columns [64 cq, 64 cq + 64), walked in four 16-column halves with the TMEM
             // load of the next half in flight while one is gated, packed, stored (next A operand + dY stash)
             auto half = [&](const uint32_t (&v)[16], int h) {
@@ -311,8 +357,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
                 o.y = relu_gate2(gb, pos0 + j * 8 + 2, __uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
                 o.z = relu_gate2(gb, pos0 + j * 8 + 4, __uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
                 o.w = relu_gate2(gb, pos0 + j * 8 + 6, __uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
-                sts_v4(bufX_t + (kg0 + j) * PLANE + q * 16, o);
-                if (tile_ok) *reinterpret_cast<uint4*>(dyo + stash_off(q, kg0 + j, 32)) = o;
+                sts_v4(bufX_t + (kg0 + j) * PLANE + q * 16, o);       // next A operand; the stash warps copy it to HBM
               }
             };
             uint32_t va[16], vb[16];
@@ -414,6 +459,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
             tc::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_remote(a_ready_leader + t * 8);
+          }
+          if (jb.kind == BK_MASK_STORE) {
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bars->st_full[t]);
+            st_pending |= 1u << t;
           }
         }
         par ^= 1;
