@@ -33,10 +33,11 @@ METRIC = "train_rays_per_sec_64c_128f"
 UNIT = "rays/s"
 N_CAM, IMG, RAYS, SC, SCALE = 110, 800, 4096, 64, 2
 MACS_PER_EVAL = 629248          # GEMM MACs per MLP evaluation (8x256, skip[4], sigma + SH-27 heads)
-# Bytes the weight-gradient kernel must read per MLP evaluation: every (dY, X) operand pair once, bf16, per 128-row
-# tile: layer 0: 64+16 KB; six plain trunk layers: 128 KB each; skip layer: (64+16) + 128; sigma.0, sh.0: 128 each;
-# sh.2, sigma.2: 64 + 8 (head-gradient tile) each  ->  1456 KB / 128 rows
-WGRAD_BYTES_PER_EVAL = 1456 * 1024 // 128
+# Bytes the weight-gradient kernel must read per MLP evaluation: every DISTINCT operand tile once, bf16, per 128-row
+# tile: ten dY tiles and ten activation tiles of 64 KB, the encoding tile (16 KB) and the head-gradient tile (8 KB)
+# = 1304 KB / 128 rows.  (Its 13 jobs fetch 1456 KB: dY of the skip layer, the last trunk activation, the encoding and
+# the head tile are each used by two jobs - the second fetch is an L2 hit when the jobs run in step.)  DESIGN.md §3.4
+WGRAD_BYTES_PER_EVAL = 1304 * 1024 // 128
 STAGE, RATIO = "GLOBAL_OPTIM_EPOCH", 0.5
 
 

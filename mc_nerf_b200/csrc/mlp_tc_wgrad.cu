@@ -8,6 +8,8 @@
 //   warps 2-5: epilogue - TMEM -> per-CTA partial in a scratch buffer; a second small kernel sums the partials into
 //              the fp32 parameter gradients (deterministic, no fp32 atomics) and column-sums dY for the biases.
 // HBM-bound by construction (64 KB of operands per 2 x 4 MMAs): see DESIGN.md for the roofline.
+#include <math.h>
+#include <stdlib.h>
 #include "mlp_tc.cuh"
 
 namespace mlptc {
@@ -265,15 +267,19 @@ int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const u
   a.stash = stash; a.stash_enc = stash_enc; a.dy = dy; a.dy_head = dy_head;
   a.n_rows = n_rows; a.n_rows_dev = n_rows_dev;
   a.scratch = scratch;
-  // CTAs per job: every job streams n_tiles x 2 stages of (32 + N/8) KB, a CTA's time is its job's stage size x its share
-  // of the tiles, and the kernel ends with the slowest job.  Greedy makespan minimisation: start with one CTA per job
-  // and keep giving the next CTA to the job with the most bytes per CTA (8x256 net on 148 SMs: within 2 % of the
-  // mean; proportional rounding had left sigma.2 with 6 CTAs, 15 % over the mean, and a tail the HBM pipe idled in).
+  // CTAs per job.  Every job streams n_tiles x 2 stages of (32 + N/8) KB and the kernel ends with the slowest job.
+  // With the HBM pipe saturated a CTA's bandwidth share follows the bytes it keeps in flight (3 stages), so a job's
+  // time per stage lies between "proportional to its stage size" and "the same for every job": weight = stage size
+  // ^ alpha.  Measured (backward, 786 k rows): alpha 1: 2.505 ms, alpha 0.75 / 0.5 / 0.25 / 0: 2.430-2.435 ms = the HBM
+  // floor (chain + 8.6 GB at the copy peak); 0.5 is the default (env MCNERF_WG_ALPHA for measurements).  The counts
+  // are integers: greedy makespan minimisation (start with one CTA per job, give the next CTA to the job with the
+  // largest weight per CTA); proportional rounding had left the sigma.2 job 15 % over the mean.
   const int nj = L.wg.n_jobs;
   MC_ARG(nj <= sms);
   int used = nj, cnt[MAX_STEPS];
   double w[MAX_STEPS];
-  for (int j = 0; j < nj; ++j) { cnt[j] = 1; w[j] = 32 + L.wg.j[j].N / 8; }
+  static const double alpha = getenv("MCNERF_WG_ALPHA") ? atof(getenv("MCNERF_WG_ALPHA")) : 0.5;
+  for (int j = 0; j < nj; ++j) { cnt[j] = 1; w[j] = pow(32 + L.wg.j[j].N / 8, alpha); }
   for (; used < sms; ++used) {
     int best = 0;
     for (int j = 1; j < nj; ++j) if (w[j] / cnt[j] > w[best] / cnt[best]) best = j;
