@@ -128,7 +128,11 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(device))
     from mc_nerf_b200._lib import lib
-    sp, model, loss_fn, opt, batch = build_workload(device, rank, args.precision, args.rays, args.img)
+    strong = args.scaling == "strong" and world > 1
+    rays_rank = args.rays // world if strong else args.rays      # strong: BASELINE configs[2], the 4096-ray batch of ONE
+    sp, model, loss_fn, opt, batch = build_workload(device, 0 if strong else rank, args.precision, rays_rank, args.img)
+    if strong:                                                   # camera split into equal slices, one per rank
+        torch.manual_seed(4242 + rank)                           # same weights / image everywhere, different pixels
     net, sync_grads = model, (lambda: None)
     if world > 1:
         if args.allreduce == "ddp":     # exactly the reference's wrapper (main.py:61)
@@ -196,7 +200,7 @@ def run_ours(args):
     for _ in range(2):
         step(host_batch, True)
     ms_e2e, _ = timed(host_batch, True, args.steps)
-    rays_step = args.rays * world
+    rays_step = rays_rank * world
     value = rays_step * args.steps / (ms / 1e3)
     e2e = rays_step * args.steps / (ms_e2e / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in batch)
@@ -216,7 +220,7 @@ def run_ours(args):
         prof = L.profile_end()
         from mc_nerf_b200 import render
         n_fine = int(render.LAST["n_rows_dev"].item()) if render.LAST.get("n_rows_dev") is not None else render.LAST["n_rows"]
-        evals = args.rays * SC + n_fine
+        evals = rays_rank * SC + n_fine
         mlp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_mlp_")) / 3
         comp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_composite") or k.startswith("mcnerf_sigma2w")) / 3
         peaks = load_peaks()
@@ -254,11 +258,11 @@ def run_ours(args):
                     frac=round(ach / peaks["tensor"], 4), traffic=traffic, traffic_unit="GB", traffic_source=traffic_src,
                     peak_source=peaks["src"],
                     kernel="mcnerf_mlp_* (fwd+bwd, coarse+fine)", kernel_ms_per_step=round(mlp_ms, 3),
-                    mlp_evals_per_step=evals, fine_selected_frac=round(n_fine / (args.rays * SC * SCALE), 4),
+                    mlp_evals_per_step=evals, fine_selected_frac=round(n_fine / (rays_rank * SC * SCALE), 4),
                     kernel_ms_by_name={k: round(v / 3, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:12]})
         # compositing kernels against the HBM roofline (SURVEY §8d algorithmic bytes: 3348 B fwd + 6156 B bwd per ray)
         if comp_ms > 0:
-            gbs = 9504.0 * args.rays / (comp_ms / 1e3) / 1e9
+            gbs = 9504.0 * rays_rank / (comp_ms / 1e3) / 1e9
             roof["compositing"] = dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s",
                                        frac=round(gbs / peaks["hbm"], 4), kernel_ms_per_step=round(comp_ms, 4))
     cpu = None
@@ -267,13 +271,15 @@ def run_ours(args):
     if rank == 0:
         line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
-                    scaling="weak", vs_baseline=None, dtype="bf16" if args.precision == "bf16" else "f32",
+                    scaling="strong" if strong else "weak", vs_baseline=None,
+                    dtype="bf16" if args.precision == "bf16" else "f32",
                     data="synthetic",
                     config=dict(workload="BASELINE configs[1]: 110 cameras, 800x800, 4096 rays/batch/GPU, 64 coarse + 128 "
                                          "fine samples, coarse+fine 8x256 MLPs, GLOBAL_OPTIM stage (fwd+loss+bwd+RAdam)",
-                                rays_per_step_per_gpu=args.rays, img=args.img,
-                                parallelism=(f"dp{world}: one camera's {args.rays}-ray batch per rank, {args.allreduce} NCCL "
-                                             "all-reduce of MLP+camera grads") if world > 1 else "single GPU",
+                                rays_per_step_per_gpu=rays_rank, img=args.img,
+                                parallelism=((f"dp{world}: one camera's {args.rays}-ray batch split into {rays_rank}-ray slices, "
+                                              if strong else f"dp{world}: one camera's {args.rays}-ray batch per rank, ")
+                                             + f"{args.allreduce} NCCL all-reduce of MLP+camera grads") if world > 1 else "single GPU",
                                 l2="per-step working set (activation stash > 3 GB) exceeds the 126 MB L2; no flush needed",
                                 precision=args.precision,
                                 issue=("CUDA-graph replay of forward+loss+backward per step (GraphedTrainStep); "
@@ -344,6 +350,9 @@ def main():
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--allreduce", default="flat", choices=["flat", "ddp"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the reference's DDP semantic): every rank renders its own camera's --rays batch; "
+                         "strong: ONE --rays batch split into equal slices across the ranks (BASELINE configs[2])")
     ap.add_argument("--no-graph", dest="graph", action="store_false", default=os.environ.get("MCNERF_BENCH_GRAPH", "1") != "0",
                     help="issue every step with eager launches instead of replaying the captured CUDA graph")
     args = ap.parse_args()
