@@ -182,3 +182,33 @@ def test_one_graph_follows_the_barf_schedule():
     assert len(set(round(x, 6) for x in want[:4])) == 4          # the window really moves the loss
     for a, b in zip(got, want):
         assert abs(a - b) <= 2e-6 * abs(b), (got, want)
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_short_training_run_learns(graphed):
+    """End-to-end sanity of the whole loop (render -> loss -> backward -> RAdam -> re-packed weights -> render ...):
+    200 steps on a flat-coloured target must cut the rgb loss several-fold, eager and graph-replayed alike."""
+    from mc_nerf_b200.graph import GraphedTrainStep
+    from mc_nerf_b200.model import RAdam
+    sp, m, loss_fn = build(7)
+    sp["pixel_sampler"] = "device"
+    torch.manual_seed(0)
+    gt_img, img_id, iw, ip, ew, ep = syn.make_train_batch(sp, img_id=1, seed=3)
+    gt_img = torch.tensor([0.8, 0.3, 0.1]).expand_as(gt_img).contiguous()          # one colour everywhere
+    batch = tuple(t.to(DEV) for t in (gt_img, img_id, iw, ip, ew, ep))
+    opt = RAdam(list(m.nerf.parameters()), lr=2e-3)
+    step = GraphedTrainStep(m, loss_fn) if graphed else None
+    rgb_losses = []
+    for i in range(200):
+        if graphed:
+            step(batch, 25, STAGE, 0.9)
+        else:
+            opt.zero_grad()
+            loss_dict = m(batch, 25, STAGE, 0.9)[0]
+            loss_fn(loss_dict, STAGE).backward()
+        opt.step()
+        if i % 20 == 0 or i == 199:
+            with torch.no_grad():
+                ld = m(batch, 25, STAGE, 0.9)[0]
+                rgb_losses.append(float(((ld["rgb"][1] - ld["rgb"][2]) ** 2).mean()))
+    assert rgb_losses[-1] < 0.25 * rgb_losses[0], rgb_losses
