@@ -262,9 +262,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_cons
         }
       }
       // ---------------- head backward: eval_sh + sigmoid, builds the [128 x 32] head-gradient tile.
-      // warps 0-3 own the rows of slot 0, warps 4-7 those of slot 1.
-      if (cq < 2) {
-        const int t = cq, tile = 2 * pair + t, row_g = tile * TM + q;
+      // warps 8-11 own the rows of slot 0, warps 12-15 those of slot 1: column quarters 2 and 3 have nothing to do in
+      // the previous iteration's last epilogue (the encoding backward is done by column quarter 0 alone), so this
+      // prologue of the next tiles overlaps it instead of following it (the head tile buffer was last read by the
+      // first job's MMAs).
+      if (cq >= 2) {
+        const int t = cq - 2, tile = 2 * pair + t, row_g = tile * TM + q;
         const bool valid = row_g < rows, tile_ok = tile < n_tiles;
         float hv[32];
 #pragma unroll

@@ -480,10 +480,15 @@ __global__ void __launch_bounds__(TRAIN ? FWD_THREADS_TRAIN : FWD_THREADS, 1) ml
     uint32_t par = 0, stpar = 0;
     for (int it = 0; it < n_iter; ++it) {
       const int pair = blockIdx.x + it * gridDim.x;
-      if (cq < 2) {       // warps 0-3 encode the rows of slot 0, warps 4-7 those of slot 1
-        const int tile = 2 * pair + cq, row_g = tile * TM + q;
+      // Warps 8-11 encode the rows of slot 0, warps 12-15 those of slot 1: these column quarters have nothing to do in
+      // the previous iteration's last epilogue (sh.2 -> out4 is done by column quarter 0 alone), so they run ahead and
+      // the encoding (index -> ray -> sin/cos, ~3 k cycles) overlaps it instead of following it.  The encoding tile
+      // was last read by the skip layer's MMAs, long complete.
+      if (cq >= 2) {
+        const int es = cq - 2;
+        const int tile = 2 * pair + es, row_g = tile * TM + q;
         uint8_t* st_enc = (TRAIN && tile < n_tiles) ? a.stash_enc + (size_t)tile * ENC_BYTES : nullptr;
-        encode_row(a, row_g, tile < n_tiles && row_g < rows, enc0 + cq * ENC_BYTES, q, st_enc, w2s + 264);
+        encode_row(a, row_g, tile < n_tiles && row_g < rows, enc0 + es * ENC_BYTES, q, st_enc, w2s + 264);
       }
       tc::fence_proxy_async();
       tc::tcgen05_fence_before();
