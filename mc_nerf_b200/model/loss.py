@@ -20,7 +20,7 @@ class MC_NeRF_Loss(nn.Module):
         if ("rgb" in loss_dict and "extr" not in loss_dict and epoch_type != "CAM_PARAM_EPOCH"
                 and loss_dict["rgb"][0].is_cuda and loss_dict["rgb"][0].dtype == torch.float32):
             # rendering stages on the GPU: the whole expression below, forward and backward, is one kernel
-            from .. import ops
+            from mc_nerf_b200 import ops
             rgb_c, rgb_f, gt = loss_dict["rgb"]
             px, px_gt = loss_dict["intr"] if "intr" in loss_dict else (None, None)
             return ops.TrainLossFn.apply(rgb_c, rgb_f, gt, px, px_gt, self.img_w, self.img_h, True)

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from .. import ops, render
+from mc_nerf_b200 import ops, render
 from .net_block import CorseFine_NeRF, SinCosEmbedding
 from .net_utils import get_rank
 

@@ -3,7 +3,7 @@ names and checkpoint layout (ref: model/net_block.py), computed by libmcnerf.so 
 import torch
 import torch.nn as nn
 
-from .. import ops
+from mc_nerf_b200 import ops
 
 
 class SinCosEmbedding(nn.Module):

@@ -7,8 +7,8 @@ import torch
 import torch.distributed as dist
 from torch.optim.optimizer import Optimizer
 
-from .. import ops
-from .._lib import lib
+from mc_nerf_b200 import ops
+from mc_nerf_b200._lib import lib
 
 
 def eval_sh(deg, sh, dirs):

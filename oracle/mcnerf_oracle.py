@@ -326,6 +326,24 @@ def train_step(cam, params_c, params_f, cfg, batch, rng, step_r=0.5, stage="GLOB
     return dict(loss=loss.detach(), rgb_c=rgb_c.detach(), rgb_f=rgb_f.detach())
 
 
+def camera_stage_step(cam, cfg, batch):
+    """One CAM_PARAM_EPOCH step (stage 1): model/mc_nerf.py:64-71 + model/loss.py:18-26.  Both calibration point
+    sets are reprojected - the "intr" set through the calibration poses (weights_pose_intr), the "extr" set through
+    the main poses - and the two reprojection losses are summed UN-normalised.  The NeRF is not evaluated.
+    Returns dict(loss, reproj_intr, reproj_extr); gradients are left in .grad of the camera leaves."""
+    _, _, intr_wpts, intr_pts, extr_wpts, extr_pts = batch
+    H, W = cfg["img_h"], cfg["img_w"]
+    K = intrinsics_from_weights(cam["weights_fx"], cam["weights_fy"], cam["weights_ux"], cam["weights_uy"], H, W)
+    pose = se3_to_SE3(cam["weights_pose"])
+    calib_pose = se3_to_SE3(cam["weights_pose_intr"])
+    r_intr = reproject(intr_wpts, K, calib_pose)
+    r_extr = reproject(extr_wpts, K, pose)
+    loss = reproject_loss(r_intr, intr_pts, H, W) + reproject_loss(r_extr, extr_pts, H, W)
+    loss.backward()
+    return dict(loss=loss.detach(), reproj_intr=r_intr.detach(), reproj_extr=r_extr.detach(), K=K.detach(),
+                pose=pose.detach())
+
+
 def cfg_from_sys_param(sp):
     return dict(near=sp["near"], far=sp["far"], Sc=sp["samples"], scale=sp["scale"], n_freqs=sp["emb_freqs_xyz"],
                 white_back=sp["white_back"], sigma_default=sp["sigma_default"], thresh=sp["sample_weight_thresh"],

@@ -9,6 +9,9 @@ path can be fed the identical values.  Outputs:
 
   tests/golden/modules.pt  - per-function in/out pairs (a2-a5, a7, a10-a14 of SURVEY §8a)
   tests/golden/tiny.pt     - a complete tiny train step + test render, all tensors and all gradients
+  tests/golden/cfg2.pt     - BASELINE configs[1], the BENCHED configuration (110 cams, 800x800, 4096 rays, 64+128, 8x256):
+                             renders, loss, camera grads, MLP grad norms + slices + probe dot products
+  tests/golden/cam_stage.pt - CAM_PARAM_EPOCH step (stage 1: reprojection only), every output and gradient
   tests/golden/cfg1.pt     - BASELINE config 1 (110 cams, 100x100, 1024 rays, 64+128, 8x256):
                              outputs, loss, camera grads, per-tensor MLP grad norms + slices.
                              Inputs are regenerated from seeds (checksums stored).
@@ -179,7 +182,7 @@ def make_modules():
     return fx
 
 
-def make_step(name, sp_kw, n_rays, stage, step_r, img_id, full):
+def make_step(name, sp_kw, n_rays, stage, step_r, img_id, full, keep_grads=False):
     sp = syn.make_sys_param(**sp_kw)
     cam_w = syn.init_camera_weights(sp)
     pc = orc.init_mlp_params(sp["coarse_MLP_depth"], sp["coarse_MLP_width"], tuple(sp["coarse_MLP_skip"]), seed=42)
@@ -208,8 +211,61 @@ def make_step(name, sp_kw, n_rays, stage, step_r, img_id, full):
         fx["checksums"] = dict(gt=checksum(batch[0]), noise_f=checksum(rng["noise_f"]), jitter=checksum(rng["jitter"]),
                                rand_idx=checksum(rng["rand_idx"]), w_c0=checksum(pc["xyz_encoding_1.0.weight"]),
                                w_f7=checksum(pf["xyz_encoding_8.0.weight"]), pose_w=checksum(cam_w["weights_pose"]))
+    if keep_grads:
+        fx["_grads"] = grads
     print(f"{name}: reference step {dt:.2f}s loss={float(out['loss']):.6f}")
     return fx
+
+
+PROBES = 8
+
+
+def probe_dots(name_index, g):
+    """Dot products of a gradient tensor with PROBES seeded N(0,1) vectors: a direction-sensitive
+    fingerprint (E[(u.e)^2] = |e|^2 for an error vector e) that stays tiny for the 631 836-parameter networks."""
+    gen = torch.Generator().manual_seed(90000 + name_index)
+    u = torch.randn(PROBES, g.numel(), generator=gen, dtype=torch.float64)
+    return (u @ g.reshape(-1).double()).float()
+
+
+def make_cfg2():
+    """BASELINE configs[1] - the benched configuration: 110 cameras, 800x800, 4096 rays, 64+128, both nets 8x256.
+    Inputs come from seeds (checksums stored); stored: renders, loss, all six camera gradients, and for every MLP
+    tensor its norm, a 64-element slice and PROBES probe dot products."""
+    kw = dict(n_cam=110, img_h=800, img_w=800, batch=4096, samples=64, scale=2, with_images=False)
+    fx = make_step("cfg2", kw, 4096, "GLOBAL_OPTIM_EPOCH", 0.5, 3, False, keep_grads=True)
+    grads = fx.pop("_grads")
+    names = sorted(k for k in grads if k.startswith("nerf."))
+    fx["g_mlp_probe"] = {k: probe_dots(i, grads[k]) for i, k in enumerate(names)}
+    fx["probe_check"] = checksum(torch.randn(4, 7, generator=torch.Generator().manual_seed(90000), dtype=torch.float64))
+    return fx
+
+
+def make_cam_stage():
+    """CAM_PARAM_EPOCH (stage 1, ref model/mc_nerf.py:64-71, loss.py:18-26): reprojection of the calibration points
+    through both pose sets, un-normalised loss, NeRF untouched.  No random draws."""
+    kw = dict(n_cam=5, img_h=10, img_w=12, batch=24, samples=8, scale=2, coarse=(3, 32, (1,)), fine=(4, 64, (2,)))
+    sp = syn.make_sys_param(**kw)
+    cam_w = syn.init_camera_weights(sp)
+    g = torch.Generator().manual_seed(77)
+    cam_w["weights_pose_intr"] = cam_w["weights_pose"] + 0.05 * torch.randn(5, 6, generator=g)
+    pc = orc.init_mlp_params(3, 32, (1,), seed=42)
+    pf = orc.init_mlp_params(4, 64, (2,), seed=43)
+    batch = syn.make_train_batch(sp, img_id=2)
+    m = build_reference(sp, cam_w, pc, pf)
+    loss_fn = MC_NeRF_Loss(sp)
+    loss_dict, intr_show, pose_show, rays_valid = m(batch, 3, "CAM_PARAM_EPOCH", 0.1)
+    loss = loss_fn(loss_dict, "CAM_PARAM_EPOCH")
+    loss.backward()
+    grads = {k: (p.grad.clone() if p.grad is not None else None) for k, p in m.named_parameters()}
+    assert m.opt_idx == 0 and "rgb" not in loss_dict
+    return dict(name="cam_stage", sp_kw=kw, stage="CAM_PARAM_EPOCH", img_id=2,
+                inputs=dict(cam_w=cam_w, pc=pc, pf=pf, batch=batch),
+                loss=loss.detach().clone(), reproj_intr=loss_dict["intr"][0].detach().clone(),
+                reproj_extr=loss_dict["extr"][0].detach().clone(), K=intr_show[1].clone(), pose=pose_show[1].clone(),
+                rays_valid_d=rays_valid[0].clone(), rays_valid_o=rays_valid[1].clone(),
+                g_cam={k: v for k, v in grads.items() if not k.startswith("nerf.")},
+                g_mlp_none=all(v is None for k, v in grads.items() if k.startswith("nerf.")))
 
 
 def make_radam():
@@ -233,6 +289,13 @@ def make_radam():
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])
+    if only:       # python tests/golden/make_golden.py cfg2 cam_stage : just these fixtures
+        if "cfg2" in only:
+            torch.save(make_cfg2(), os.path.join(HERE, "cfg2.pt"))
+        if "cam_stage" in only:
+            torch.save(make_cam_stage(), os.path.join(HERE, "cam_stage.pt"))
+        sys.exit(0)
     torch.save(make_radam(), os.path.join(HERE, "radam.pt"))
     torch.save(make_modules(), os.path.join(HERE, "modules.pt"))
     tiny_kw = dict(n_cam=5, img_h=10, img_w=12, batch=24, samples=8, scale=2, coarse=(3, 32, (1,)), fine=(4, 64, (2,)))
@@ -240,5 +303,7 @@ if __name__ == "__main__":
     torch.save(make_step("tiny_ft", tiny_kw, 24, "FINE_TUNE_EPOCH", 0.9, 1, True), os.path.join(HERE, "tiny_ft.pt"))
     cfg1_kw = dict(n_cam=110, img_h=100, img_w=100, batch=1024, samples=64, scale=2)
     torch.save(make_step("cfg1", cfg1_kw, 1024, "GLOBAL_OPTIM_EPOCH", 0.5, 3, False), os.path.join(HERE, "cfg1.pt"))
-    for f in ("modules.pt", "tiny.pt", "tiny_ft.pt", "cfg1.pt"):
+    torch.save(make_cfg2(), os.path.join(HERE, "cfg2.pt"))
+    torch.save(make_cam_stage(), os.path.join(HERE, "cam_stage.pt"))
+    for f in ("modules.pt", "tiny.pt", "tiny_ft.pt", "cfg1.pt", "cfg2.pt", "cam_stage.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
