@@ -295,32 +295,104 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------------------------- reference arm
-def cpu_reference(steps, warmup, rays):
-    """The reference's CPU implementation of the path (oracle port), all host threads, bounded sample."""
+def workload_config(rays_rank, img, world, strong, total_rays):
+    """`config` of the JSON line: names the workload only, identical for the GPU arm and the reference arm."""
+    if world > 1:
+        par = (f"dp{world}: one camera's {total_rays}-ray batch split into {rays_rank}-ray slices" if strong
+               else f"dp{world}: one camera's {total_rays}-ray batch per rank") + ", all-reduce of MLP+camera gradients"
+    else:
+        par = "single device"
+    return dict(workload="BASELINE configs[1]: 110 cameras, 800x800, 4096 rays/batch, 64 coarse + 128 fine samples, "
+                         "coarse+fine 8x256 MLPs, GLOBAL_OPTIM stage, one step = fwd+loss+bwd+RAdam",
+                rays_per_step_per_gpu=rays_rank, img=img, parallelism=par,
+                l2="per-step working set (activation stash > 3 GB) exceeds the 126 MB L2; no flush needed")
+
+
+def reference_modules():
+    """The UNMODIFIED reference (baseline/_ref, installed by baseline/install_ref.py) or None."""
+    try:
+        from baseline import ref_loader
+        if ref_loader.reference_root() is None:
+            return None
+        return ref_loader.import_reference()
+    except Exception as e:      # noqa: BLE001 - an unimportable reference falls back to the port, loudly
+        sys.stderr.write(f"bench.py: reference modules not importable ({e!r}); timing the oracle port instead\n")
+        return None
+
+
+def cpu_reference(steps, warmup, rays, budget_s=None):
+    """The reference's own CPU implementation of one train step, all host threads.
+
+    kind "reference": the unmodified modules from baseline/_ref - MC_Model.forward -> MC_NeRF_Loss -> backward ->
+    RAdam.step exactly as reference main.py:79-85 (incl. its two full-image get_rays, the 110-iteration inverse loop and
+    randperm(H*W)); kind "port": oracle/mcnerf_oracle.py, only when baseline/_ref is absent.
+    Times EXACTLY `steps` steps after `warmup`.  budget_s: if the first warm-up step predicts a longer run, the rays
+    per step are reduced (a bounded sample of the same workload; reported)."""
     from mc_nerf_b200 import synthetic as syn
-    from oracle import mcnerf_oracle as orc
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sp = syn.make_sys_param(n_cam=N_CAM, img_h=IMG, img_w=IMG, batch=rays, samples=SC, scale=SCALE, with_images=False)
-    cfg = orc.cfg_from_sys_param(sp)
-    cam = {k: v.clone().requires_grad_(True) for k, v in syn.init_camera_weights(sp).items()}
-    pc = {k: v.clone().requires_grad_(True) for k, v in orc.init_mlp_params(*cfg["coarse"], seed=42).items()}
-    pf = {k: v.clone().requires_grad_(True) for k, v in orc.init_mlp_params(*cfg["fine"], seed=43).items()}
-    batch = syn.make_train_batch(sp, img_id=3)
+    ref = reference_modules()
+
+    def build(n_rays):
+        sp = syn.make_sys_param(n_cam=N_CAM, img_h=IMG, img_w=IMG, batch=n_rays, samples=SC, scale=SCALE,
+                                with_images=False)
+        batch = syn.make_train_batch(sp, img_id=3)
+        torch.manual_seed(42)
+        if ref is not None:
+            MC_Model, _, MC_NeRF_Loss, _, net_utils = ref
+            m = MC_Model(sp)
+            with torch.no_grad():
+                for k, v in syn.init_camera_weights(sp).items():
+                    getattr(m, k).copy_(v)
+            loss_fn = MC_NeRF_Loss(sp)
+            opt = net_utils.RAdam([p for p in m.parameters()], lr=5e-4, eps=1e-8, weight_decay=4e-4)
+
+            def one(i):
+                opt.zero_grad()
+                loss_dict, _, _, _ = m(batch, 25, STAGE, RATIO)
+                loss = loss_fn(loss_dict, STAGE)
+                loss.backward()
+                opt.step()
+                return float(loss.item())
+            return one
+        from oracle import mcnerf_oracle as orc
+        cfg = orc.cfg_from_sys_param(sp)
+        cam = {k: v.clone().requires_grad_(True) for k, v in syn.init_camera_weights(sp).items()}
+        pc = {k: v.clone().requires_grad_(True) for k, v in orc.init_mlp_params(*cfg["coarse"], seed=42).items()}
+        pf = {k: v.clone().requires_grad_(True) for k, v in orc.init_mlp_params(*cfg["fine"], seed=43).items()}
+
+        def one(i):
+            rng = syn.draw_step_rng(sp, n_rays, seed=100 + i)
+            for d in (cam, pc, pf):
+                for v in d.values():
+                    v.grad = None
+            return float(orc.train_step(cam, pc, pf, cfg, batch, rng, step_r=RATIO, stage=STAGE)["loss"])
+        return one
+
+    one = build(rays)
+    t0 = time.perf_counter()
+    one(0)
+    first = time.perf_counter() - t0
+    if budget_s is not None and first * (steps + warmup) > budget_s and rays > 512:
+        shrink = max(512, int(rays * budget_s / (first * (steps + warmup))) // 512 * 512)
+        sys.stderr.write(f"bench.py: reference step takes {first:.1f} s at {rays} rays; sampling {shrink} rays/step\n")
+        rays = shrink
+        one = build(rays)
+        one(0)
+    for i in range(1, warmup):
+        one(i)
     times = []
-    for i in range(warmup + steps):
-        rng = syn.draw_step_rng(sp, rays, seed=100 + i)
-        for d in (cam, pc, pf):
-            for v in d.values():
-                v.grad = None
+    for i in range(steps):
         t0 = time.perf_counter()
-        orc.train_step(cam, pc, pf, cfg, batch, rng, step_r=RATIO, stage=STAGE)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+        one(warmup + i)
+        times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    return dict(value=round(rays / sec, 2), unit=UNIT, cores=cores, kind="port",
-                sample=f"{steps} train steps (fwd+loss+bwd, no optimiser) of {rays} rays of the same workload "
-                       f"(110 cameras, 800x800, 64+128 samples, 8x256 MLPs), torch CPU fp32 oracle, {cores} threads",
+    kind = "reference" if ref is not None else "port"
+    what = ("unmodified reference modules (baseline/_ref): MC_Model.forward -> MC_NeRF_Loss -> backward -> RAdam.step"
+            if ref is not None else "oracle port (oracle/mcnerf_oracle.py; baseline/_ref absent): fwd+loss+bwd, no optimiser")
+    return dict(value=round(rays / sec, 2), unit=UNIT, cores=cores, kind=kind, rays_per_step=rays,
+                sample=f"{steps} timed train steps (after {warmup} warm-up) of {rays} rays of the same workload "
+                       f"(110 cameras, 800x800, 64+128 samples, 8x256 MLPs), torch CPU fp32, {cores} threads; {what}",
                 sec_per_step=round(sec, 3))
 
 
@@ -328,12 +400,13 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    rays = 1024
-    cpu = cpu_reference(steps=max(1, min(args.steps, 5)), warmup=max(1, min(args.warmup, 1)), rays=rays)
-    line = dict(metric=METRIC, value=cpu["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=round(cpu["sec_per_step"] * 1e3, 1), higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="BASELINE configs[1] (bounded sample: 1024 rays/step of the 4096-ray batch)"),
+    cpu = cpu_reference(steps=args.steps, warmup=max(1, args.warmup), rays=args.rays, budget_s=280.0)
+    cfg = workload_config(args.rays, args.img, 1, False, args.rays)
+    if cpu["rays_per_step"] != args.rays:
+        cfg["bounded_sample"] = f"{cpu['rays_per_step']} rays/step of the {args.rays}-ray batch (CPU time budget)"
+    line = dict(metric=METRIC, value=cpu["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=max(1, args.warmup), ms_per_step=round(cpu["sec_per_step"] * 1e3, 1), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference", config=cfg,
                 cpu_baseline=cpu, e2e=dict(value=cpu["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)

@@ -237,8 +237,42 @@ def make_cfg2():
     grads = fx.pop("_grads")
     names = sorted(k for k in grads if k.startswith("nerf."))
     fx["g_mlp_probe"] = {k: probe_dots(i, grads[k]) for i, k in enumerate(names)}
+    fx["g_mlp_small"] = {k: grads[k].clone() for k in names if grads[k].numel() <= 8192}     # biases, sigma.2, sh.2: in full
     fx["probe_check"] = checksum(torch.randn(4, 7, generator=torch.Generator().manual_seed(90000), dtype=torch.float64))
     return fx
+
+
+def make_cfg2_bf16emu():
+    """The benched configuration through the ORACLE with the tcgen05 path's rounding points emulated
+    (tests/bf16_emu.py): what a correct bf16-in / fp32-accumulate implementation must produce, to which the kernels
+    are compared tightly.  (Against the fp32 reference some gradients are ill-conditioned at random init - the coarse
+    sigma head: the colours along a ray are nearly constant, so d rgb / d sigma is a small difference of large terms -
+    and no bf16 forward can reproduce them to better than tens of percent; the emulation shows exactly that.)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bf16_emu
+    kw = dict(n_cam=110, img_h=800, img_w=800, batch=4096, samples=64, scale=2, with_images=False)
+    sp = syn.make_sys_param(**kw)
+    cfg = orc.cfg_from_sys_param(sp)
+    cam = {k: v.clone().requires_grad_(True) for k, v in syn.init_camera_weights(sp).items()}
+    pc = {k: v.clone().requires_grad_(True) for k, v in orc.init_mlp_params(*cfg["coarse"], seed=42).items()}
+    pf = {k: v.clone().requires_grad_(True) for k, v in orc.init_mlp_params(*cfg["fine"], seed=43).items()}
+    batch = syn.make_train_batch(sp, img_id=3)
+    rng = syn.draw_step_rng(sp, 4096, seed=123)
+    plain = orc.mlp_forward
+    orc.mlp_forward = lambda p, x, d, depth, skips, deg=2: bf16_emu.mlp_forward_bf16emu_trainable(p, x, d, depth, skips)
+    try:
+        out = orc.train_step(cam, pc, pf, cfg, batch, rng, step_r=0.5, stage="GLOBAL_OPTIM_EPOCH")
+    finally:
+        orc.mlp_forward = plain
+    grads = {f"nerf.nerf_coarse.{k}": v.grad for k, v in pc.items()}
+    grads.update({f"nerf.nerf_fine.{k}": v.grad for k, v in pf.items()})
+    names = sorted(grads)
+    return dict(name="cfg2_bf16emu", sp_kw=kw, n_rays=4096, stage="GLOBAL_OPTIM_EPOCH", step_r=0.5, img_id=3,
+                loss=out["loss"], rgb_c=out["rgb_c"], rgb_f=out["rgb_f"],
+                g_cam={k: v.grad.clone() for k, v in cam.items()},
+                g_mlp_norm={k: float(grads[k].norm()) for k in names},
+                g_mlp_probe={k: probe_dots(i, grads[k]) for i, k in enumerate(names)},
+                g_mlp_small={k: grads[k].clone() for k in names if grads[k].numel() <= 8192})
 
 
 def make_cam_stage():
@@ -293,6 +327,8 @@ if __name__ == "__main__":
     if only:       # python tests/golden/make_golden.py cfg2 cam_stage : just these fixtures
         if "cfg2" in only:
             torch.save(make_cfg2(), os.path.join(HERE, "cfg2.pt"))
+        if "cfg2_bf16emu" in only:
+            torch.save(make_cfg2_bf16emu(), os.path.join(HERE, "cfg2_bf16emu.pt"))
         if "cam_stage" in only:
             torch.save(make_cam_stage(), os.path.join(HERE, "cam_stage.pt"))
         sys.exit(0)
@@ -305,5 +341,6 @@ if __name__ == "__main__":
     torch.save(make_step("cfg1", cfg1_kw, 1024, "GLOBAL_OPTIM_EPOCH", 0.5, 3, False), os.path.join(HERE, "cfg1.pt"))
     torch.save(make_cfg2(), os.path.join(HERE, "cfg2.pt"))
     torch.save(make_cam_stage(), os.path.join(HERE, "cam_stage.pt"))
+    torch.save(make_cfg2_bf16emu(), os.path.join(HERE, "cfg2_bf16emu.pt"))
     for f in ("modules.pt", "tiny.pt", "tiny_ft.pt", "cfg1.pt", "cfg2.pt", "cam_stage.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

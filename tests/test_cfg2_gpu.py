@@ -26,10 +26,17 @@ from tests_checksum import checksum, probe_dots
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-# measured on B200 (round 2) -> thresholds; see the docstring
+# Thresholds = at most 3x the values measured on a B200 in round 2 (gpurun_out/parity_cfg2_*.json, quoted per entry)
 TOL = {
-    "fp32": dict(loss=2e-5, rgb_tol=1e-4, rgb_bad=16, cam=3e-2, mlp_norm=5e-3, mlp_probe=3e-2),
-    "bf16": dict(loss=2e-4, rgb_tol=1e-3, rgb_bad=16, cam=5e-2, mlp_norm=3e-2, mlp_probe=6e-2),
+    # measured: loss 0, rgb max 3.6e-7 (0 rays over), cam 2.6e-5, MLP norm 6.1e-5 / probe 6.8e-4 (coarse sigma head
+    # 1.8e-3), max-abs 2.4e-8
+    "fp32": dict(loss=1e-6, rgb_tol=1e-5, rgb_bad=4, cam=8e-5, mlp_norm=2e-4, mlp_probe=2e-3, mlp_probe_ill=6e-3,
+                 mlp_maxabs=8e-8),
+    # measured: loss < 1e-7, rgb max 1.8e-5 (0 rays over), cam 6.6e-3 (weights_pose), MLP norm 2.8e-3 / probe 5.2e-2
+    # (coarse sigma head 0.41, see ILL-CONDITIONED), max-abs 1.4e-6;
+    # vs the emulated oracle: rgb 4.8e-6, cam 5.7e-4, probe 1.0e-2 (coarse sigma head 6.2e-2)
+    "bf16": dict(loss=2e-5, rgb_tol=6e-5, rgb_bad=4, cam=2e-2, mlp_norm=9e-3, mlp_probe=1.6e-1, mlp_probe_ill=1.2,
+                 mlp_maxabs=5e-6, emu_rgb=1.5e-5, emu_cam=2e-3, emu_probe=1.9e-1),
 }
 
 
@@ -109,16 +116,49 @@ def test_benched_config_train_step_matches_reference(precision):
         rep["mlp_probe"][k] = float((probe_dots(i, g) - fx["g_mlp_probe"][k]).pow(2).mean().sqrt()) / max(n, 1e-12)
         s_ref = fx["g_mlp_slice"][k]
         rep["mlp_slice"][k] = float((g.reshape(-1)[:64].cpu() - s_ref).norm() / s_ref.norm().clamp_min(1e-12))
-    rep["worst"] = dict(cam=max(rep["cam"].values()), mlp_norm=max(rep["mlp_norm"].values()),
-                        mlp_probe=max(rep["mlp_probe"].values()))
+    # north_star states the gradient tolerance as a max-abs error: checked in full on every small tensor
+    # (biases, sigma.2, sh.2) and on the 64-element slices of the large ones
+    rep["mlp_maxabs"] = {k: float((named[k].grad.cpu() - g).abs().max()) for k, g in fx["g_mlp_small"].items()}
+    rep["mlp_maxabs_slice"] = {k: float((named[k].grad.reshape(-1)[:64].cpu() - fx["g_mlp_slice"][k]).abs().max())
+                               for k in names}
+    rep["mlp_absmax_ref"] = {k: float(g.abs().max()) for k, g in fx["g_mlp_small"].items()}
+    ill = [k for k in names if k.startswith("nerf.nerf_coarse.sigma.")]         # see ILL-CONDITIONED below
+    well = [k for k in names if k not in ill]
+    rep["worst"] = dict(cam=max(rep["cam"].values()), mlp_norm=max(rep["mlp_norm"][k] for k in well),
+                        mlp_probe=max(rep["mlp_probe"][k] for k in well),
+                        mlp_probe_ill=max(rep["mlp_probe"][k] for k in ill),
+                        mlp_maxabs=max(list(rep["mlp_maxabs"].values()) + list(rep["mlp_maxabs_slice"].values())))
+    if precision == "bf16":
+        # ... and against the oracle with the path's rounding points emulated (tests/bf16_emu.py): tight everywhere
+        emu = load_golden("cfg2_bf16emu.pt")
+        rep["emu"] = dict(loss=abs(float(loss.detach()) - float(emu["loss"])),
+                          rgb_c=float((loss_dict["rgb"][0].detach().cpu() - emu["rgb_c"]).abs().max()),
+                          rgb_f_q999=float((loss_dict["rgb"][1].detach().cpu() - emu["rgb_f"]).abs().flatten().quantile(0.999)),
+                          cam={k: float((named[k].grad.cpu() - g).norm() / g.norm().clamp_min(1e-12))
+                               for k, g in emu["g_cam"].items()},
+                          mlp_probe={k: float((probe_dots(i, named[k].grad) - emu["g_mlp_probe"][k]).pow(2).mean().sqrt())
+                                     / max(emu["g_mlp_norm"][k], 1e-12) for i, k in enumerate(names)})
+        rep["worst"]["emu_probe"] = max(rep["emu"]["mlp_probe"].values())
+        rep["worst"]["emu_cam"] = max(rep["emu"]["cam"].values())
     _report(f"cfg2_{precision}", rep)
     for key in ("rgb_c", "rgb_f"):
         assert rep[key]["rays_over"] <= tol["rgb_bad"], (key, rep[key])
     for k, v in rep["cam"].items():
         assert v <= tol["cam"], (k, v)
-    for k in names:
+    for k in well:
         assert rep["mlp_norm"][k] <= tol["mlp_norm"], (k, rep["mlp_norm"][k])
         assert rep["mlp_probe"][k] <= tol["mlp_probe"], (k, rep["mlp_probe"][k])
+    # ILL-CONDITIONED at random init: the coarse network's sigma head.  The colours along a coarse ray are nearly
+    # constant, so d rgb / d sigma is a small difference of large terms; its gradient is ~1e-4 of the network's
+    # gradient norm and ANY bf16 forward moves it by tens of percent (the emulated oracle differs from the fp32
+    # reference by the same 0.12-0.37, tests/golden/make_golden.py::make_cfg2_bf16emu).  It is bounded in absolute
+    # terms (north_star's form of the tolerance) and, for bf16, tightly against the emulation.
+    for k in ill:
+        assert rep["mlp_probe"][k] <= tol["mlp_probe_ill"], (k, rep["mlp_probe"][k])
+    assert rep["worst"]["mlp_maxabs"] <= tol["mlp_maxabs"], rep["worst"]
+    if precision == "bf16":
+        assert rep["emu"]["loss"] <= 1e-6 and rep["emu"]["rgb_c"] <= tol["emu_rgb"], rep["emu"]
+        assert rep["worst"]["emu_cam"] <= tol["emu_cam"] and rep["worst"]["emu_probe"] <= tol["emu_probe"], rep["worst"]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -145,10 +185,12 @@ def test_benched_config_test_render_matches_reference(precision):
         err = (a.detach().cpu().reshape(b.shape) - b).abs()
         rep[name] = dict(max=float(err.max()), q999=float(err.flatten().quantile(0.999)), mean=float(err.mean()))
     _report(f"cfg2_test_render_{precision}", rep)
-    lim = dict(fp32=dict(rgb=1e-4, depth=2e-3, opacity=1e-4), bf16=dict(rgb=1e-3, depth=2e-2, opacity=1e-3))[precision]
+    # measured q999: fp32 rgb 2.9e-7 / depth 1.9e-6 / opacity 8.9e-7; bf16 rgb 1.35e-5 / depth 2.5e-5 / opacity 8.9e-7
+    lim = dict(fp32=dict(rgb=1e-6, depth=6e-6, opacity=3e-6), bf16=dict(rgb=4e-5, depth=8e-5, opacity=3e-6))[precision]
     for k in ("rgb", "depth", "opacity"):
         assert rep[k]["q999"] <= lim[k], (k, rep[k])      # 99.9 % of the rays; flipped-gate rays excepted
-        assert rep[k]["mean"] <= lim[k] / 10, (k, rep[k])
+        assert rep[k]["mean"] <= lim[k], (k, rep[k])
+        assert rep[k]["max"] <= 1e-3 if k != "depth" else rep[k]["max"] <= 2e-2, (k, rep[k])
 
 
 def test_tiny_test_render_bf16_matches_reference():
@@ -169,7 +211,8 @@ def test_tiny_test_render_bf16_matches_reference():
     rep = dict(rgb=float((rgb.cpu() - t["rgb"]).abs().max()), depth=float((dep.cpu() - t["depth"]).abs().max()),
                opacity=float((opa.cpu() - t["opacity"]).abs().max()))
     _report("tiny_test_render_bf16", rep)
-    assert rep["rgb"] <= 1e-3 and rep["opacity"] <= 1e-3 and rep["depth"] <= 2e-2, rep
+    # measured: rgb 4.7e-5, depth 9.3e-5, opacity 2.4e-7
+    assert rep["rgb"] <= 1.5e-4 and rep["opacity"] <= 1e-6 and rep["depth"] <= 3e-4, rep
 
 
 def test_camera_stage_step_matches_reference():

@@ -211,7 +211,7 @@ def test_cfg1_train_step_bf16_tensor_core_path():
     print("rgb (max abs err, rays > 1e-3):", stats)
     print("relative errors:", {k: f"{v:.1e}" for k, v in rel.items()})
     for k, v in rel.items():
-        assert v < 0.15, (k, v)
+        assert v < 0.03, (k, v)          # measured on B200: <= 9.5e-3 (coarse sigma head), others <= 7.4e-3
 
 
 def test_demo_mode_renders_from_checkpoint(tmp_path):
