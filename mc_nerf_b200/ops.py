@@ -5,6 +5,7 @@ PyTorch is plumbing here (device memory, streams, autograd bookkeeping); all ari
 happens in the CUDA library.  Nothing in this file computes on the CPU or falls back to torch ops.
 """
 import ctypes
+import os
 
 import torch
 
@@ -617,7 +618,10 @@ def mlp_tc_bwd(ps, tcw, tcin, out4, g_out4, stash, workspace, grads_struct, g_ra
     args = (ctypes.byref(ps), _p(tcw.wb, torch.uint8), _p(tcw.bias), ctypes.byref(tcin),
             _p(out4), _p(g_out4), _p(stash, torch.uint8), _p(workspace, torch.uint8), ctypes.byref(grads_struct),
             _p(g_rays_o), _p(g_rays_d), _p(g_x_enc), _p(g_dirs_rows), _stream())
-    if lib().profiling():        # per-kernel timing: the chain and the weight-gradient kernels as two calls
+    if lib().profiling() and os.environ.get("MCNERF_BWD_FUSED", "0") == "1":
+        lib().call("mcnerf_mlp_tc_bwd", *args, label="mcnerf_mlp_tc_bwd[fused]")     # one launch (mlp_tc_bwd_fused.cu)
+        return
+    if lib().profiling():        # two-kernel mode: the chain and the weight-gradient kernels as two timed calls
         try:
             lib().cdll.mcnerf_mlp_tc_bwd_phases(1)
             lib().call("mcnerf_mlp_tc_bwd", *args, label="mcnerf_mlp_tc_bwd[chain]")

@@ -174,3 +174,34 @@ def test_tc_backward_rays_mode():
     print("vs fp32 oracle  :", {k: f"{v:.1e}" for k, v in errs.items()})
     bad = {k: v for k, v in errs.items() if not v < 0.2}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("depth,skips,M", [(8, (4,), 128 * 37 + 11), (4, (2,), 300), (3, (), 1000)])
+def test_fused_backward_launch_matches_the_two_kernel_path(depth, skips, M, monkeypatch):
+    """MCNERF_BWD_FUSED=1: chain CTA pairs + weight-gradient CTA pairs in ONE launch with an L2 hand-off of the dY
+    tiles (mlp_tc_bwd_fused.cu; experimental, off by default).  Same gradients as the default two-kernel path up to
+    the summation order of the weight-gradient partials; data gradients bit-identical."""
+    ops, p, tensors, ps, tcw = setup(depth, skips)
+    g = torch.Generator().manual_seed(M)
+    xyz = (torch.rand(M, 3, generator=g) - 0.5) * 6
+    xd = orc.sincos_encode(xyz, 10).to(DEV).contiguous()
+    dd = F.normalize(torch.randn(M, 3, generator=g), dim=-1).to(DEV).contiguous()
+    gout = torch.randn(M, 4, generator=g).to(DEV).contiguous()
+    tin = ops.make_tc_input_enc(xd, dd)
+    out = torch.empty(M, 4, device=DEV)
+    stash = ops.tc_stash(ps, M, DEV)
+    ops.mlp_tc_fwd(ps, tcw, tin, out, stash)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MCNERF_BWD_FUSED", mode)
+        grads = {k: torch.zeros_like(v) for k, v in tensors.items()}
+        gs = ops.fill_mlp_struct(ops.MlpGrads(), grads, depth)
+        ws = ops.tc_bwd_workspace(ps, M, DEV)
+        g_x, g_d = torch.zeros(M, 63, device=DEV), torch.zeros(M, 3, device=DEV)
+        ops.mlp_tc_bwd(ps, tcw, tin, out, gout, stash, ws, gs, g_x_enc=g_x, g_dirs_rows=g_d)
+        torch.cuda.synchronize()
+        res[mode] = (grads, g_x, g_d)
+    assert torch.equal(res["0"][1], res["1"][1]) and torch.equal(res["0"][2], res["1"][2])
+    for k in tensors:
+        a, b = res["1"][0][k], res["0"][0][k]
+        assert float((a - b).norm()) <= 2e-4 * float(b.norm()) + 1e-12, (k, rel_err(a, b))
