@@ -11,9 +11,13 @@ reference main.py:79-85 drives it: optimizer.zero_grad -> MC_Model(data, epoch, 
  value : rays/s with the step's inputs already resident in HBM (CUDA-event timed, max over ranks)
  e2e   : the same steps with HOST (pinned) inputs: H2D of the image/calibration tensors and the D2H read of
          the loss are inside the timed region
- N > 1 : one process per GPU (torchrun), each rank renders its own camera's 4096 rays (the reference's DDP
-         semantic: weak scaling) and gradients are all-reduced by NCCL through DistributedDataParallel.
- --impl reference : the CPU oracle port of the reference's path (oracle/), all host threads, bounded sample.
+ N > 1 : one process per GPU (torchrun).  Default = STRONG scaling, BASELINE configs[2] / north_star: ONE 4096-ray batch
+         split into equal ray slices, MLP + camera gradients all-reduced with NCCL (parallel.GradSync: the fine
+         network's flat gradient buffer is reduced on a communication stream inside backward, the rest right after;
+         1/N folded into RAdam).  The WEAK mode (the reference's DDP semantic: every rank its own camera's 4096 rays)
+         is measured in the same run and reported under `other_scaling`.  After the timed steps all ranks are checked
+         to hold bit-identical parameters (`ranks_identical`).
+ --impl reference : the UNMODIFIED reference (baseline/_ref) on the host CPUs, all threads, the same workload.
 """
 import argparse
 import json
@@ -118,50 +122,48 @@ def build_workload(device, rank, precision, rays=RAYS, img=IMG):
     return sp, model, loss_fn, opt, batch
 
 
-def run_ours(args):
-    rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the MC-NeRF hot path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    device = f"cuda:{local}"
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(device))
+def measure(args, strong, rank, world, local, device, full):
+    """Time the train step in one sharding mode.  strong: ONE --rays batch of one camera split into equal ray slices
+    (BASELINE configs[2], north_star); weak: every rank renders its own camera's --rays batch (the reference's DDP
+    semantic, ref: main.py:60-62).  full: also the e2e leg, the per-kernel roofline and the collective's exposed time."""
     from mc_nerf_b200._lib import lib
-    strong = args.scaling == "strong" and world > 1
-    rays_rank = args.rays // world if strong else args.rays      # strong: BASELINE configs[2], the 4096-ray batch of ONE
+    from mc_nerf_b200 import parallel
+    rays_rank = args.rays // world if strong else args.rays
     sp, model, loss_fn, opt, batch = build_workload(device, 0 if strong else rank, args.precision, rays_rank, args.img)
-    if strong:                                                   # camera split into equal slices, one per rank
-        torch.manual_seed(4242 + rank)                           # same weights / image everywhere, different pixels
-    net, sync_grads = model, (lambda: None)
+    if strong:
+        torch.manual_seed(4242 + rank)           # same weights / image everywhere, different pixels per rank
+    parallel.broadcast_parameters(model)         # what DDP does at construction (ref: main.py:61)
+    net, sync = model, None
     if world > 1:
         if args.allreduce == "ddp":     # exactly the reference's wrapper (main.py:61)
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
-        else:                           # one flat-buffer NCCL all-reduce of MLP + camera gradients per step
-            from mc_nerf_b200.parallel import FlatGradAllReduce
-            sync_grads = FlatGradAllReduce(list(model.parameters()))
+        else:                           # all-reduce of the flat gradient buffers overlapped with the backward pass
+            sync = parallel.GradSync(model, overlap=args.allreduce == "overlap").install()
+            opt.grad_scale = 1.0 / world
     dev_batch = tuple(t.to(device) for t in batch)
     host_batch = tuple(t.pin_memory() for t in batch)
 
-    def eager_step(data, read_loss):
+    def eager_step(data, read_loss, do_sync=True):
         opt.zero_grad()
         loss_dict, _, _, _ = net(data, 25, STAGE, RATIO)
         loss = loss_fn(loss_dict, STAGE)
         loss.backward()
-        sync_grads()
+        if sync is not None and do_sync:
+            sync.finish()
         opt.step()
         return loss.item() if read_loss else loss
 
     use_graph = args.graph and not (world > 1 and args.allreduce == "ddp")
-    if use_graph:      # forward + loss + backward replayed from one CUDA graph (mc_nerf_b200/graph.py); the gradient
-        from mc_nerf_b200.graph import GraphedTrainStep          # all-reduce and RAdam.step stay eager launches
+    if use_graph:      # forward + loss + backward (+ the gradient all-reduce) replayed from one CUDA graph
+        from mc_nerf_b200.graph import GraphedTrainStep
         gstep = GraphedTrainStep(model, loss_fn)
+        if sync is not None:
+            gstep.after_backward.append(sync.finish)
 
         def step(data, read_loss):
-            loss = gstep(data, 25, STAGE, RATIO)
+            loss = gstep(data, 25, STAGE, RATIO)      # (`gstep` is rebound below for the exchange-free timing)
             if not data[0].is_cuda:
                 gstep.prefetch(data)          # e2e: the next step's H2D upload overlaps this step's graph
-            sync_grads()
             opt.step()
             return loss.item() if read_loss else loss
     else:
@@ -172,13 +174,13 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(data, read_loss, steps):
+    def timed(fn, data, read_loss, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
         for _ in range(steps):
-            last = step(data, read_loss)
+            last = fn(data, read_loss)
         timed.host_ms = (time.perf_counter() - t0) * 1e3 / steps      # CPU time to ISSUE a step (no sync inside)
         e1.record()
         barrier()
@@ -191,54 +193,96 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step(dev_batch, False)
-    sampler = ClockSampler(local, period=float(os.environ.get('MCNERF_CLOCK_PERIOD', '0.05'))) if rank == 0 and os.environ.get('MCNERF_NO_CLOCKS') is None else None
-    if sampler:
+    sampler = None
+    if full and rank == 0 and os.environ.get("MCNERF_NO_CLOCKS") is None:
+        sampler = ClockSampler(local, period=float(os.environ.get("MCNERF_CLOCK_PERIOD", "0.05")))
         sampler.start()
-    ms, last = timed(dev_batch, False, args.steps)
-    host_issue_ms = timed.host_ms
-    clocks = sampler.stop() if sampler else None
+    ms, last = timed(step, dev_batch, False, args.steps)
+    res = dict(strong=strong, rays_rank=rays_rank, ms=ms, host_issue_ms=timed.host_ms, use_graph=use_graph,
+               clocks=sampler.stop() if sampler else None, loss=float(last.item()) if torch.is_tensor(last) else float(last))
+    rays_step = rays_rank * world
+    res["value"] = rays_step * args.steps / (ms / 1e3)
+    res["ranks_identical"] = parallel.parameters_identical(model) if world > 1 else None
     for _ in range(2):
         step(host_batch, True)
-    ms_e2e, _ = timed(host_batch, True, args.steps)
-    rays_step = rays_rank * world
-    value = rays_step * args.steps / (ms / 1e3)
-    e2e = rays_step * args.steps / (ms_e2e / 1e3)
-    h2d = sum(t.numel() * t.element_size() for t in batch)
+    ms_e2e, _ = timed(step, host_batch, True, args.steps)
+    res["ms_e2e"] = ms_e2e
+    res["e2e"] = rays_step * args.steps / (ms_e2e / 1e3)
+    res["h2d"] = sum(t.numel() * t.element_size() for t in batch)
+    res["collectives_per_step"] = None
+    if sync is not None:
+        sync.n_collectives = 0
+        ms2, _ = timed(step, dev_batch, False, 5)
+        res["collectives_per_step"] = sync.n_collectives / 5
+    if not full:
+        if sync is not None:
+            sync.uninstall()
+        return res
 
-    # per-kernel device time of the dominant kernels (CUDA events on the launching stream), 3 extra steps
-    roof = None
+    # exposed (non-overlapped) time of the gradient exchange: the same graph-replayed steps captured once more WITHOUT
+    # it (ranks then diverge: timing only, done after every parity-relevant measurement)
+    if sync is not None and use_graph:
+        ms_with, _ = timed(step, dev_batch, False, args.steps)
+        sync.uninstall()
+        gstep = GraphedTrainStep(model, loss_fn)          # `step` picks up the new (exchange-free) graph
+        for _ in range(3):
+            step(dev_batch, False)
+        ms_without, _ = timed(step, dev_batch, False, args.steps)
+        res["allreduce_exposed_us"] = round((ms_with - ms_without) / args.steps * 1e3, 1)
+        sync.install()
     L = lib()
-    # (eager launches: the per-kernel events need host-side launches; no graph replay may follow an eager step)
     if rank == 0:
         L.profile_begin()
     n0 = L.launch_count()
     for _ in range(3):                 # every rank steps (the step contains the gradient all-reduce)
         eager_step(dev_batch, False)
     barrier()
-    launches = (L.launch_count() - n0) // 3 * args.steps     # the graph replays exactly the eager step's kernels
+    res["launches"] = (L.launch_count() - n0) // 3 * args.steps     # the graph replays exactly the eager step's kernels
+    res["prof"] = L.profile_end() if rank == 0 else None
     if rank == 0:
-        prof = L.profile_end()
         from mc_nerf_b200 import render
-        n_fine = int(render.LAST["n_rows_dev"].item()) if render.LAST.get("n_rows_dev") is not None else render.LAST["n_rows"]
+        res["n_fine"] = int(render.LAST["n_rows_dev"].item()) if render.LAST.get("n_rows_dev") is not None else render.LAST["n_rows"]
+    if sync is not None:
+        sync.uninstall()
+    return res
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the MC-NeRF hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    scaling = args.scaling or ("strong" if world > 1 else "weak")
+    strong = scaling == "strong" and world > 1
+    other = None
+    if world > 1 and not args.single_mode:        # the other sharding mode rides along as an extra key of the same line
+        other = measure(args, not strong, rank, world, local, device, full=False)
+    m = measure(args, strong, rank, world, local, device, full=True)
+    ms, rays_rank = m["ms"], m["rays_rank"]
+    roof = None
+    if rank == 0:
+        prof, n_fine = m["prof"], m["n_fine"]
         evals = rays_rank * SC + n_fine
         mlp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_mlp_")) / 3
         comp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_composite") or k.startswith("mcnerf_sigma2w")) / 3
         peaks = load_peaks()
         flops = 6.0 * MACS_PER_EVAL * evals          # fwd + dgrad + wgrad
         ach = flops / (mlp_ms / 1e3) / 1e12
-        traffic, traffic_src = None, None
-        try:   # DRAM bytes per MLP evaluation from the committed ncu --set full capture (dram__bytes_read+write)
-            summ = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
-            per_eval = sum(k["dram_bytes_per_eval"] for n, k in summ["kernels"].items() if n != "mlp_tc_fwd_k<0>")   # <0> = inference variant
-            traffic = round(per_eval * evals / 1e9, 3)
-            traffic_src = "GB per step = ncu dram bytes/evaluation (fwd+bwd-chain+wgrad, profiles/r01_ncu_summary.json) x evaluations"
-        except Exception:
-            pass
+        traffic, traffic_src, ncu = None, None, {}
+        for name in ("r02_ncu_summary.json", "r01_ncu_summary.json"):
+            try:   # DRAM bytes per MLP evaluation from the committed ncu --set full capture (dram__bytes_read+write)
+                ncu = json.load(open(os.path.join(ROOT, "profiles", name)))["kernels"]
+                per_eval = sum(k["dram_bytes_per_eval"] for n, k in ncu.items() if n != "mlp_tc_fwd_k<0>")   # <0> = inference variant
+                traffic = round(per_eval * evals / 1e9, 3)
+                traffic_src = f"GB per step = ncu dram bytes/evaluation (fwd+bwd-chain+wgrad, profiles/{name}) x evaluations"
+                break
+            except Exception:
+                continue
         per_kernel = []
-        try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))["kernels"]
-        except Exception:
-            ncu = {}
         for label, ncu_name, bound in (("mcnerf_mlp_tc_fwd", "mlp_tc_fwd_k<1>", "tensor"),
                                        ("mcnerf_mlp_tc_bwd[chain]", "mlp_tc_bwd_k", "tensor"),
                                        ("mcnerf_mlp_tc_bwd[wgrad]", "mlp_tc_wgrad_k", "hbm")):
@@ -260,35 +304,39 @@ def run_ours(args):
                     kernel="mcnerf_mlp_* (fwd+bwd, coarse+fine)", kernel_ms_per_step=round(mlp_ms, 3),
                     mlp_evals_per_step=evals, fine_selected_frac=round(n_fine / (rays_rank * SC * SCALE), 4),
                     kernel_ms_by_name={k: round(v / 3, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:12]})
-        # compositing kernels against the HBM roofline (SURVEY §8d algorithmic bytes: 3348 B fwd + 6156 B bwd per ray)
+        # compositing kernels against the HBM roofline (SURVEY section 8d algorithmic bytes: 3348 B fwd + 6156 B bwd per ray)
         if comp_ms > 0:
             gbs = 9504.0 * rays_rank / (comp_ms / 1e3) / 1e9
             roof["compositing"] = dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s",
                                        frac=round(gbs / peaks["hbm"], 4), kernel_ms_per_step=round(comp_ms, 4))
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference(steps=2, warmup=1, rays=1024)
+        cpu = cpu_reference(steps=2, warmup=1, rays=args.rays)
     if rank == 0:
-        line = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps,
+        def side(r):
+            return dict(scaling="strong" if r["strong"] else "weak", value=round(r["value"], 1), unit=UNIT,
+                        ms_per_step=round(r["ms"] / args.steps, 3), rays_per_step_per_gpu=r["rays_rank"],
+                        e2e=round(r["e2e"], 1), ranks_identical=r["ranks_identical"],
+                        collectives_per_step=r["collectives_per_step"])
+        line = dict(metric=METRIC, value=round(m["value"], 1), unit=UNIT, n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
                     scaling="strong" if strong else "weak", vs_baseline=None,
-                    dtype="bf16" if args.precision == "bf16" else "f32",
-                    data="synthetic",
-                    config=dict(workload="BASELINE configs[1]: 110 cameras, 800x800, 4096 rays/batch/GPU, 64 coarse + 128 "
-                                         "fine samples, coarse+fine 8x256 MLPs, GLOBAL_OPTIM stage (fwd+loss+bwd+RAdam)",
-                                rays_per_step_per_gpu=rays_rank, img=args.img,
-                                parallelism=((f"dp{world}: one camera's {args.rays}-ray batch split into {rays_rank}-ray slices, "
-                                              if strong else f"dp{world}: one camera's {args.rays}-ray batch per rank, ")
-                                             + f"{args.allreduce} NCCL all-reduce of MLP+camera grads") if world > 1 else "single GPU",
-                                l2="per-step working set (activation stash > 3 GB) exceeds the 126 MB L2; no flush needed",
-                                precision=args.precision,
-                                issue=("CUDA-graph replay of forward+loss+backward per step (GraphedTrainStep); "
-                                       "gradient all-reduce and RAdam.step launched eagerly") if use_graph else "eager launches"),
-                    e2e=dict(value=round(e2e, 1), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-                             ms_per_step=round(ms_e2e / args.steps, 3)),
-                    allreduce_collectives_per_step=getattr(sync_grads, "n_collectives", None),
-                    gpu_launches=int(launches), host_issue_ms_per_step=round(host_issue_ms, 3), clocks=clocks, roofline=roof, cpu_baseline=cpu,
-                    loss=float(last.item()) if torch.is_tensor(last) else float(last))
+                    dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
+                    config=workload_config(rays_rank, args.img, world, strong, args.rays),
+                    impl_notes=dict(precision=args.precision,
+                                    issue=("CUDA-graph replay of forward+loss+backward (+ gradient all-reduce) per step "
+                                           "(GraphedTrainStep); RAdam.step launched eagerly") if m["use_graph"] else "eager launches",
+                                    allreduce=(f"{args.allreduce}: fine network's flat gradient buffer all-reduced on a "
+                                               "communication stream inside backward, coarse + camera gradients after it; "
+                                               "1/N folded into RAdam") if world > 1 and args.allreduce != "ddp" else
+                                              ("DistributedDataParallel" if world > 1 else None)),
+                    e2e=dict(value=round(m["e2e"], 1), unit=UNIT, h2d_bytes_per_step=m["h2d"], d2h_bytes_per_step=4,
+                             ms_per_step=round(m["ms_e2e"] / args.steps, 3)),
+                    allreduce_collectives_per_step=m["collectives_per_step"],
+                    allreduce_exposed_us=m.get("allreduce_exposed_us"), ranks_identical=m["ranks_identical"],
+                    other_scaling=side(other) if other else None,
+                    gpu_launches=int(m["launches"]), host_issue_ms_per_step=round(m["host_issue_ms"], 3), clocks=m["clocks"],
+                    roofline=roof, cpu_baseline=cpu, loss=m["loss"])
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -422,10 +470,14 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--allreduce", default="flat", choices=["flat", "ddp"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default, the reference's DDP semantic): every rank renders its own camera's --rays batch; "
-                         "strong: ONE --rays batch split into equal slices across the ranks (BASELINE configs[2])")
+    ap.add_argument("--allreduce", default="overlap", choices=["overlap", "flat", "ddp"],
+                    help="overlap (default): flat-buffer all-reduce on a communication stream inside backward; flat: the "
+                         "same collectives on the main stream; ddp: the reference's DistributedDataParallel wrapper")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="N > 1 default: strong = ONE --rays batch split into equal ray slices across the ranks (BASELINE "
+                         "configs[2], north_star); weak (the reference's DDP semantic): every rank renders its own "
+                         "camera's --rays batch.  The other mode is measured too and reported under `other_scaling`.")
+    ap.add_argument("--single-mode", action="store_true", help="N > 1: measure only the selected scaling mode")
     ap.add_argument("--no-graph", dest="graph", action="store_false", default=os.environ.get("MCNERF_BENCH_GRAPH", "1") != "0",
                     help="issue every step with eager launches instead of replaying the captured CUDA graph")
     args = ap.parse_args()

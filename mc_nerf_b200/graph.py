@@ -32,6 +32,8 @@ class GraphedTrainStep:
     def __init__(self, model, loss_fn, warmup=3):
         self.model, self.loss_fn, self.warmup = model, loss_fn, warmup
         self._graphs = {}
+        self.after_backward = []   # callables run right after loss.backward() INSIDE the captured region (e.g. the join of
+                                   # parallel.GradSync's communication stream + the camera-gradient all-reduce)
         self._staged = None       # (ids of the host tensors, device staging copies, upload-done event)
         self._consumed = None     # event: the last staging -> static copy has been issued on the main stream
         self._copy_stream = None
@@ -60,6 +62,8 @@ class GraphedTrainStep:
         loss_dict, _, _, _ = self.model(static, epoch, epoch_type, ratio)
         loss = self.loss_fn(loss_dict, epoch_type)
         loss.backward()
+        for fn in self.after_backward:
+            fn()
         return loss
 
     def _capture(self, data, key):

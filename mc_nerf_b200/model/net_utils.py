@@ -45,6 +45,8 @@ class RAdam(Optimizer):
         if not 0.0 <= betas[1] < 1.0:
             raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
         self.degenerated_to_sgd = degenerated_to_sgd
+        self.grad_scale = 1.0     # every gradient is multiplied by this inside the update kernel (1 / world size when
+                                  # the data-parallel all-reduce leaves the SUM in .grad: parallel.GradSync)
         if isinstance(params, (list, tuple)) and len(params) > 0 and isinstance(params[0], dict):
             for param in params:
                 if "betas" in param and (param["betas"][0] != betas[0] or param["betas"][1] != betas[1]):
@@ -110,7 +112,7 @@ class RAdam(Optimizer):
                            vp(*[st["exp_avg_sq"].data_ptr() for _, st in items]),
                            (ctypes.c_int64 * n)(*[p.numel() for p, _ in items]),
                            float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
-                           float(group["weight_decay"]), float(step_size), mode, 1.0, stream)
+                           float(group["weight_decay"]), float(step_size), mode, float(self.grad_scale), stream)
                 # the kernel wrote the parameters through raw pointers: bump their version counters as an in-place
                 # torch op would, so that derived caches (the packed bf16 weight images) and autograd notice
                 torch.autograd.graph.increment_version([p for p, _ in items])

@@ -21,6 +21,9 @@ _p, _stream = ops._p, ops._stream
 
 
 LAST = {}      # debug/bench: row counts of the most recent fine pass (device tensor: no sync is forced here)
+GRAD_HOOK = None   # callable(name, flat) or None: called inside RenderFn.backward, on the launching stream, as soon as
+                   # ONE network's gradients ("fine", then "coarse") are final in their flat fp32 buffer - the gradient
+                   # all-reduce of the fine network then overlaps the coarse network's backward (parallel.GradSync)
 
 
 class RenderCfg:
@@ -170,11 +173,12 @@ def _flat_zero_grads(*nets):
     flat = torch.zeros(total, dtype=torch.float32, device=next(iter(nets[0].values())).device)
     outs, off = [], 0
     for tensors in nets:
-        out = {}
+        out, begin = {}, off
         for k, v in tensors.items():
             out[k] = flat[off:off + v.numel()].view_as(v)
             off += v.numel()
         outs.append(out)
+        outs[-1]["__flat__"] = flat[begin:off]
     return outs
 
 
@@ -266,6 +270,7 @@ class RenderFn(torch.autograd.Function):
         tc, tf = ctx.tc, ctx.tf
         (net_c, net_f), (pad_c, pad_f) = ctx.nets, ctx.pads
         gc, gf = _flat_zero_grads(tc, tf)
+        flat_c, flat_f = gc.pop("__flat__"), gf.pop("__flat__")
         g_o = torch.zeros_like(rays_o)
         g_d = torch.zeros_like(rays_d)
         if g_rgb_f is not None and n_rows > 0:
@@ -278,6 +283,8 @@ class RenderFn(torch.autograd.Function):
                        _p(n_rows_dev, torch.int32), _p(g_sel), _stream())
             _branch_bwd(cfg, net_f, tf, gf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx, n_rows, n_rows_dev,
                         saved_f, out_sel, g_sel, g_o, g_d)
+        if GRAD_HOOK is not None and pad_f is None:
+            GRAD_HOOK("fine", flat_f)          # fine gradients are final: their all-reduce overlaps the coarse backward
         if g_rgb_c is not None:
             cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
             g_out_c = torch.empty_like(out_c)
@@ -285,6 +292,8 @@ class RenderFn(torch.autograd.Function):
                        _p(ops._f32(g_rgb_c)), _p(g_out_c), _stream())
             _branch_bwd(cfg, net_c, tc, gc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
                         saved_c, out_c, g_out_c, g_o, g_d)
+        if GRAD_HOOK is not None and pad_c is None:
+            GRAD_HOOK("coarse", flat_c)        # overlaps the camera-model backward that follows
         if pad_c is not None:
             gc = pad_c.unpad(gc)
         if pad_f is not None:
