@@ -342,6 +342,242 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------- other BASELINE configs
+DEMO_METRIC, STRESS_METRIC = "demo_render_rays_per_sec_64c_128f", "train_rays_per_sec_64c_256f"
+DEMO_CHUNK, STRESS_RAYS, STRESS_MICRO, STRESS_SCALE = 65536, 65536, 8, 4
+
+
+def demo_config(img, chunk):
+    return dict(workload="BASELINE configs[3]: --demo render of whole 800x800 test views of the 110-camera rig, inference-only "
+                         "sampling + coarse/fine 8x256 MLPs + compositing (64+128 samples), one step = one view",
+                rays_per_step_per_gpu=img * img, img=img, chunk_rays=chunk, parallelism="single device",
+                l2="every chunk's activations stay on chip; ray / output tensors of a view (26 MB) are streamed once")
+
+
+def stress_config():
+    return dict(workload="BASELINE configs[4]: Room-style stress, 65536 rays per optimiser step x (64 coarse + 256 fine) samples, "
+                         "coarse+fine 8x256 MLPs, GLOBAL_OPTIM stage, one step = fwd+loss+bwd over 8 accumulation "
+                         "micro-batches of 8192 rays + RAdam",
+                rays_per_step_per_gpu=STRESS_RAYS, img=IMG, micro_batches=STRESS_MICRO, parallelism="single device",
+                l2="per-step working set (activation stash > 3 GB per micro-batch) exceeds the 126 MB L2; no flush needed")
+
+
+def run_demo(args):
+    """BASELINE configs[3] through the drop-in API: MC_Model(mode=1)(img_idx) (ref: model/mc_nerf.py:106-122).
+    value: views rendered with rays and outputs resident on the device; e2e: the public call, whose three outputs
+    arrive in pinned host memory (chunk-wise D2H on a side stream, inside the timed region)."""
+    import tempfile
+    from mc_nerf_b200 import synthetic as syn, render
+    from mc_nerf_b200.model import MC_Model
+    from mc_nerf_b200._lib import lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the MC-NeRF hot path has no CPU fallback)")
+    dev = "cuda:0"
+    torch.cuda.set_device(0)
+    kw = dict(n_cam=N_CAM, img_h=args.img, img_w=args.img, batch=DEMO_CHUNK, samples=SC, scale=SCALE, with_images=False)
+    sp = syn.make_sys_param(device=dev, **kw)
+    sp["mlp_precision"] = args.precision
+    torch.manual_seed(42)
+    m = MC_Model(sp).to(dev)
+    with torch.no_grad():
+        for k, v in syn.init_camera_weights(sp).items():
+            getattr(m, k).copy_(v)
+    tmp = tempfile.mkdtemp()
+    m.nerf.weights_pth = tmp
+    m.nerf.save_model(m, 0)
+    sp2 = syn.make_sys_param(device=dev, mode=1, **kw)
+    sp2["mlp_precision"] = args.precision
+    sp2["demo_ckpt"] = m.nerf.file_path
+    demo = MC_Model(sp2).to(dev).eval()
+    n = args.img * args.img
+
+    def view_resident(v):
+        rays_d, rays_o = demo.get_rays(demo.test_pose, v, demo.intr_test_inv.to(dev))
+        outs = []
+        for ii in range(0, n, DEMO_CHUNK):
+            outs.append(demo.nerf(rays_d[ii:ii + DEMO_CHUNK], rays_o[ii:ii + DEMO_CHUNK]))
+        return outs
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn((i + 1) % N_CAM)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            view_resident(i % N_CAM)
+        sampler = ClockSampler(0)
+        sampler.start()
+        ms = timed(view_resident, args.steps)
+        clocks = sampler.stop()
+        for i in range(2):
+            demo(torch.tensor([i]))
+        ms_e2e = timed(lambda v: demo(torch.tensor([v])), args.steps)
+        L = lib()
+        L.profile_begin()
+        n0 = L.launch_count()
+        view_resident(7)
+        torch.cuda.synchronize()
+        evals, fine_rows = 0, []
+        launches = L.launch_count() - n0
+        prof = L.profile_end()
+        # MLP evaluations of one view: coarse grid + the fine samples selected on the device
+        rays_d, rays_o = demo.get_rays(demo.test_pose, 7, demo.intr_test_inv.to(dev))
+        for ii in range(0, n, DEMO_CHUNK):
+            demo.nerf(rays_d[ii:ii + DEMO_CHUNK], rays_o[ii:ii + DEMO_CHUNK])
+            nd = render.LAST.get("n_rows_dev")
+            fine_rows.append(int(nd.item()) if nd is not None else int(render.LAST["n_rows"]))
+        evals = n * SC + sum(fine_rows)
+    peaks = load_peaks()
+    mlp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_mlp_"))
+    ach = 2.0 * MACS_PER_EVAL * evals / (mlp_ms / 1e3) / 1e12
+    roof = dict(bound="tensor", achieved=round(ach, 2), peak=peaks["tensor"], unit="TFLOP/s", frac=round(ach / peaks["tensor"], 4),
+                traffic=None, peak_source=peaks["src"], kernel="mlp_tc_fwd_k<0> (inference variant, coarse+fine)",
+                kernel_ms_per_step=round(mlp_ms, 3), mlp_evals_per_step=evals,
+                fine_selected_frac=round(sum(fine_rows) / (n * SC * SCALE), 4),
+                kernel_ms_by_name={k: round(v, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:8]})
+    cpu = None if args.no_cpu else cpu_reference_demo(steps=1, warmup=1, rays=8192)
+    line = dict(metric=DEMO_METRIC, value=round(n * args.steps / (ms / 1e3), 1), unit=UNIT, n_gpus=1, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
+                config=demo_config(args.img, DEMO_CHUNK),
+                e2e=dict(value=round(n * args.steps / (ms_e2e / 1e3), 1), unit=UNIT, h2d_bytes_per_step=8,
+                         d2h_bytes_per_step=n * 5 * 4, ms_per_step=round(ms_e2e / args.steps, 3)),
+                gpu_launches=int(launches) * args.steps, clocks=clocks, roofline=roof, cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_reference_demo(steps, warmup, rays):
+    """The reference's test render (ref: model/mc_nerf.py:648-680) on the host CPUs, a bounded sample of `rays` rays."""
+    from mc_nerf_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = reference_modules()
+    sp = syn.make_sys_param(n_cam=N_CAM, img_h=IMG, img_w=IMG, batch=rays, samples=SC, scale=SCALE, with_images=False)
+    g = torch.Generator().manual_seed(5)
+    rd = torch.nn.functional.normalize(torch.randn(rays, 3, generator=g), dim=-1)
+    ro = torch.randn(rays, 3, generator=g) * 0.3
+    torch.manual_seed(42)
+    if ref is not None:
+        nerf = ref[1](sp)
+
+        def one():
+            with torch.no_grad():
+                nerf.render_rays_test(rd, ro, nerf.nerf_coarse, nerf.nerf_fine)
+    else:
+        from oracle import mcnerf_oracle as orc
+        cfg = orc.cfg_from_sys_param(sp)
+        pc, pf = orc.init_mlp_params(*cfg["coarse"], seed=42), orc.init_mlp_params(*cfg["fine"], seed=43)
+
+        def one():
+            rng = syn.draw_step_rng(sp, rays, seed=1, train=False)
+            with torch.no_grad():
+                orc.render_rays(pc, pf, cfg, rd, ro, rng, train=False)
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    sec = (time.perf_counter() - t0) / steps
+    return dict(value=round(rays / sec, 2), unit=UNIT, cores=cores, kind="reference" if ref is not None else "port",
+                rays_per_step=rays, sec_per_step=round(sec, 3),
+                sample=f"{steps} timed test renders (after {warmup} warm-up) of {rays} rays (64+128 samples, 8x256 MLPs), torch "
+                       f"CPU fp32, {cores} threads; " + ("unmodified reference NeRF_Model.render_rays_test (baseline/_ref)"
+                                                          if ref is not None else "oracle port"))
+
+
+def run_stress(args):
+    """BASELINE configs[4]: 65536 rays per optimiser step, 64 + 256 samples, as 8 accumulation micro-batches (the
+    activation + gradient stashes of one 65536-ray batch, ~190 GB, exceed the 180 GB of HBM; the reference would need the
+    same accumulation).  With scale 4 the reference's train-only 128-per-ray cap is active (model/mc_nerf.py:630-632)."""
+    from mc_nerf_b200 import synthetic as syn, render
+    from mc_nerf_b200.model import MC_Model, MC_NeRF_Loss, RAdam
+    from mc_nerf_b200._lib import lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the MC-NeRF hot path has no CPU fallback)")
+    dev = "cuda:0"
+    torch.cuda.set_device(0)
+    rays = STRESS_RAYS // STRESS_MICRO
+    sp = syn.make_sys_param(n_cam=N_CAM, img_h=args.img, img_w=args.img, batch=rays, samples=SC, scale=STRESS_SCALE,
+                            device=dev, with_images=False)
+    sp["mlp_precision"] = args.precision
+    sp["pixel_sampler"] = "device"
+    torch.manual_seed(42)
+    model = MC_Model(sp).to(dev)
+    with torch.no_grad():
+        for k, v in syn.init_camera_weights(sp).items():
+            getattr(model, k).copy_(v)
+    loss_fn = MC_NeRF_Loss(sp)
+    opt = RAdam(list(model.parameters()), lr=5e-4, eps=1e-8, weight_decay=4e-4)
+    host = [tuple(t.pin_memory() for t in syn.make_train_batch(sp, img_id=(3 + 7 * i) % N_CAM, seed=11 + i))
+            for i in range(STRESS_MICRO)]
+    devb = [tuple(t.to(dev) for t in b) for b in host]
+
+    def step(batches, read_loss=False, count=False):
+        opt.zero_grad()
+        evals, loss = 0, None
+        for b in batches:
+            loss_dict, _, _, _ = model(b, 25, STAGE, 0.8)
+            loss = loss_fn(loss_dict, STAGE) / STRESS_MICRO
+            loss.backward()
+            if count:      # (one host sync per micro-batch: only in the untimed warm-up)
+                nd = render.LAST.get("n_rows_dev")
+                evals += rays * SC + (int(nd.item()) if nd is not None else int(render.LAST["n_rows"]))
+        opt.step()
+        if read_loss:
+            loss.item()
+        return evals
+
+    def timed(batches, read_loss, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(batches, read_loss)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(max(args.warmup, 3) - 1):
+        step(devb)
+    evals = step(devb, count=True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    ms = timed(devb, False, args.steps)
+    clocks = sampler.stop()
+    step(host, True)
+    ms_e2e = timed(host, True, args.steps)
+    L = lib()
+    L.profile_begin()
+    n0 = L.launch_count()
+    step(devb)
+    torch.cuda.synchronize()
+    launches = L.launch_count() - n0
+    prof = L.profile_end()
+    peaks = load_peaks()
+    mlp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_mlp_"))
+    ach = 6.0 * MACS_PER_EVAL * evals / (mlp_ms / 1e3) / 1e12
+    roof = dict(bound="tensor", achieved=round(ach, 2), peak=peaks["tensor"], unit="TFLOP/s", frac=round(ach / peaks["tensor"], 4),
+                traffic=None, peak_source=peaks["src"], kernel="mcnerf_mlp_* (fwd+bwd, coarse+fine)",
+                kernel_ms_per_step=round(mlp_ms, 3), mlp_evals_per_step=evals,
+                kernel_ms_by_name={k: round(v, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:8]})
+    h2d = sum(t.numel() * t.element_size() for b in host for t in b)
+    line = dict(metric=STRESS_METRIC, value=round(STRESS_RAYS * args.steps / (ms / 1e3), 1), unit=UNIT, n_gpus=1,
+                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 3), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
+                config=stress_config(),
+                e2e=dict(value=round(STRESS_RAYS * args.steps / (ms_e2e / 1e3), 1), unit=UNIT, h2d_bytes_per_step=h2d,
+                         d2h_bytes_per_step=4, ms_per_step=round(ms_e2e / args.steps, 3)),
+                gpu_launches=int(launches) * args.steps, clocks=clocks, roofline=roof, cpu_baseline=None,
+                peak_mem_gb=round(torch.cuda.max_memory_allocated() / 1e9, 1))
+    print(json.dumps(line), flush=True)
+
+
 # --------------------------------------------------------------------------------------------- reference arm
 def workload_config(rays_rank, img, world, strong, total_rays):
     """`config` of the JSON line: names the workload only, identical for the GPU arm and the reference arm."""
@@ -480,9 +716,29 @@ def main():
     ap.add_argument("--single-mode", action="store_true", help="N > 1: measure only the selected scaling mode")
     ap.add_argument("--no-graph", dest="graph", action="store_false", default=os.environ.get("MCNERF_BENCH_GRAPH", "1") != "0",
                     help="issue every step with eager launches instead of replaying the captured CUDA graph")
+    ap.add_argument("--workload", default="train", choices=["train", "demo", "stress"],
+                    help="train (default): BASELINE configs[1]/[2], the headline metric; demo: configs[3], whole-view "
+                         "inference renders; stress: configs[4], 65536 rays x (64+256) samples per optimiser step")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        if args.workload == "demo":
+            rank, _, _ = dist_env()
+            if rank == 0:
+                cpu = cpu_reference_demo(steps=args.steps, warmup=max(1, args.warmup), rays=8192)
+                cfg = demo_config(IMG, DEMO_CHUNK)
+                cfg["bounded_sample"] = "8192 rays per step of the 640000-ray view (CPU time budget)"
+                print(json.dumps(dict(metric=DEMO_METRIC, value=cpu["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                                      warmup=max(1, args.warmup), ms_per_step=round(cpu["sec_per_step"] * 1e3, 1),
+                                      higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                                      impl="reference", config=cfg, cpu_baseline=cpu, gpu_launches=0,
+                                      e2e=dict(value=cpu["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))),
+                      flush=True)
+        else:
+            run_reference(args)
+    elif args.workload == "demo":
+        run_demo(args)
+    elif args.workload == "stress":
+        run_stress(args)
     else:
         run_ours(args)
 

@@ -23,7 +23,7 @@ using namespace mlptc;
 
 size_t mlp_tc_wgrad_scratch_bytes(int n_ctas);
 int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const uint8_t* stash, const uint8_t* stash_enc,
-                        const uint8_t* dy, const uint8_t* dy_head, float* scratch, int n_rows,
+                        const uint8_t* dy, const uint8_t* dy_head, float* scratch, float* bias_part, int n_rows,
                         const int32_t* n_rows_dev, const mcnerf_mlp_grads* g, cudaStream_t st);
 size_t mlp_tc_fused_extra_bytes(int n_rows, int n_slots);
 int mlp_tc_bwd_fused_launch(const mcnerf_mlp_params* p, const PackLayout& L, const BwdArgs& chain, const uint8_t* stash,
@@ -77,11 +77,8 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
   a.sel_idx = in->sample_idx; a.n_rows = in->n_rows; a.n_rows_dev = in->n_rows_dev;
   a.x_enc = in->x_enc; a.ld_enc = in->ld_enc; a.dirs_rows = in->dirs_rows;
   a.g_rays_o = g_rays_o; a.g_rays_d = g_rays_d; a.g_x_enc = g_x_enc; a.g_dirs_rows = g_dirs_rows;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MC_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
-    attr_set = true;
-  }
+  // per device / context attribute: set on every call (cheap), not once per process
+  MC_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
   const int n_tiles = (in->n_rows + TM - 1) / TM;
   const int n_pairs = (n_tiles + 1) / 2;
   int dev = 0, sms = 148;
@@ -118,5 +115,6 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
   // weight gradients (tcgen05, reduction over all rows) and bias gradients (column sums of the dY stash)
   MC_ARG(sms <= WG_MAX_CTAS);
   float* scratch = (float*)(a.dy_head + tiles * HEAD_BYTES);
-  return mlp_tc_wgrad_launch(p, L, stash_act, stash_enc, a.dy, a.dy_head, scratch, in->n_rows, in->n_rows_dev, g, st);
+  float* bias_part = (float*)((uint8_t*)scratch + mlp_tc_wgrad_scratch_bytes(WG_MAX_CTAS));     // [CTA][256], in the extra region
+  return mlp_tc_wgrad_launch(p, L, stash_act, stash_enc, a.dy, a.dy_head, scratch, bias_part, in->n_rows, in->n_rows_dev, g, st);
 }

@@ -766,12 +766,9 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   } else {
     a.stash = nullptr; a.stash_enc = nullptr; a.stash_sh = nullptr; a.stash_bits = nullptr;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
-    MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
-    attr_set = true;
-  }
+  // per device / context attribute: set on every call (cheap), not once per process
+  MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+  MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
   int n_pairs = ((in->n_rows + TM - 1) / TM + 1) / 2;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

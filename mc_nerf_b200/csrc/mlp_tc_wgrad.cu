@@ -30,7 +30,7 @@ struct WArgs {
   const int32_t* n_rows_dev;
   float* scratch;                    // [gridDim.x][2][128][256] fp32 partials
   int cta_begin[MAX_STEPS + 1];
-  float* db[MAX_STEPS];              // bias gradient of each job (bias_mode != 0), accumulated with atomics
+  float* bias_part;                  // [gridDim.x][256] per-CTA column sums (bias gradients), reduced by wgrad_reduce_k
 };
 
 struct __align__(16) WBars {
@@ -168,23 +168,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) mlp_tc_wgrad_k(const __grid_con
         if (++stage == WG_NSTAGE) { stage = 0; par ^= 1; }
       }
     }
+    // per-CTA partial column sums (no atomics: the reduction kernel adds them in a fixed order)
+    float* bpart = a.bias_part + (size_t)blockIdx.x * 256;
     if (bm == 1) {
 #pragma unroll
       for (int pl = 0; pl < 8; ++pl)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float s = warp_sum(acc[pl][j]);
-          if (lane == 0) atomicAdd(a.db[job] + (w4 * 8 + pl) * 8 + j, s);
+          if (lane == 0) bpart[(w4 * 8 + pl) * 8 + j] = s;
         }
     } else if (bm >= 2 && w4 < nb_planes) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float s = warp_sum(acc[0][j]);
-        const int col = (b_plane0 + w4) * 8 + j;          // head-tile column
-        if (lane == 0) {
-          if (bm == 2 && col < 27) atomicAdd(a.db[job] + col, s);
-          if (bm == 3 && col == 31) atomicAdd(a.db[job], s);
-        }
+        if (lane == 0) bpart[(b_plane0 + w4) * 8 + j] = s;          // indexed by head-tile column
       }
     }
     // ---- epilogue proper: lane quarter (warp % 4), both halves
@@ -227,12 +225,25 @@ struct RArgs {
   int cta_begin[MAX_STEPS + 1];
   float* dst[MAX_STEPS];
   int ld[MAX_STEPS];
+  const float* bias_part;            // [CTA][256] partial column sums
+  float* db[MAX_STEPS];              // bias gradient of each job (null: none)
 };
 
 __global__ void __launch_bounds__(256) wgrad_reduce_k(const __grid_constant__ RArgs a) {
   const int job = blockIdx.y;
   const WJob& wj = a.plan.j[job];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // (m, n) of the 256 x N accumulator
+  if (blockIdx.x == 0 && a.db[job]) {
+    // bias gradient of this job: column sums of the dY operand (mode 1), of the head tile's SH columns (2) or its
+    // g_sigma column (3), summed over the job's CTAs in a fixed order
+    const int t = threadIdx.x;
+    const bool mine = wj.bias_mode == 1 || (wj.bias_mode == 2 && t < 27) || (wj.bias_mode == 3 && t == 31);
+    if (mine) {
+      float s = 0.f;
+      for (int p = a.cta_begin[job]; p < a.cta_begin[job + 1]; ++p) s += a.bias_part[(size_t)p * 256 + t];
+      a.db[job][wj.bias_mode == 3 ? 0 : t] += s;
+    }
+  }
   const int N = wj.N;
   if (idx >= 256 * N) return;
   const int m = idx / N, n = idx - m * N;
@@ -255,7 +266,7 @@ using namespace mlptc;
 size_t mlp_tc_wgrad_scratch_bytes(int n_ctas) { return (size_t)n_ctas * 2 * 128 * 256 * sizeof(float); }
 
 int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const uint8_t* stash, const uint8_t* stash_enc,
-                        const uint8_t* dy, const uint8_t* dy_head, float* scratch, int n_rows,
+                        const uint8_t* dy, const uint8_t* dy_head, float* scratch, float* bias_part, int n_rows,
                         const int32_t* n_rows_dev, const mcnerf_mlp_grads* g, cudaStream_t st) {
   const int D = p->depth;
   int dev = 0, sms = 148;
@@ -267,6 +278,7 @@ int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const u
   a.stash = stash; a.stash_enc = stash_enc; a.dy = dy; a.dy_head = dy_head;
   a.n_rows = n_rows; a.n_rows_dev = n_rows_dev;
   a.scratch = scratch;
+  a.bias_part = bias_part;
   // CTAs per job.  Every job streams n_tiles x 2 stages of (32 + N/8) KB and the kernel ends with the slowest job.
   // With the HBM pipe saturated a CTA's bandwidth share follows the bytes it keeps in flight (3 stages), so a job's
   // time per stage lies between "proportional to its stage size" and "the same for every job": weight = stage size
@@ -287,19 +299,17 @@ int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const u
   }
   a.cta_begin[0] = 0;
   for (int j = 0; j < nj; ++j) a.cta_begin[j + 1] = a.cta_begin[j] + cnt[j];
+  float* dbs[MAX_STEPS];
   for (int j = 0; j < nj; ++j) {
     const int which = L.wg.j[j].which;
     float* db = nullptr;
     if (L.wg.j[j].bias_mode == 1) db = which < D ? g->b[which] : (which == D ? g->b_sigma0 : g->b_sh0);
     else if (L.wg.j[j].bias_mode == 2) db = g->b_sh2;
     else if (L.wg.j[j].bias_mode == 3) db = g->b_sigma2;
-    a.db[j] = db;
+    dbs[j] = db;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    MC_CUDA(cudaFuncSetAttribute(mlp_tc_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG));
-    attr_set = true;
-  }
+  // per device / context attribute: set on every call (cheap), not once per process
+  MC_CUDA(cudaFuncSetAttribute(mlp_tc_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WG));
   mlp_tc_wgrad_k<<<used, WG_THREADS, SMEM_WG, st>>>(a);
   MC_LAUNCHED();
 
@@ -319,6 +329,8 @@ int mlp_tc_wgrad_launch(const mcnerf_mlp_params* p, const PackLayout& L, const u
     return g->W_sigma2;
   };
   for (int j = 0; j < nj; ++j) r.dst[j] = wptr(L.wg.j[j].which, &r.ld[j]);
+  r.bias_part = bias_part;
+  for (int j = 0; j < nj; ++j) r.db[j] = dbs[j];
   wgrad_reduce_k<<<dim3(256, nj), 256, 0, st>>>(r);
   MC_LAUNCHED();
 

@@ -124,16 +124,28 @@ class MC_Model(nn.Module):
         return loss_dict, intr_show, pose_show, rays_valid
 
     def _forward_demo(self, *args):
-        """ref: model/mc_nerf.py:106-122.  Chunks stay on the device; one copy to the host per output."""
+        """ref: model/mc_nerf.py:106-122 (chunk loop with three blocking `.cpu()` per chunk).  Here every chunk's three
+        outputs are copied to PINNED host tensors on a side stream while the next chunk renders; one wait at the end.
+        Fresh host tensors per call (main.py:119-120 keeps every view's result until all views are rendered)."""
         img_id = args[0] if len(args) == 1 else args
-        rgbs, depth, opacity = [], [], []
         rays_d, rays_o = self.get_rays(self.test_pose, img_id, self.intr_test_inv.to(self.device))
-        for ii in range(0, rays_d.shape[0], self.batch):
-            r, d, o = self.nerf(rays_d[ii:ii + self.batch], rays_o[ii:ii + self.batch])
-            rgbs.append(r.detach())
-            depth.append(d.detach())
-            opacity.append(o.detach())
-        return torch.cat(rgbs, 0).cpu(), torch.cat(depth, 0).cpu(), torch.cat(opacity, 0).cpu()
+        n = rays_d.shape[0]
+        if not rays_d.is_cuda:
+            raise ops._lib.McnerfError("MC_Model demo mode needs a CUDA device (no CPU fallback)")
+        host = [torch.empty((n, c), dtype=torch.float32, pin_memory=True) for c in (3, 1, 1)]
+        if self.__dict__.get("_d2h_stream") is None:
+            self.__dict__["_d2h_stream"] = torch.cuda.Stream(device=rays_d.device)
+        side, main = self._d2h_stream, torch.cuda.current_stream(rays_d.device)
+        for ii in range(0, n, self.batch):
+            outs = self.nerf(rays_d[ii:ii + self.batch], rays_o[ii:ii + self.batch])
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for h, o in zip(host, outs):
+                    o = o.detach()
+                    h[ii:ii + o.shape[0]].copy_(o, non_blocking=True)
+                    o.record_stream(side)
+        side.synchronize()
+        return host[0], host[1], host[2]
 
     # ------------------------------------------------------------------ rays
     def _cam_index(self, img_id, n_rays=None):
@@ -434,7 +446,12 @@ class NeRF_Model(nn.Module):
             return self._coarse_only(rays_d, rays_o, step_r)
         band_w = self.emmbedding_xyz.band_weights(step_r)
         if band_w is not None and self.__dict__.get("_band_w_dev") is not None:
-            band_w = self._band_w_dev          # device-side weights, filled by set_band_weights(step_r) for this step
+            # device-side weights (CUDA-graph replays follow a moving window).  A captured graph reads whatever
+            # set_band_weights stored before the replay; an EAGER call refreshes the buffer from its own step_r, so
+            # mixing graphed and eager steps on one model can never apply a stale window.
+            if not torch.cuda.is_current_stream_capturing():
+                self.set_band_weights(step_r)
+            band_w = self._band_w_dev
         rgb_c, rgb_f, _, _ = render.render(self.render_cfg, self.nerf_coarse.param_dict(), self.nerf_fine.param_dict(),
                                            rays_d, rays_o, True, band_w, rng, cap_perm)
         return rgb_c, rgb_f

@@ -27,6 +27,10 @@ def _p(t, dtype=torch.float32):
         return None
     if not t.is_cuda:
         raise _lib.McnerfError("libmcnerf kernels need CUDA tensors (no CPU fallback)")
+    if t.device.index != torch._C._cuda_getDevice():
+        # launches go to the CURRENT device's current stream: a tensor of another GPU would be dereferenced there
+        raise _lib.McnerfError(f"tensor on cuda:{t.device.index} but the current device is cuda:{torch._C._cuda_getDevice()}: "
+                               "wrap the call in torch.cuda.device(...)")
     if t.dtype != dtype:
         raise _lib.McnerfError(f"expected {dtype}, got {t.dtype}")
     if not t.is_contiguous():
