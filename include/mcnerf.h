@@ -177,6 +177,35 @@ int mcnerf_sigma2weights(const float* sigma, int sigma_stride, const float* nois
                          int n_rays, const mcnerf_composite_cfg* cfg,
                          float* weights, float* w_max, void* stream);
 
+/* ------------------------------------------------------------------ fused tails + device RNG (a13-a15, perf mode)
+ * ref: model/mc_nerf.py:601 (jitter uniform_), :619/:662/:719 (three torch.randn density-noise draws), :613-621,
+ * :688-701, :705-736.  Noise arguments: an explicit [B,S] tensor (parity mode: the reference's draws replayed), or NULL
+ * with `seed` = two device-side int64 words -> N(0,1) from Philox4x32-10 generated (and, in the backward pass,
+ * re-generated) inside the kernel; both NULL = no noise.  Streams: 1 coarse colour, 2 selection, 3 fine colour, 4 jitter. */
+/* out[i] = N(0,1) (normal != 0) or uniform in (lo, hi) of Philox stream `stream_id`, element i */
+int mcnerf_philox_fill(const int64_t* seed, int stream_id, int64_t n, int normal, float lo, float hi, float* out,
+                       void* stream);
+/* coarse tail: ONE pass over out4 [B,S,4]: rgb [B,3] = noisy compositing (+ white background), w_sel [B,S] = selection
+ * weights from an independent noise draw, *w_max = max(w_sel) folded in atomically (caller zeroes).  S <= 256. */
+int mcnerf_coarse_tail_fwd(const float* out4, const float* noise_rgb, const float* noise_sel, const int64_t* seed,
+                           const float* jitter, int n_rays, const mcnerf_composite_cfg* cfg, float* rgb, float* w_sel,
+                           float* w_max, void* stream);
+/* g_out4 [B,S,4] overwritten (same noise as the forward: noise_rgb, or stream 1 of `seed`) */
+int mcnerf_coarse_tail_bwd(const float* out4, const float* noise_rgb, const int64_t* seed, const float* jitter,
+                           int n_rays, const mcnerf_composite_cfg* cfg, const float* g_rgb, float* g_out4, void* stream);
+/* fine tail: compositing of the fine grid (cfg->S = Sf samples) straight from the COMPACTED rows out_sel of the
+ * selected samples, in the order mcnerf_select_fine emits them (ray r: sel_offsets[r] + rank * scale + j); unselected
+ * samples are (sigma_default, 1, 1, 1).  w_sel [B,Sf/scale], *w_max, thresh as given to mcnerf_select_fine. */
+int mcnerf_fine_tail_fwd(const float* out_sel, const float* w_sel, const float* w_max, float thresh, int scale,
+                         const int32_t* sel_offsets, const float* rays_d, const float* jitter, const float* noise,
+                         const int64_t* seed, int n_rays, const mcnerf_composite_cfg* cfg, float sigma_default,
+                         float* rgb, float* depth /*[B] or NULL*/, float* opacity /*[B] or NULL*/, void* stream);
+/* g_sel: gradients w.r.t. the compacted rows (rows of unselected samples do not exist; rows beyond the count untouched) */
+int mcnerf_fine_tail_bwd(const float* out_sel, const float* w_sel, const float* w_max, float thresh, int scale,
+                         const int32_t* sel_offsets, const float* jitter, const float* noise, const int64_t* seed,
+                         int n_rays, const mcnerf_composite_cfg* cfg, float sigma_default, const float* g_rgb,
+                         float* g_sel, void* stream);
+
 /* ------------------------------------------------------------------ fine-sample selection (a15)
  * ref: model/mc_nerf.py:623-629, 663-667.  keep coarse sample (r,i) iff w[r,i] >= min(thresh, *w_max);
  * emits flat fine indices r*Sf + i*scale + j (ray-major, ascending - the order torch.nonzero gives),

@@ -1,6 +1,7 @@
 // Loss seed (MSE on the two renders) and the fused multi-tensor RAdam update on flat buffers.
 // ref: model/loss.py:33-43 ; model/net_utils.py:10-101.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -162,18 +163,6 @@ train_loss_k(const float* __restrict__ rc, const float* __restrict__ rf, const f
 // keys would give.  Pass 1 keeps the pixels whose random bits fall under a threshold chosen so that
 // batch + 8 sqrt(batch) + 16 are expected (P[fewer than batch] < 1e-12); pass 2 ranks those few thousand candidates
 // (one block, bucket counting sort) and emits the head.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
-  }
-  return c;
-}
-
 __device__ __forceinline__ uint64_t pixel_key(int i, const int64_t* seed, int idx_bits) {
   const uint64_t s0 = (uint64_t)seed[0], s1 = (uint64_t)seed[1];
   const uint4 r = philox4x32_10(make_uint4((uint32_t)i, 0u, (uint32_t)s1, (uint32_t)(s1 >> 32)),

@@ -187,7 +187,9 @@ class MC_Model(nn.Module):
             if ws is None or ws[0] != (n, self.batch):
                 ws = self.__dict__["_pixel_ws"] = ((n, self.batch), ops.sample_pixels_workspace(n, self.batch, self.device))
             if ws[1] is not None:
-                seed = torch.randint(-(1 << 62), 1 << 62, (2,), device=self.device, dtype=torch.int64)
+                seed = ops.draw_seed(self.device)
+                # the same two key words serve the renderer's device-side draws of this step (other Philox streams)
+                self.nerf.__dict__["_step_seed"] = seed
                 return ops.sample_pixels(n, self.batch, seed, ws[1])
         rand_idx = torch.randperm(n, device=self.device)[:self.batch]
         return rand_idx, rand_idx.to(torch.int32)
@@ -452,6 +454,9 @@ class NeRF_Model(nn.Module):
             if not torch.cuda.is_current_stream_capturing():
                 self.set_band_weights(step_r)
             band_w = self._band_w_dev
+        seed = self.__dict__.pop("_step_seed", None)
+        if rng is None:
+            rng = render.draw_rng(self.render_cfg, rays_d.shape[0], rays_d.device, True, seed=seed)
         rgb_c, rgb_f, _, _ = render.render(self.render_cfg, self.nerf_coarse.param_dict(), self.nerf_fine.param_dict(),
                                            rays_d, rays_o, True, band_w, rng, cap_perm)
         return rgb_c, rgb_f
@@ -462,7 +467,7 @@ class NeRF_Model(nn.Module):
         cfg = self.render_cfg
         if (model_coarse.cfg(), model_fine.cfg()) != (cfg.coarse, cfg.fine):
             cfg = render.RenderCfg(cfg.near, cfg.far, cfg.Sc, cfg.scale, cfg.n_freqs, cfg.white_back, cfg.sigma_default,
-                                   cfg.thresh, model_coarse.cfg(), model_fine.cfg(), cfg.precision)
+                                   cfg.thresh, model_coarse.cfg(), model_fine.cfg(), cfg.precision, cfg.device_rng)
         _, rgb_f, depth_f, opa_f = render.render(cfg, model_coarse.param_dict(), model_fine.param_dict(),
                                                  rays_d, rays_o, False, band_w, rng, None)
         return rgb_f, depth_f, opa_f

@@ -424,6 +424,30 @@ def sigma2weights(sigmas, noise, deltas=None, jitter=None, near=0.0, far=1.0, si
     return w
 
 
+def philox_fill(seed, stream_id, n, normal=True, lo=0.0, hi=1.0):
+    """n draws of Philox stream `stream_id` keyed by `seed` (int64 [2] on the device): N(0,1) or uniform(lo, hi)."""
+    out = torch.empty(n, device=seed.device)
+    lib().call("mcnerf_philox_fill", _p(seed, torch.int64), int(stream_id), int(n), int(bool(normal)), float(lo), float(hi),
+               _p(out), _stream())
+    return out
+
+
+def draw_seed(device):
+    """two int64 key words from torch's CUDA generator (torch.manual_seed governs every device-side draw; graph-safe)"""
+    return torch.randint(-(1 << 62), 1 << 62, (2,), device=device, dtype=torch.int64)
+
+
+def coarse_tail_fwd(out_c, noise_rgb, noise_sel, seed, jitter, B, near, far, S, white_back):
+    """-> rgb [B,3], w_sel [B,S], w_max [1].  ref: model/mc_nerf.py:613-621, 719-727."""
+    cfg = make_composite_cfg(near, far, S, white_back)
+    rgb = torch.empty(B, 3, device=out_c.device)
+    w_sel = torch.empty(B, S, device=out_c.device)
+    w_max = torch.zeros(1, device=out_c.device)
+    lib().call("mcnerf_coarse_tail_fwd", _p(out_c), _p(noise_rgb), _p(noise_sel), _p(seed, torch.int64), _p(jitter), B,
+               ctypes.byref(cfg), _p(rgb), _p(w_sel), _p(w_max), _stream())
+    return rgb, w_sel, w_max
+
+
 def select_fine(weights, w_max, scale, thresh):
     """-> (sel_idx int32 [B*Sc*scale] capacity, sel_offsets int32 [B+1], n_sel int32 [1]); no host sync."""
     B, Sc = weights.shape

@@ -30,7 +30,7 @@ class RenderCfg:
     """Static renderer configuration (the sys_param keys NeRF_Model reads, ref: model/mc_nerf.py:547-571)."""
 
     def __init__(self, near, far, Sc, scale, n_freqs, white_back, sigma_default, thresh,
-                 coarse, fine, precision="fp32"):
+                 coarse, fine, precision="fp32", device_rng=False):
         self.near, self.far, self.Sc, self.scale = float(near), float(far), int(Sc), int(scale)
         self.Sf = self.Sc * self.scale
         self.n_freqs, self.white_back = int(n_freqs), bool(white_back)
@@ -38,6 +38,10 @@ class RenderCfg:
         self.coarse, self.fine = coarse, fine            # (depth, width, skips)
         self.in_ch = 3 + 6 * self.n_freqs
         self.precision = precision
+        # True: jitter and the three density-noise draws come from Philox inside the kernels (keyed from torch's CUDA
+        # generator: same distributions as the reference's uniform_/randn draws, not the same values);
+        # False: torch.rand / torch.randn in the reference's order (draw-for-draw replay, tests)
+        self.device_rng = bool(device_rng)
 
     @staticmethod
     def from_sys_param(sp, precision=None):
@@ -46,10 +50,13 @@ class RenderCfg:
         import os
         if precision is None:
             precision = sp.get("mlp_precision", os.environ.get("MCNERF_PRECISION", "bf16"))
+        # `noise_sampler` ("device" | "torch") follows `pixel_sampler` unless given: "device" is the package default
+        device_rng = sp.get("noise_sampler", "torch" if sp.get("pixel_sampler", "device") == "randperm" else "device") \
+            == "device" and str(sp.get("device_type", "cuda")).startswith("cuda")
         return RenderCfg(sp["near"], sp["far"], sp["samples"], sp["scale"], sp["emb_freqs_xyz"], sp["white_back"],
                          sp["sigma_default"], sp["sample_weight_thresh"],
                          (sp["coarse_MLP_depth"], sp["coarse_MLP_width"], tuple(sp["coarse_MLP_skip"])),
-                         (sp["fine_MLP_depth"], sp["fine_MLP_width"], tuple(sp["fine_MLP_skip"])), precision)
+                         (sp["fine_MLP_depth"], sp["fine_MLP_width"], tuple(sp["fine_MLP_skip"])), precision, device_rng)
 
 
 def _owner_cache(params):
@@ -182,16 +189,15 @@ def _flat_zero_grads(*nets):
     return outs
 
 
-def select_and_cap(cfg, out_c, noise_sel, jitter, B, train, cap_perm=None):
-    """Selection weights with their own noise draw, device-side compaction; the reference's train-only
-    128-per-ray cap (model/mc_nerf.py:630-632) is reproduced when it can trigger (Sf > 128)."""
-    dev = out_c.device
-    w_max = torch.zeros(1, device=dev)
-    w_sel = ops.sigma2weights(out_c, noise_sel, jitter=jitter, near=cfg.near, far=cfg.far, sigma_stride=4,
-                              n_rays=B, S=cfg.Sc, w_max=w_max)
+def select_and_cap(cfg, w_sel, w_max, B, train, cap_perm=None):
+    """Device-side compaction of the selected fine samples from the selection weights; the reference's train-only
+    128-per-ray cap (model/mc_nerf.py:630-632) is reproduced when it can trigger (Sf > 128).
+    -> (sel_idx, n_rows capacity, n_rows_dev, sel_offsets or None when the cap reshuffled the rows)"""
+    dev = w_sel.device
     sel_idx, offs, n_sel = ops.select_fine(w_sel, w_max, cfg.scale, cfg.thresh)
     n_rows, n_rows_dev = B * cfg.Sf, n_sel
     if train and cfg.Sf > 128:
+        offs = None                                # capped rows are a random subset: no per-ray structure left
         K = B * 128
         if cap_perm is not None:                   # test hook: an explicit permutation of the n selected samples
             n = int(n_sel.item())                  # (host synchronisation, as in the reference)
@@ -209,7 +215,7 @@ def select_and_cap(cfg, out_c, noise_sel, jitter, B, train, cap_perm=None):
             keys.masked_fill_(torch.arange(sel_idx.shape[0], device=dev, dtype=torch.int32) >= n_sel, 2.0)
             sel_idx = sel_idx[torch.argsort(keys)[:K]].contiguous()
             n_rows, n_rows_dev = K, torch.clamp(n_sel, max=K)
-    return sel_idx, n_rows, n_rows_dev, w_sel
+    return sel_idx, n_rows, n_rows_dev, offs
 
 
 class RenderFn(torch.autograd.Function):
@@ -223,7 +229,9 @@ class RenderFn(torch.autograd.Function):
         tc = {k: ops._f32(v) for k, v in zip(ops.param_names(cfg.coarse[0]), params[:nc])}
         tf = {k: ops._f32(v) for k, v in zip(ops.param_names(cfg.fine[0]), params[nc:])}
         jitter = ops._f32(rng["jitter"]).reshape(-1) if (train and rng.get("jitter") is not None) else None
-        noise_c, noise_sel, noise_f = (ops._f32(rng[k]) for k in ("noise_c", "noise_sel", "noise_f"))
+        seed = rng.get("seed")                     # device RNG mode: noise is generated inside the tail kernels
+        noise_c, noise_sel, noise_f = (ops._f32(rng[k]) if rng.get(k) is not None else None
+                                       for k in ("noise_c", "noise_sel", "noise_f"))
         net_c, run_c, pad_c, cache_c = _tc_view(cfg, cfg.coarse, tc, caches[0])    # what the kernels see (narrow nets:
         net_f, run_f, pad_f, cache_f = _tc_view(cfg, cfg.fine, tf, caches[1])      # the 256-wide shadow)
         # coarse
@@ -232,12 +240,23 @@ class RenderFn(torch.autograd.Function):
         # demo / validation renders
         out_c, saved_c = _branch_fwd(cfg, net_c, run_c, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
                                      need_grad, cache_c)
-        cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
-        rgb_c = torch.empty(B, 3, device=dev)
-        lib().call("mcnerf_composite_fwd", _p(out_c), _p(noise_c), _p(rays_d), _p(jitter), None, B,
-                   ctypes.byref(cc), _p(rgb_c), None, None, None, _stream())
+        fused = cfg.Sc <= 256 and cfg.Sf <= 256 and os.environ.get("MCNERF_FUSED_TAILS", "1") != "0"
+        if fused:     # colour + selection weights + their maximum in one pass over out_c (tails.cu)
+            rgb_c, w_sel, w_max = ops.coarse_tail_fwd(out_c, noise_c, noise_sel, seed, jitter, B, cfg.near, cfg.far,
+                                                      cfg.Sc, cfg.white_back)
+        else:
+            if seed is not None:
+                noise_c = ops.philox_fill(seed, 1, B * cfg.Sc).view(B, cfg.Sc)
+                noise_sel = ops.philox_fill(seed, 2, B * cfg.Sc).view(B, cfg.Sc)
+            cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
+            rgb_c = torch.empty(B, 3, device=dev)
+            lib().call("mcnerf_composite_fwd", _p(out_c), _p(noise_c), _p(rays_d), _p(jitter), None, B,
+                       ctypes.byref(cc), _p(rgb_c), None, None, None, _stream())
+            w_max = torch.zeros(1, device=dev)
+            w_sel = ops.sigma2weights(out_c, noise_sel, jitter=jitter, near=cfg.near, far=cfg.far, sigma_stride=4,
+                                      n_rays=B, S=cfg.Sc, w_max=w_max)
         # selection
-        sel_idx, n_rows, n_rows_dev, _ = select_and_cap(cfg, out_c, noise_sel, jitter, B, train, cap_perm)
+        sel_idx, n_rows, n_rows_dev, offs = select_and_cap(cfg, w_sel, w_max, B, train, cap_perm)
         LAST["n_rows"], LAST["n_rows_dev"] = n_rows, n_rows_dev
         # fine
         if n_rows > 0:
@@ -245,20 +264,30 @@ class RenderFn(torch.autograd.Function):
                                            n_rows, n_rows_dev, need_grad, cache_f)
         else:
             out_sel, saved_f = torch.empty(0, 4, device=dev), None
-        dense = torch.empty(B * cfg.Sf, 4, device=dev)
-        lib().call("mcnerf_scatter_fine", _p(out_sel) if n_rows else None, _p(sel_idx, torch.int32) if n_rows else None,
-                   n_rows, _p(n_rows_dev, torch.int32), B * cfg.Sf, cfg.sigma_default, _p(dense), _stream())
         cf = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sf, cfg.white_back)
         rgb_f = torch.empty(B, 3, device=dev)
         depth_f = torch.empty(B, 1, device=dev)
         opa_f = torch.empty(B, 1, device=dev)
-        lib().call("mcnerf_composite_fwd", _p(dense), _p(noise_f), _p(rays_d), _p(jitter), None, B,
-                   ctypes.byref(cf), _p(rgb_f), _p(depth_f), _p(opa_f), None, _stream())
+        compact = fused and offs is not None and n_rows > 0
+        dense = None
+        if compact:   # compositing straight from the compacted rows: no dense [B,Sf,4] tensor, no scatter
+            lib().call("mcnerf_fine_tail_fwd", _p(out_sel), _p(w_sel), _p(w_max), cfg.thresh, cfg.scale,
+                       _p(offs, torch.int32), _p(rays_d), _p(jitter), _p(noise_f), _p(seed, torch.int64), B,
+                       ctypes.byref(cf), cfg.sigma_default, _p(rgb_f), _p(depth_f), _p(opa_f), _stream())
+        else:
+            if seed is not None and noise_f is None:
+                noise_f = ops.philox_fill(seed, 3, B * cfg.Sf).view(B, cfg.Sf)
+            dense = torch.empty(B * cfg.Sf, 4, device=dev)
+            lib().call("mcnerf_scatter_fine", _p(out_sel) if n_rows else None, _p(sel_idx, torch.int32) if n_rows else None,
+                       n_rows, _p(n_rows_dev, torch.int32), B * cfg.Sf, cfg.sigma_default, _p(dense), _stream())
+            lib().call("mcnerf_composite_fwd", _p(dense), _p(noise_f), _p(rays_d), _p(jitter), None, B,
+                       ctypes.byref(cf), _p(rgb_f), _p(depth_f), _p(opa_f), None, _stream())
         ctx.cfg, ctx.band_w, ctx.n_rows = cfg, band_w, n_rows
         ctx.tc, ctx.tf = run_c, run_f
         ctx.nets, ctx.pads = (net_c, net_f), (pad_c, pad_f)
         ctx.saved = (rays_d, rays_o, jitter, noise_c, noise_f, out_c, saved_c, sel_idx, n_rows_dev, dense, saved_f,
                      out_sel)
+        ctx.tail = (fused, compact, seed, w_sel, w_max, offs)
         ctx.mark_non_differentiable(depth_f, opa_f)
         return rgb_c, rgb_f, depth_f, opa_f
 
@@ -273,14 +302,20 @@ class RenderFn(torch.autograd.Function):
         flat_c, flat_f = gc.pop("__flat__"), gf.pop("__flat__")
         g_o = torch.zeros_like(rays_o)
         g_d = torch.zeros_like(rays_d)
+        fused, compact, seed, w_sel, w_max, offs = ctx.tail
         if g_rgb_f is not None and n_rows > 0:
             cf = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sf, cfg.white_back)
-            g_dense = torch.empty_like(dense)
-            lib().call("mcnerf_composite_bwd", _p(dense), _p(noise_f), _p(jitter), None, B, ctypes.byref(cf),
-                       _p(ops._f32(g_rgb_f)), _p(g_dense), _stream())
             g_sel = torch.empty(n_rows, 4, device=dev)
-            lib().call("mcnerf_gather_fine", _p(g_dense), _p(sel_idx, torch.int32), n_rows,
-                       _p(n_rows_dev, torch.int32), _p(g_sel), _stream())
+            if compact:    # gradients of the compacted rows directly: no dense gradient tensor, no gather
+                lib().call("mcnerf_fine_tail_bwd", _p(out_sel), _p(w_sel), _p(w_max), cfg.thresh, cfg.scale,
+                           _p(offs, torch.int32), _p(jitter), _p(noise_f), _p(seed, torch.int64), B, ctypes.byref(cf),
+                           cfg.sigma_default, _p(ops._f32(g_rgb_f)), _p(g_sel), _stream())
+            else:
+                g_dense = torch.empty_like(dense)
+                lib().call("mcnerf_composite_bwd", _p(dense), _p(noise_f), _p(jitter), None, B, ctypes.byref(cf),
+                           _p(ops._f32(g_rgb_f)), _p(g_dense), _stream())
+                lib().call("mcnerf_gather_fine", _p(g_dense), _p(sel_idx, torch.int32), n_rows,
+                           _p(n_rows_dev, torch.int32), _p(g_sel), _stream())
             _branch_bwd(cfg, net_f, tf, gf, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx, n_rows, n_rows_dev,
                         saved_f, out_sel, g_sel, g_o, g_d)
         if GRAD_HOOK is not None and pad_f is None:
@@ -288,8 +323,14 @@ class RenderFn(torch.autograd.Function):
         if g_rgb_c is not None:
             cc = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sc, cfg.white_back)
             g_out_c = torch.empty_like(out_c)
-            lib().call("mcnerf_composite_bwd", _p(out_c), _p(noise_c), _p(jitter), None, B, ctypes.byref(cc),
-                       _p(ops._f32(g_rgb_c)), _p(g_out_c), _stream())
+            if fused:
+                lib().call("mcnerf_coarse_tail_bwd", _p(out_c), _p(noise_c), _p(seed, torch.int64), _p(jitter), B,
+                           ctypes.byref(cc), _p(ops._f32(g_rgb_c)), _p(g_out_c), _stream())
+            else:
+                if seed is not None and noise_c is None:
+                    noise_c = ops.philox_fill(seed, 1, B * cfg.Sc).view(B, cfg.Sc)
+                lib().call("mcnerf_composite_bwd", _p(out_c), _p(noise_c), _p(jitter), None, B, ctypes.byref(cc),
+                           _p(ops._f32(g_rgb_c)), _p(g_out_c), _stream())
             _branch_bwd(cfg, net_c, tc, gc, rays_o, rays_d, jitter, cfg.Sc, band_w, None, B * cfg.Sc, None,
                         saved_c, out_c, g_out_c, g_o, g_d)
         if GRAD_HOOK is not None and pad_c is None:
@@ -302,10 +343,17 @@ class RenderFn(torch.autograd.Function):
         return (None, None, None, None, None, None, None, g_d, g_o) + tuple(pg)
 
 
-def draw_rng(cfg, B, device, train):
-    """The reference's draws in the reference's order from torch's current generator:
+def draw_rng(cfg, B, device, train, seed=None):
+    """The random inputs of one render.  cfg.device_rng: two key words from torch's generator (or `seed`) - jitter
+    from Philox stream 4, the density noise generated inside the tail kernels.  Otherwise the reference's draws in the
+    reference's order from torch's current generator:
     uniform_[B,1] (train only) -> randn[B,Sc] -> randn[B,Sc] -> randn[B,Sf]."""
     rng = {}
+    if cfg.device_rng and torch.device(device).type == "cuda":
+        rng["seed"] = seed if seed is not None else ops.draw_seed(device)
+        if train:
+            rng["jitter"] = ops.philox_fill(rng["seed"], 4, B, normal=False, lo=0.0, hi=(cfg.far - cfg.near) / cfg.Sc)
+        return rng
     if train:
         rng["jitter"] = torch.empty(B, 1, device=device).uniform_(0.0, (cfg.far - cfg.near) / cfg.Sc)
     rng["noise_c"] = torch.randn((B, cfg.Sc), device=device)

@@ -385,3 +385,40 @@ def sample_pixels(n, batch, seed0, seed1):
     comp = (r << np.uint64(bits)) | i
     order = np.sort(comp)[:min(n, batch)]
     return (order & np.uint64((1 << bits) - 1)).astype(np.int64)
+
+
+# --------------------------------------------------------------------------- device RNG streams (checker of philox.cuh)
+
+
+def philox_stream(n, seed0, seed1, stream_id):
+    """First two Philox4x32-10 output words of elements 0..n-1 of stream `stream_id`: counter
+    (i_lo, stream | i_hi << 8, seed1_lo, seed1_hi), key (seed0_lo, seed0_hi) - mc_nerf_b200/csrc/philox.cuh."""
+    import numpy as np
+    s0, s1 = int(seed0) & 0xFFFFFFFFFFFFFFFF, int(seed1) & 0xFFFFFFFFFFFFFFFF
+    i = np.arange(n, dtype=np.uint64)
+    c0, c1 = i & np.uint64(0xFFFFFFFF), np.uint64(stream_id) | ((i >> np.uint64(32)) << np.uint64(8))
+    c2 = np.full(n, s1 & 0xFFFFFFFF, dtype=np.uint64)
+    c3 = np.full(n, s1 >> 32, dtype=np.uint64)
+    r0, r1, _, _ = _philox4x32_10(c0, c1, c2, c3, s0 & 0xFFFFFFFF, s0 >> 32)
+    return r0.astype(np.uint32), r1.astype(np.uint32)
+
+
+def _u01(x):
+    import numpy as np
+    return (x.astype(np.float32) + np.float32(0.5)) * np.float32(2.3283064365386963e-10)
+
+
+def philox_uniform(n, seed0, seed1, stream_id, lo=0.0, hi=1.0):
+    import numpy as np
+    r0, _ = philox_stream(n, seed0, seed1, stream_id)
+    return np.float32(lo) + np.float32(hi - lo) * _u01(r0)
+
+
+def philox_normal(n, seed0, seed1, stream_id):
+    """N(0,1) by Box-Muller from the first two words (cos branch), as the render kernels draw their density noise in
+    device-RNG mode (the reference draws torch.randn: same distribution, different values)."""
+    import numpy as np
+    r0, r1 = philox_stream(n, seed0, seed1, stream_id)
+    u1 = np.minimum(_u01(r0), np.float32(0.99999994)).astype(np.float64)
+    u2 = _u01(r1).astype(np.float64)
+    return (np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)).astype(np.float32)
