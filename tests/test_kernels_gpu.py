@@ -286,14 +286,22 @@ def test_device_side_sample_cap_keeps_a_uniform_subset():
     noise = torch.randn(B, Sc, generator=g).to(DEV)
     jitter = (torch.rand(B, generator=g) * 0.1).to(DEV)
     out_c = out_c.to(DEV)
-    all_idx, n_all, n_all_dev, _ = render.select_and_cap(cfg, out_c, noise, jitter, B, train=False)
+
+    def weights(o):
+        w_max = torch.zeros(1, device=DEV)
+        w = ops.sigma2weights(o, noise, jitter=jitter, near=1.0, far=8.0, sigma_stride=4, n_rays=B, S=Sc, w_max=w_max)
+        return w, w_max
+
+    from mc_nerf_b200 import ops
+    w_sel, w_max = weights(out_c)
+    all_idx, n_all, n_all_dev, _ = render.select_and_cap(cfg, w_sel, w_max, B, train=False)
     n = int(n_all_dev.item())
     assert n > K and n_all == B * Sc * scale
     pool = all_idx[:n].cpu()
     first_half = 0.0
     draws = []
     for _ in range(6):
-        idx, n_rows, n_dev, _ = render.select_and_cap(cfg, out_c, noise, jitter, B, train=True)
+        idx, n_rows, n_dev, _ = render.select_and_cap(cfg, w_sel, w_max, B, train=True)
         kept = idx[:K].cpu()
         assert n_rows == K and int(n_dev.item()) == K and idx.shape[0] == K
         assert len(torch.unique(kept)) == K and bool(torch.isin(kept, pool).all())
@@ -305,9 +313,10 @@ def test_device_side_sample_cap_keeps_a_uniform_subset():
     sparse = out_c.clone()
     sparse[:, 0] = -30.0
     sparse[::7, 0] = 5.0
-    all2, _, n2_dev, _ = render.select_and_cap(cfg, sparse, noise, jitter, B, train=False)
+    w2, wm2 = weights(sparse)
+    all2, _, n2_dev, _ = render.select_and_cap(cfg, w2, wm2, B, train=False)
     n2 = int(n2_dev.item())
     assert 0 < n2 <= K
-    idx2, n_rows2, n_dev2, _ = render.select_and_cap(cfg, sparse, noise, jitter, B, train=True)
+    idx2, n_rows2, n_dev2, _ = render.select_and_cap(cfg, w2, wm2, B, train=True)
     assert n_rows2 == K and int(n_dev2.item()) == n2
     assert torch.equal(torch.sort(idx2[:n2]).values, all2[:n2])

@@ -149,8 +149,12 @@ def test_device_rng_render_equals_render_with_explicit_streams(precision):
     b = run(dict(jitter=jitter, noise_c=ops.philox_fill(seed, 1, B * Sc).view(B, Sc),
                  noise_sel=ops.philox_fill(seed, 2, B * Sc).view(B, Sc), noise_f=ops.philox_fill(seed, 3, B * Sf).view(B, Sf)))
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
-    for x, y in zip(a[2], b[2]):
-        assert torch.equal(x, y)
+    n_par = len(list(m.nerf.parameters()))
+    for i, (x, y) in enumerate(zip(a[2], b[2])):
+        if precision == "bf16" and i < n_par:
+            assert torch.equal(x, y)        # weight / bias gradients of the tensor-core path: fixed reduction order
+        else:                               # ray gradients (and the fp32 path's split-K sums) use fp32 atomics: the
+            torch.testing.assert_close(x, y, rtol=2e-5, atol=1e-9)      # run-to-run summation order is free
     # and the default path draws its own seed from torch's generator: reproducible under torch.manual_seed
     torch.manual_seed(11)
     c = m.nerf.render_rays_train(rd, ro, 25, 1.0)
@@ -185,4 +189,4 @@ def test_fused_tails_switch_gives_identical_renders(monkeypatch):
         res[mode] = (rgb_c.detach(), rgb_f.detach(), [p.grad.clone() for p in m.nerf.parameters()])
     assert torch.equal(res["0"][0], res["1"][0]) and torch.equal(res["0"][1], res["1"][1])
     for x, y in zip(res["0"][2], res["1"][2]):
-        torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-9)
+        torch.testing.assert_close(x, y, rtol=2e-5, atol=1e-8)      # fp32 path: atomics in its split-K sums
