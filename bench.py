@@ -138,7 +138,8 @@ def measure(args, strong, rank, world, local, device, full):
         if args.allreduce == "ddp":     # exactly the reference's wrapper (main.py:61)
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
         else:                           # all-reduce of the flat gradient buffers overlapped with the backward pass
-            sync = parallel.GradSync(model, overlap=args.allreduce == "overlap").install()
+            sync = parallel.GradSync(model, overlap=args.allreduce != "flat",
+                                     transport="p2p" if args.allreduce == "p2p" else "nccl").install()
             opt.grad_scale = 1.0 / world
     dev_batch = tuple(t.to(device) for t in batch)
     host_batch = tuple(t.pin_memory() for t in batch)
@@ -327,8 +328,10 @@ def run_ours(args):
                                     issue=("CUDA-graph replay of forward+loss+backward (+ gradient all-reduce) per step "
                                            "(GraphedTrainStep); RAdam.step launched eagerly") if m["use_graph"] else "eager launches",
                                     allreduce=(f"{args.allreduce}: fine network's flat gradient buffer all-reduced on a "
-                                               "communication stream inside backward, coarse + camera gradients after it; "
-                                               "1/N folded into RAdam") if world > 1 and args.allreduce != "ddp" else
+                                               "communication stream inside backward, coarse + camera gradients after it "
+                                               + ("(mcnerf_allreduce_p2p: one two-shot kernel per buffer over NVLink-mapped "
+                                                  "symmetric memory); " if args.allreduce == "p2p" else "(NCCL); ")
+                                               + "1/N folded into RAdam") if world > 1 and args.allreduce != "ddp" else
                                               ("DistributedDataParallel" if world > 1 else None)),
                     e2e=dict(value=round(m["e2e"], 1), unit=UNIT, h2d_bytes_per_step=m["h2d"], d2h_bytes_per_step=4,
                              ms_per_step=round(m["ms_e2e"] / args.steps, 3)),
@@ -706,9 +709,10 @@ def main():
     ap.add_argument("--rays", type=int, default=RAYS)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--allreduce", default="overlap", choices=["overlap", "flat", "ddp"],
-                    help="overlap (default): flat-buffer all-reduce on a communication stream inside backward; flat: the "
-                         "same collectives on the main stream; ddp: the reference's DistributedDataParallel wrapper")
+    ap.add_argument("--allreduce", default=os.environ.get("MCNERF_ALLREDUCE", "p2p"), choices=["p2p", "overlap", "flat", "ddp"],
+                    help="p2p (default): libmcnerf's two-shot NVLink all-reduce kernel on symmetric gradient buffers, on a "
+                         "communication stream inside backward; overlap: the same schedule with NCCL all-reduces; flat: "
+                         "NCCL on the main stream; ddp: the reference's DistributedDataParallel wrapper")
     ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
                     help="N > 1 default: strong = ONE --rays batch split into equal ray slices across the ranks (BASELINE "
                          "configs[2], north_star); weak (the reference's DDP semantic): every rank renders its own "

@@ -314,6 +314,21 @@ int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, const float* b
 int mcnerf_mlp_tc_bwd_phases(int mask);
 
 
+/* ------------------------------------------------------------------ gradient all-reduce over NVLink peer memory (e)
+ * ref: main.py:61,84 (DistributedDataParallel's NCCL all-reduce of the MLP + camera gradients).  Two-shot all-reduce in
+ * ONE kernel over symmetric buffers mapped into every rank of one NVSwitch box: buf[p] / flags[p] are rank p's buffer and
+ * flag pad as seen from THIS process (peer pointers; the caller exchanges the handles, e.g. with
+ * torch.distributed._symmetric_memory), flags zeroed once: n_ctas * 2 * 8 uint32 per rank; epoch: n_ctas zeroed uint32
+ * in local memory.  buf[*][offset .. offset + count) = scale * sum over ranks, bit-identical on every rank.
+ * Every rank must issue the same sequence of calls; the kernel needs its n_ctas CTAs resident on every rank. */
+typedef struct {
+  int rank, n_ranks, n_ctas;
+  void* buf[8];
+  void* flags[8];
+  void* epoch;
+} mcnerf_p2p;
+int mcnerf_allreduce_p2p(const mcnerf_p2p* ctx, int64_t offset, int64_t count, float scale, void* stream);
+
 /* ------------------------------------------------------------------ tensor-core self test
  * One 128xN tcgen05 tile: D = A B^T (mn_major = 0: A [128,K], B [N,K] bf16, K-major operands) or
  * D = A^T B (mn_major = 1: A [K,128], B [K,N], MN-major operands).  Used by tests/ to pin the UMMA

@@ -51,7 +51,12 @@ class TcInput(ctypes.Structure):
                 ("x_enc", _fp), ("ld_enc", ctypes.c_int), ("dirs_rows", _fp)]
 
 
-_STRUCTS = {"mcnerf_tc_input": TcInput, "mcnerf_sampling": Sampling, "mcnerf_mlp_params": MlpParams, "mcnerf_mlp_grads": MlpGrads,
+class P2P(ctypes.Structure):
+    _fields_ = [("rank", ctypes.c_int), ("n_ranks", ctypes.c_int), ("n_ctas", ctypes.c_int),
+                ("buf", _fp * 8), ("flags", _fp * 8), ("epoch", _fp)]
+
+
+_STRUCTS = {"mcnerf_p2p": P2P, "mcnerf_tc_input": TcInput, "mcnerf_sampling": Sampling, "mcnerf_mlp_params": MlpParams, "mcnerf_mlp_grads": MlpGrads,
             "mcnerf_dirs": Dirs, "mcnerf_composite_cfg": CompositeCfg}
 _SCALARS = {"int": ctypes.c_int, "float": ctypes.c_float, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t,
             "uint64_t": ctypes.c_uint64, "uint32_t": ctypes.c_uint32, "void": None}

@@ -67,17 +67,25 @@ class GradSync:
     The renderer's backward finishes the FINE network first (render.RenderFn.backward); through render.GRAD_HOOK its
     flat gradient buffer is all-reduced on a communication stream right there, overlapping the coarse network's
     backward (~0.8 ms of kernels at the benched shape); the coarse buffer follows and overlaps the camera-model
-    backward.  `finish()` - after backward - all-reduces what is left (the six camera tensors, 7 KB, as ONE coalesced
-    NCCL launch; gradients of networks that did not go through the hook) and joins the communication stream.
+    backward.  `finish()` - after backward - reduces what is left (the six camera tensors, 7 KB; gradients of networks
+    that did not go through the hook) and joins the communication stream.
     Buffers, order and sizes are fixed by the model, never by a rank's local gradient state, so all ranks always
-    issue the same collectives.  The sum is NOT divided here: pass `grad_scale = 1 / world` to the optimiser
-    (model.RAdam reads `opt.grad_scale`), which folds the division into its update kernel.
+    issue the same collectives.  The SUM is left in .grad: pass `grad_scale = 1 / world` to the optimiser (model.RAdam
+    reads `opt.grad_scale`), which folds the division into its update kernel.
+
+    transport = "p2p" (default on one NVSwitch box): the gradients live in SYMMETRIC memory mapped into every rank
+      (torch.distributed._symmetric_memory does the handle exchange; render.GRAD_ALLOC places both networks' gradient
+      buffers there, so nothing is copied) and each reduction is ONE launch of libmcnerf's two-shot NVLink all-reduce
+      kernel (csrc/allreduce.cu): ~3 launches of NCCL cost 110-120 us of exposed time per step, this costs a fraction;
+    transport = "nccl": torch.distributed all-reduces (any topology; also the gloo CPU tests).
 
     Works eagerly and under CUDA-graph capture (append `finish` to GraphedTrainStep.after_backward: the fork and the
     join of the communication stream are then part of the captured graph).  Requires gradients to be None before
     backward (zero_grad(set_to_none=True), the default): the in-place reduction must not race an accumulation."""
 
-    def __init__(self, model, overlap=True):
+    P2P_CTAS = 24
+
+    def __init__(self, model, overlap=True, transport="nccl"):
         self.model = model
         self.n = world()
         self.overlap = overlap
@@ -88,27 +96,83 @@ class GradSync:
         self._net_params = {"coarse": [p for k, p in named if k.startswith("nerf.nerf_coarse.")],
                             "fine": [p for k, p in named if k.startswith("nerf.nerf_fine.")]}
         self._other = [p for k, p in named if not k.startswith("nerf.nerf_coarse.") and not k.startswith("nerf.nerf_fine.")]
+        self.transport = transport if self.n > 1 else "nccl"
+        self._p2p = None
+        if self.transport == "p2p":
+            self._setup_p2p()
+
+    # ------------------------------------------------------------------ symmetric memory (p2p transport)
+    def _setup_p2p(self):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        from ._lib import P2P
+        dev = next(self.model.parameters()).device
+        pad4 = lambda n: (n + 3) // 4 * 4
+        self._n_nets = sum(p.numel() for ps in self._net_params.values() for p in ps)
+        self._cam_off = pad4(self._n_nets)
+        self._rest_cap = pad4(sum(p.numel() for p in self._other)) + pad4(self._n_nets)      # room for un-hooked networks
+        total = self._cam_off + self._rest_cap
+        group = dist.group.WORLD
+        self._sym = symm.empty(total, dtype=torch.float32, device=dev)
+        self._sym.zero_()
+        hdl = symm.rendezvous(self._sym, group)
+        self._flags = symm.empty(64 * 2 * 8, dtype=torch.int32, device=dev)
+        self._flags.zero_()
+        hdl_f = symm.rendezvous(self._flags, group)
+        self._epoch = torch.zeros(64, dtype=torch.int32, device=dev)
+        ctx = P2P()
+        ctx.rank, ctx.n_ranks, ctx.n_ctas = dist.get_rank(), self.n, self.P2P_CTAS
+        for p in range(self.n):
+            ctx.buf[p] = int(hdl.buffer_ptrs[p])
+            ctx.flags[p] = int(hdl_f.buffer_ptrs[p])
+        ctx.epoch = self._epoch.data_ptr()
+        self._p2p, self._hdls = ctx, (hdl, hdl_f)
+        torch.cuda.synchronize()
+        dist.barrier()                       # every rank's buffers are zeroed and mapped before the first kernel
+
+    def _alloc(self, numel, device):
+        """render.GRAD_ALLOC: both networks' gradient buffer inside the symmetric region (zeroed)"""
+        if self._p2p is None or numel != self._n_nets or device != self._sym.device:
+            return None
+        flat = self._sym[:numel]
+        flat.zero_()
+        return flat
+
+    def _reduce(self, flat):
+        """SUM-all-reduce a contiguous fp32 buffer on the current stream"""
+        if self._p2p is not None and flat.is_cuda:
+            base = self._sym.data_ptr()
+            off = (flat.data_ptr() - base) // 4
+            if 0 <= off and off + flat.numel() <= self._sym.numel() and off % 4 == 0 and flat.numel() % 4 == 0:
+                import ctypes
+                from . import ops
+                from ._lib import lib
+                lib().call("mcnerf_allreduce_p2p", ctypes.byref(self._p2p), int(off), int(flat.numel()), 1.0, ops._stream())
+                return
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
 
     def install(self):
         from . import render
         render.GRAD_HOOK = self._on_ready if self.n > 1 else None
+        render.GRAD_ALLOC = self._alloc if (self.n > 1 and self._p2p is not None) else None
         return self
 
     def uninstall(self):
         from . import render
         render.GRAD_HOOK = None
+        render.GRAD_ALLOC = None
 
     def _on_ready(self, name, flat):
         self.n_collectives += 1
         if not self.overlap or not flat.is_cuda:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            self._reduce(flat)
         else:
             main = torch.cuda.current_stream(flat.device)
             if self._comm is None:
-                self._comm = torch.cuda.Stream(device=flat.device)
+                self._comm = torch.cuda.Stream(device=flat.device, priority=-1)      # its few CTAs go first when SMs free up
             self._comm.wait_stream(main)
             with torch.cuda.stream(self._comm):
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+                self._reduce(flat)
             flat.record_stream(self._comm)
         self._hooked.add(name)
 
@@ -124,9 +188,22 @@ class GradSync:
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
         grads = [p.grad for p in rest]
+        if self._comm is not None:           # the p2p kernels of one rank must run in the same order on every rank
+            torch.cuda.current_stream().wait_stream(self._comm)
         if grads:
             dev = grads[0].device
-            if dev.type == "cuda":
+            n_rest = sum(g.numel() for g in grads)
+            if self._p2p is not None and dev.type == "cuda" and n_rest <= self._rest_cap:
+                # gather the small tensors into the symmetric region (one launch), reduce it (one launch), and let
+                # .grad point at the reduced values (no copy back)
+                region = self._sym[self._cam_off:self._cam_off + (n_rest + 3) // 4 * 4]
+                torch.cat([g.reshape(-1) for g in grads], out=region[:n_rest])
+                self._reduce(region)
+                off = 0
+                for p, g in zip(rest, grads):
+                    p.grad = region[off:off + g.numel()].view_as(g)
+                    off += g.numel()
+            elif dev.type == "cuda":
                 with dist._coalescing_manager(device=dev, async_ops=False):     # one NCCL launch for all of them
                     for g in grads:
                         dist.all_reduce(g, op=dist.ReduceOp.SUM)
@@ -134,8 +211,6 @@ class GradSync:
                 for g in grads:
                     dist.all_reduce(g, op=dist.ReduceOp.SUM)
             self.n_collectives += 1
-        if self._comm is not None:
-            torch.cuda.current_stream().wait_stream(self._comm)
 
     def collectives_per_step(self, steps):
         return self.n_collectives / max(1, steps)

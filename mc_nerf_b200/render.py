@@ -21,6 +21,8 @@ _p, _stream = ops._p, ops._stream
 
 
 LAST = {}      # debug/bench: row counts of the most recent fine pass (device tensor: no sync is forced here)
+GRAD_ALLOC = None  # callable(numel, device) -> zeroed flat fp32 buffer for BOTH networks' gradients, or None: lets the
+                   # data-parallel layer place the gradients straight into NVLink-mapped symmetric memory (parallel.GradSync)
 GRAD_HOOK = None   # callable(name, flat) or None: called inside RenderFn.backward, on the launching stream, as soon as
                    # ONE network's gradients ("fine", then "coarse") are final in their flat fp32 buffer - the gradient
                    # all-reduce of the fine network then overlaps the coarse network's backward (parallel.GradSync)
@@ -177,7 +179,10 @@ def _flat_zero_grads(*nets):
     """zero gradients for every tensor of the given networks as views of ONE zero-filled buffer, in parameter order
     (1 fill instead of 48, and the gradient all-reduce sees a single contiguous run: parallel.FlatGradAllReduce)."""
     total = sum(v.numel() for tensors in nets for v in tensors.values())
-    flat = torch.zeros(total, dtype=torch.float32, device=next(iter(nets[0].values())).device)
+    dev = next(iter(nets[0].values())).device
+    flat = GRAD_ALLOC(total, dev) if GRAD_ALLOC is not None else None
+    if flat is None:
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
     outs, off = [], 0
     for tensors in nets:
         out, begin = {}, off

@@ -320,3 +320,39 @@ def test_device_side_sample_cap_keeps_a_uniform_subset():
     idx2, n_rows2, n_dev2, _ = render.select_and_cap(cfg, w2, wm2, B, train=True)
     assert n_rows2 == K and int(n_dev2.item()) == n2
     assert torch.equal(torch.sort(idx2[:n2]).values, all2[:n2])
+
+
+def test_p2p_allreduce_kernel_two_virtual_ranks_on_one_gpu():
+    """mcnerf_allreduce_p2p (csrc/allreduce.cu): the two-shot NVLink all-reduce, exercised on ONE device by two
+    "ranks" whose buffers both live on it and whose kernels run concurrently on two streams - the flag barriers,
+    the slice split and the fused all-gather are the same code path as across GPUs (bench.py --gpus N checks the
+    multi-GPU case: `ranks_identical`)."""
+    import ctypes
+    from mc_nerf_b200 import ops
+    from mc_nerf_b200._lib import P2P, lib
+    n_ctas, count, off = 8, 4 * 50001, 16
+    g = torch.Generator().manual_seed(4)
+    bufs = [torch.randn(off + count + 8, generator=g).to(DEV) for _ in range(2)]
+    flags = [torch.zeros(64 * 2 * 8, dtype=torch.int32, device=DEV) for _ in range(2)]
+    epochs = [torch.zeros(64, dtype=torch.int32, device=DEV) for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ctxs = []
+    for r in range(2):
+        c = P2P()
+        c.rank, c.n_ranks, c.n_ctas = r, 2, n_ctas
+        for p in range(2):
+            c.buf[p], c.flags[p] = bufs[p].data_ptr(), flags[p].data_ptr()
+        c.epoch = epochs[r].data_ptr()
+        ctxs.append(c)
+    torch.cuda.synchronize()
+    for it in range(3):                    # epochs advance: the flag pads are never reset
+        before = [b.clone() for b in bufs]
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                lib().call("mcnerf_allreduce_p2p", ctypes.byref(ctxs[r]), off, count, 0.5, ops._stream())
+        torch.cuda.synchronize()
+        want = (before[0][off:off + count] + before[1][off:off + count]) * 0.5
+        for r in range(2):
+            assert torch.equal(bufs[r][off:off + count], want)                  # identical bits on both "ranks"
+            assert torch.equal(bufs[r][:off], before[r][:off]) and torch.equal(bufs[r][off + count:], before[r][off + count:])
+        assert int(epochs[0][0]) == it + 1 and int(epochs[1][n_ctas - 1]) == it + 1
