@@ -58,6 +58,20 @@ int mcnerf_reproject_fwd(const float* wpts, const float* K, const float* Rt, int
 int mcnerf_reproject_bwd(const float* wpts, const float* K, const float* Rt, const float* g_pix, int n_cam, int n_pts,
                          float* gK, float* gRt, void* stream);
 
+/* The camera model of one train step fused (ref: model/mc_nerf.py:75-76, 87-88: add_weights2param +
+ * get_reproject_pixels): K, Kinv [n,3,3], pose, calib_pose [n,3,4] (world->camera), pix [n,P,2] = reprojection of the
+ * calibration points wpts [n,P,3] through (K, calib_pose).  One launch instead of four. */
+int mcnerf_camera_fwd(const float* w_fx, const float* w_fy, const float* w_ux, const float* w_uy, const float* w_pose,
+                      const float* w_pose_calib, const float* wpts, int n_cam, int n_pts, int img_h, int img_w,
+                      float* K, float* Kinv, float* pose, float* calib_pose, float* pix, void* stream);
+/* Backward of the above from g_Kinv [n,3,3] (may be NULL), g_pose [n,3,4] (NULL with g_w_pose = NULL: extrinsics frozen,
+ * ref: model/mc_nerf.py:87) and g_pix [n,P,2]; scratch: 21 * n_cam floats.  One launch instead of four. */
+int mcnerf_camera_bwd(const float* w_fx, const float* w_fy, const float* w_ux, const float* w_uy, const float* w_pose,
+                      const float* w_pose_calib, const float* wpts, const float* K, const float* calib_pose, int n_cam,
+                      int n_pts, int img_h, int img_w, const float* g_Kinv, const float* g_pose, const float* g_pix,
+                      float* scratch, float* g_fx, float* g_fy, float* g_ux, float* g_uy, float* g_w_pose,
+                      float* g_w_pose_calib, void* stream);
+
 /* ------------------------------------------------------------------ ray generation (a5, a6)
  * ref: model/mc_nerf.py:124-145 (get_rays), :229-256 (pix2cam, cam2world), :327-345 (gather of the
  * randperm subset).  Ray r uses camera cam_id[r] (or `cam_const` when cam_id is NULL) and pixel

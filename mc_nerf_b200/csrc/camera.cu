@@ -6,11 +6,9 @@
 
 namespace {
 
-__global__ void intrinsics_fwd_k(const float* __restrict__ wfx, const float* __restrict__ wfy,
-                                 const float* __restrict__ wux, const float* __restrict__ wuy, int n, float H, float W,
-                                 float* __restrict__ K, float* __restrict__ Kinv) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void intrinsics_fwd_dev(int i, const float* wfx, const float* wfy,
+                                 const float* wux, const float* wuy, int n, float H, float W,
+                                 float* K, float* Kinv) {
   // sic: fy is scaled by the image WIDTH in the reference (model/mc_nerf.py:173)
   float fx = fabsf(W * wfx[i]), fy = fabsf(W * wfy[i]);
   float ux = fabsf(W * 0.5f * wux[i]), uy = fabsf(H * 0.5f * wuy[i]);
@@ -29,13 +27,11 @@ __global__ void intrinsics_fwd_k(const float* __restrict__ wfx, const float* __r
 
 __device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 
-__global__ void intrinsics_bwd_k(const float* __restrict__ wfx, const float* __restrict__ wfy,
-                                 const float* __restrict__ wux, const float* __restrict__ wuy, int n, float H, float W,
-                                 const float* __restrict__ gK, const float* __restrict__ gKinv,
-                                 float* __restrict__ gfx, float* __restrict__ gfy, float* __restrict__ gux,
-                                 float* __restrict__ guy) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void intrinsics_bwd_dev(int i, const float* wfx, const float* wfy,
+                                 const float* wux, const float* wuy, int n, float H, float W,
+                                 const float* gK, const float* gKinv,
+                                 float* gfx, float* gfy, float* gux,
+                                 float* guy) {
   float afx = W * wfx[i], afy = W * wfy[i], aux = W * 0.5f * wux[i], auy = H * 0.5f * wuy[i];
   float fx = fabsf(afx), fy = fabsf(afy), ux = fabsf(aux), uy = fabsf(auy);
   float d_fx = 0.f, d_fy = 0.f, d_ux = 0.f, d_uy = 0.f;
@@ -100,9 +96,7 @@ __device__ __forceinline__ void mat3_mul(const float a[9], const float b[9], flo
     for (int j = 0; j < 3; ++j) c[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
 }
 
-__global__ void se3_fwd_k(const float* __restrict__ wu, int n, float* __restrict__ Rt) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void se3_fwd_dev(int i, const float* wu, int n, float* Rt) {
   float w[3] = {wu[6 * i], wu[6 * i + 1], wu[6 * i + 2]};
   float u[3] = {wu[6 * i + 3], wu[6 * i + 4], wu[6 * i + 5]};
   float th = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
@@ -125,9 +119,7 @@ __global__ void se3_fwd_k(const float* __restrict__ wu, int n, float* __restrict
   }
 }
 
-__global__ void se3_bwd_k(const float* __restrict__ wu, const float* __restrict__ gRt, int n, float* __restrict__ gwu) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void se3_bwd_dev(int i, const float* wu, const float* gRt, int n, float* gwu) {
   float w[3] = {wu[6 * i], wu[6 * i + 1], wu[6 * i + 2]};
   float u[3] = {wu[6 * i + 3], wu[6 * i + 4], wu[6 * i + 5]};
   float th = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
@@ -190,10 +182,8 @@ __global__ void se3_bwd_k(const float* __restrict__ wu, const float* __restrict_
 
 // Calibration-point reprojection px = K [R|t] X / z, one thread per camera (P points each).
 // ref: model/mc_nerf.py:147-152, 236-241, 260-267.
-__global__ void reproject_fwd_k(const float* __restrict__ wpts, const float* __restrict__ K,
-                                const float* __restrict__ Rt, int n, int P, float* __restrict__ pix) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+__device__ __forceinline__ void reproject_fwd_dev(int c, const float* wpts, const float* K,
+                                const float* Rt, int n, int P, float* pix) {
   const float* k = K + 9 * c;
   const float* m = Rt + 12 * c;
   for (int p = 0; p < P; ++p) {
@@ -209,11 +199,9 @@ __global__ void reproject_fwd_k(const float* __restrict__ wpts, const float* __r
   }
 }
 
-__global__ void reproject_bwd_k(const float* __restrict__ wpts, const float* __restrict__ K,
-                                const float* __restrict__ Rt, const float* __restrict__ gpix, int n, int P,
-                                float* __restrict__ gK, float* __restrict__ gRt) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+__device__ __forceinline__ void reproject_bwd_dev(int c, const float* wpts, const float* K,
+                                const float* Rt, const float* gpix, int n, int P,
+                                float* gK, float* gRt) {
   const float* k = K + 9 * c;
   const float* m = Rt + 12 * c;
   float dk[9], dm[12];
@@ -251,6 +239,65 @@ __global__ void reproject_bwd_k(const float* __restrict__ wpts, const float* __r
   for (int i = 0; i < 9; ++i) gK[9 * c + i] = dk[i];
 #pragma unroll
   for (int i = 0; i < 12; ++i) gRt[12 * c + i] = dm[i];
+}
+
+__global__ void intrinsics_fwd_k(const float* __restrict__ wfx, const float* __restrict__ wfy, const float* __restrict__ wux, const float* __restrict__ wuy, int n, float H, float W, float* __restrict__ K, float* __restrict__ Kinv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) intrinsics_fwd_dev(i, wfx, wfy, wux, wuy, n, H, W, K, Kinv);
+}
+__global__ void intrinsics_bwd_k(const float* __restrict__ wfx, const float* __restrict__ wfy, const float* __restrict__ wux, const float* __restrict__ wuy, int n, float H, float W, const float* __restrict__ gK, const float* __restrict__ gKinv, float* __restrict__ gfx, float* __restrict__ gfy, float* __restrict__ gux, float* __restrict__ guy) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) intrinsics_bwd_dev(i, wfx, wfy, wux, wuy, n, H, W, gK, gKinv, gfx, gfy, gux, guy);
+}
+__global__ void se3_fwd_k(const float* __restrict__ wu, int n, float* __restrict__ Rt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) se3_fwd_dev(i, wu, n, Rt);
+}
+__global__ void se3_bwd_k(const float* __restrict__ wu, const float* __restrict__ gRt, int n, float* __restrict__ gwu) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) se3_bwd_dev(i, wu, gRt, n, gwu);
+}
+__global__ void reproject_fwd_k(const float* __restrict__ wpts, const float* __restrict__ K, const float* __restrict__ Rt, int n, int P, float* __restrict__ pix) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) reproject_fwd_dev(i, wpts, K, Rt, n, P, pix);
+}
+__global__ void reproject_bwd_k(const float* __restrict__ wpts, const float* __restrict__ K, const float* __restrict__ Rt, const float* __restrict__ gpix, int n, int P, float* __restrict__ gK, float* __restrict__ gRt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) reproject_bwd_dev(i, wpts, K, Rt, gpix, n, P, gK, gRt);
+}
+
+// ---- the whole camera model of a train step in ONE launch each way (one thread per camera):
+// forward : intrinsics (K, K^-1) + se3 -> SE3 of the main and of the calibration poses + reprojection of the calibration
+//           points through the calibration pose (ref: model/mc_nerf.py:75-76 = add_weights2param + get_reproject_pixels);
+// backward: reprojection -> (dK, d calib pose) -> both se(3) backward passes + the intrinsics backward (which also takes
+//           the gradient of K^-1 coming from the rays).  The unfused entry points remain for the module-level API.
+__global__ void camera_fwd_k(const float* wfx, const float* wfy, const float* wux,
+                             const float* wuy, const float* w_pose,
+                             const float* w_calib, const float* wpts, int n, int P, float H,
+                             float W, float* K, float* Kinv, float* pose,
+                             float* calib, float* pix) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  intrinsics_fwd_dev(i, wfx, wfy, wux, wuy, n, H, W, K, Kinv);
+  se3_fwd_dev(i, w_pose, n, pose);
+  se3_fwd_dev(i, w_calib, n, calib);
+  reproject_fwd_dev(i, wpts, K, calib, n, P, pix);        // reads what this very thread just wrote
+}
+
+__global__ void camera_bwd_k(const float* wfx, const float* wfy, const float* wux,
+                             const float* wuy, const float* w_pose,
+                             const float* w_calib, const float* wpts,
+                             const float* K, const float* calib, int n, int P, float H, float W,
+                             const float* g_Kinv, const float* g_pose,
+                             const float* g_pix, float* tmp_gK, float* tmp_gcalib,
+                             float* g_fx, float* g_fy, float* g_ux,
+                             float* g_uy, float* g_wpose, float* g_wcalib) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  reproject_bwd_dev(i, wpts, K, calib, g_pix, n, P, tmp_gK, tmp_gcalib);
+  se3_bwd_dev(i, w_calib, tmp_gcalib, n, g_wcalib);
+  if (g_wpose) se3_bwd_dev(i, w_pose, g_pose, n, g_wpose);
+  intrinsics_bwd_dev(i, wfx, wfy, wux, wuy, n, H, W, tmp_gK, g_Kinv, g_fx, g_fy, g_ux, g_uy);
 }
 
 }  // namespace
@@ -300,6 +347,33 @@ extern "C" int mcnerf_se3_fwd(const float* wu, int n, float* Rt, void* stream) {
 extern "C" int mcnerf_se3_bwd(const float* wu, const float* gRt, int n, float* g_wu, void* stream) {
   MC_ARG(wu && gRt && g_wu && n > 0);
   se3_bwd_k<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(wu, gRt, n, g_wu);
+  MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcnerf_camera_fwd(const float* w_fx, const float* w_fy, const float* w_ux, const float* w_uy,
+                                 const float* w_pose, const float* w_pose_calib, const float* wpts, int n_cam, int n_pts,
+                                 int img_h, int img_w, float* K, float* Kinv, float* pose, float* calib_pose, float* pix,
+                                 void* stream) {
+  MC_ARG(w_fx && w_fy && w_ux && w_uy && w_pose && w_pose_calib && wpts && K && Kinv && pose && calib_pose && pix &&
+         n_cam > 0 && n_pts > 0);
+  camera_fwd_k<<<cdiv(n_cam, 64), 64, 0, (cudaStream_t)stream>>>(w_fx, w_fy, w_ux, w_uy, w_pose, w_pose_calib, wpts, n_cam,
+                                                                 n_pts, (float)img_h, (float)img_w, K, Kinv, pose,
+                                                                 calib_pose, pix);
+  MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcnerf_camera_bwd(const float* w_fx, const float* w_fy, const float* w_ux, const float* w_uy,
+                                 const float* w_pose, const float* w_pose_calib, const float* wpts, const float* K,
+                                 const float* calib_pose, int n_cam, int n_pts, int img_h, int img_w, const float* g_Kinv,
+                                 const float* g_pose, const float* g_pix, float* scratch, float* g_fx, float* g_fy,
+                                 float* g_ux, float* g_uy, float* g_w_pose, float* g_w_pose_calib, void* stream) {
+  MC_ARG(w_fx && w_fy && w_ux && w_uy && w_pose && w_pose_calib && wpts && K && calib_pose && g_pix && scratch && g_fx &&
+         g_fy && g_ux && g_uy && g_w_pose_calib && n_cam > 0 && n_pts > 0 && (g_w_pose == nullptr || g_pose != nullptr));
+  camera_bwd_k<<<cdiv(n_cam, 64), 64, 0, (cudaStream_t)stream>>>(
+      w_fx, w_fy, w_ux, w_uy, w_pose, w_pose_calib, wpts, K, calib_pose, n_cam, n_pts, (float)img_h, (float)img_w, g_Kinv,
+      g_pose, g_pix, scratch, scratch + (size_t)9 * n_cam, g_fx, g_fy, g_ux, g_uy, g_w_pose, g_w_pose_calib);
   MC_LAUNCHED();
   return 0;
 }

@@ -104,8 +104,19 @@ class MC_Model(nn.Module):
             glob = epoch_type == "GLOBAL_OPTIM_EPOCH"    # ref: :73-83 (global) / :85-95 (fine tune)
             self.nerf.prefetch_weights()                 # bf16 weight images pack while the camera kernels run
             self.nerf.emmbedding_xyz.barf_mode = glob
-            self.intr_adj, self.pose_adj, self.calib_pose_adj = self.add_weights2param(True, glob, True)
-            reproj = self.get_reproject_pixels(intr_wpts, self.intr_adj, self.calib_pose_adj)
+            if intr_wpts.is_cuda and intr_wpts.dim() == 4 and intr_wpts.shape[0] == 1 and not intr_wpts.requires_grad:
+                # the whole camera model in one launch (and one in backward): add_weights2param + get_reproject_pixels
+                ws = [self.weights_fx, self.weights_fy, self.weights_ux, self.weights_uy]
+                for w in ws:
+                    w.requires_grad_(True)
+                self.weights_pose.requires_grad_(glob)
+                self.weights_pose_intr.requires_grad_(True)
+                K, Kinv, self.pose_adj, self.calib_pose_adj, reproj = ops.CameraTrainFn.apply(
+                    *ws, self.weights_pose, self.weights_pose_intr, intr_wpts, self.img_h, self.img_w)
+                self.intr_adj, self._intr_inv_adj = K, (K, Kinv)
+            else:
+                self.intr_adj, self.pose_adj, self.calib_pose_adj = self.add_weights2param(True, glob, True)
+                reproj = self.get_reproject_pixels(intr_wpts, self.intr_adj, self.calib_pose_adj)
             rays_d, rays_o, rand_idx = self.generate_train_rays(img_id_host)
             rgbs_c, rgbs_f = self.nerf(rays_d, rays_o, epoch, cur_ratio if glob else 1)
             if self._gt_event is not None:          # side-stream H2D of the image must have landed

@@ -211,6 +211,45 @@ class ReprojectFn(torch.autograd.Function):
         return None, gK, gRt
 
 
+class CameraTrainFn(torch.autograd.Function):
+    """The camera model of one train step in one launch each way: (w_fx, w_fy, w_ux, w_uy, w_pose, w_pose_intr, wpts)
+    -> K, Kinv [n,3,3], pose, calib_pose [n,3,4], reprojected calibration pixels [1,n,P,2].
+    ref: model/mc_nerf.py:75-76 / 87-88 (add_weights2param + get_reproject_pixels).  Gradients: Kinv and pose from the
+    rays, the pixels from the loss; K and calib_pose are consumed by the reprojection inside."""
+
+    @staticmethod
+    def forward(ctx, w_fx, w_fy, w_ux, w_uy, w_pose, w_calib, wpts, img_h, img_w):
+        ws = [_f32(w) for w in (w_fx, w_fy, w_ux, w_uy, w_pose, w_calib)]
+        wp = _f32(wpts)
+        n, P, dev = ws[0].shape[0], wp.shape[-2], ws[0].device
+        K, Kinv = torch.empty(n, 3, 3, device=dev), torch.empty(n, 3, 3, device=dev)
+        pose, calib = torch.empty(n, 3, 4, device=dev), torch.empty(n, 3, 4, device=dev)
+        pix = torch.empty(*wp.shape[:-1], 2, device=dev)
+        lib().call("mcnerf_camera_fwd", *[_p(w) for w in ws], _p(wp), n, P, int(img_h), int(img_w), _p(K), _p(Kinv),
+                   _p(pose), _p(calib), _p(pix), _stream())
+        ctx.save_for_backward(*ws, wp, K, calib)
+        ctx.hw = (int(img_h), int(img_w))
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(K, calib)      # consumed inside (reprojection); exposed for reporting only
+        return K, Kinv, pose, calib, pix
+
+    @staticmethod
+    def backward(ctx, _gK, gKinv, gpose, _gcalib, gpix):
+        *ws, wp, K, calib = ctx.saved_tensors
+        n, P, dev = ws[0].shape[0], wp.shape[-2], ws[0].device
+        need_pose = ctx.needs_input_grad[4] and gpose is not None
+        out = torch.empty(4 * n + 12 * n + 21 * n, device=dev)          # g_fx|g_fy|g_ux|g_uy | g_pose | g_calib | scratch
+        gf = [out[k * n:(k + 1) * n] for k in range(4)]
+        g_wpose, g_wcalib = out[4 * n:10 * n].view(n, 6), out[10 * n:16 * n].view(n, 6)
+        scratch = out[16 * n:]
+        if gpix is None:
+            gpix = torch.zeros(n * P * 2, device=dev)
+        lib().call("mcnerf_camera_bwd", *[_p(w) for w in ws], _p(wp), _p(K), _p(calib), n, P, ctx.hw[0], ctx.hw[1],
+                   _p(_f32(gKinv)) if gKinv is not None else None, _p(_f32(gpose)) if need_pose else None, _p(_f32(gpix)),
+                   _p(scratch), *[_p(g) for g in gf], _p(g_wpose) if need_pose else None, _p(g_wcalib), _stream())
+        return gf[0], gf[1], gf[2], gf[3], (g_wpose if need_pose else None), g_wcalib, None, None, None
+
+
 class RaygenFn(torch.autograd.Function):
     """(Kinv [n,3,3], Rt [n,3,4], cam, pix) -> rays_o, rays_d [B,3].  ref: model/mc_nerf.py:124-145, 327-345.
     `cam` is an int or an int32 tensor [B]; `pix` is None (whole image, row-major) or an int32 tensor [B]."""
@@ -232,8 +271,8 @@ class RaygenFn(torch.autograd.Function):
     def backward(ctx, g_o, g_d):
         Kinv, Rt, cam_t, pix = ctx.saved_tensors
         cam_c, n_rays, img_w = ctx.meta
-        gK = torch.zeros_like(Kinv)
-        gRt = torch.zeros_like(Rt)
+        acc = torch.zeros(Kinv.numel() + Rt.numel(), device=Kinv.device)      # one fill for both accumulators
+        gK, gRt = acc[:Kinv.numel()].view_as(Kinv), acc[Kinv.numel():].view_as(Rt)
         g_o = _f32(g_o) if g_o is not None else torch.zeros(n_rays, 3, device=Kinv.device)
         g_d = _f32(g_d) if g_d is not None else torch.zeros(n_rays, 3, device=Kinv.device)
         lib().call("mcnerf_raygen_bwd", _p(Kinv), _p(Rt), _p(cam_t, torch.int32), cam_c, _p(pix, torch.int32),

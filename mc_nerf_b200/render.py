@@ -305,8 +305,8 @@ class RenderFn(torch.autograd.Function):
         (net_c, net_f), (pad_c, pad_f) = ctx.nets, ctx.pads
         gc, gf = _flat_zero_grads(tc, tf)
         flat_c, flat_f = gc.pop("__flat__"), gf.pop("__flat__")
-        g_o = torch.zeros_like(rays_o)
-        g_d = torch.zeros_like(rays_d)
+        g_od = torch.zeros(2, B, 3, device=dev)      # one fill for both ray-gradient accumulators
+        g_o, g_d = g_od[0], g_od[1]
         fused, compact, seed, w_sel, w_max, offs = ctx.tail
         if g_rgb_f is not None and n_rows > 0:
             cf = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sf, cfg.white_back)

@@ -356,3 +356,39 @@ def test_p2p_allreduce_kernel_two_virtual_ranks_on_one_gpu():
             assert torch.equal(bufs[r][off:off + count], want)                  # identical bits on both "ranks"
             assert torch.equal(bufs[r][:off], before[r][:off]) and torch.equal(bufs[r][off + count:], before[r][off + count:])
         assert int(epochs[0][0]) == it + 1 and int(epochs[1][n_ctas - 1]) == it + 1
+
+
+def test_fused_camera_model_equals_the_separate_kernels():
+    """mcnerf_camera_fwd / _bwd (one launch each way) against IntrinsicsFn + SE3Fn x2 + ReprojectFn, values and all six
+    parameter gradients, with the extrinsics trainable (GLOBAL_OPTIM) and frozen (FINE_TUNE, ref: model/mc_nerf.py:87)."""
+    from mc_nerf_b200 import ops
+    n, P, H, W = 11, 5, 48, 64
+    g = torch.Generator().manual_seed(6)
+    base = dict(fx=torch.rand(n, generator=g) + 0.5, fy=-(torch.rand(n, generator=g) + 0.5), ux=torch.rand(n, generator=g) + 0.5,
+                uy=torch.rand(n, generator=g) + 0.5, pose=torch.randn(n, 6, generator=g) * 0.7, calib=torch.randn(n, 6, generator=g))
+    wpts = (torch.rand(1, n, P, 3, generator=g) - 0.5).to(DEV)
+    g_kinv = torch.randn(n, 3, 3, generator=g).to(DEV)
+    g_pose = torch.randn(n, 3, 4, generator=g).to(DEV)
+    g_pix = torch.randn(1, n, P, 2, generator=g).to(DEV)
+    for train_pose in (True, False):
+        res = []
+        for fused in (True, False):
+            w = {k: v.clone().to(DEV).requires_grad_(k != "pose" or train_pose) for k, v in base.items()}
+            if fused:
+                K, Kinv, pose, calib, pix = ops.CameraTrainFn.apply(w["fx"], w["fy"], w["ux"], w["uy"], w["pose"], w["calib"],
+                                                                    wpts, H, W)
+            else:
+                K, Kinv = ops.IntrinsicsFn.apply(w["fx"], w["fy"], w["ux"], w["uy"], H, W)
+                pose, calib = ops.SE3Fn.apply(w["pose"]), ops.SE3Fn.apply(w["calib"])
+                pix = ops.ReprojectFn.apply(wpts, K, calib)
+            loss = (Kinv * g_kinv).sum() + (pix * g_pix).sum() + ((pose * g_pose).sum() if train_pose else 0.0)
+            loss.backward()
+            res.append(([K, Kinv, pose, calib, pix], {k: v.grad for k, v in w.items()}))
+        for a, b in zip(res[0][0], res[1][0]):
+            assert torch.equal(a.detach(), b.detach())
+        for k in base:
+            ga, gb = res[0][1][k], res[1][1][k]
+            if k == "pose" and not train_pose:
+                assert ga is None and gb is None
+            else:
+                close(ga, gb, rtol=1e-6, atol=1e-7)

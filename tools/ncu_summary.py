@@ -1,4 +1,4 @@
-"""profiles/r01_ncu_summary.json from an `ncu -i rep --page raw --csv` dump of tools/perf_mlp_tc.py <rows> 1 --profile --infer.
+"""profiles/rNN_ncu_summary.json from an `ncu -i rep --page raw --csv` dump of tools/perf_mlp_tc.py <rows> 1 --profile --infer.
 usage: ncu -i x.ncu-rep --page raw --csv | python tools/ncu_summary.py <rows> > profiles/r01_ncu_summary.json"""
 import csv, json, sys
 rows_n = int(sys.argv[1])
