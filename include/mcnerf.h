@@ -301,6 +301,12 @@ typedef struct {
   const float* x_enc;
   int ld_enc;
   const float* dirs_rows;
+  /* rays mode, backward only: when the rows of a ray are consecutive - no sample_idx (ray r owns rows [r*S, (r+1)*S)) or
+   * ray_offsets [n_rays+1] given (ray r owns rows [ray_offsets[r], ray_offsets[r+1]), the order mcnerf_select_fine
+   * emits) - set ordered_ray_grads = 1: per-ray gradients are then summed in a fixed order (bit-reproducible run to
+   * run) instead of with fp32 atomics. */
+  const int32_t* ray_offsets;
+  int ordered_ray_grads;
 } mcnerf_tc_input;
 
 int mcnerf_mlp_tc_supported(const mcnerf_mlp_params* p);   /* 1 if this network shape can use the tcgen05 path */

@@ -48,7 +48,8 @@ class CompositeCfg(ctypes.Structure):
 class TcInput(ctypes.Structure):
     _fields_ = [("rays_o", _fp), ("rays_d", _fp), ("jitter", _fp), ("n_rays", ctypes.c_int), ("smp", Sampling),
                 ("sample_idx", _fp), ("n_rows", ctypes.c_int), ("n_rows_dev", _fp),
-                ("x_enc", _fp), ("ld_enc", ctypes.c_int), ("dirs_rows", _fp)]
+                ("x_enc", _fp), ("ld_enc", ctypes.c_int), ("dirs_rows", _fp),
+                ("ray_offsets", _fp), ("ordered_ray_grads", ctypes.c_int)]
 
 
 class P2P(ctypes.Structure):

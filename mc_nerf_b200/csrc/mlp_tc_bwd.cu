@@ -12,6 +12,32 @@
 
 namespace mlptc {
 
+// Ordered per-ray sums of the chain kernel's segment partials: ray r owns the consecutive rows [b, e); its segments
+// start at b and at every multiple of 32 inside (b, e) (a warp of the chain kernel covers 32 consecutive rows).
+// One thread per ray, ascending row order: bit-reproducible, unlike fp32 atomics.
+__global__ void ray_grad_reduce_k(const float* __restrict__ seg_part, const int32_t* __restrict__ ray_offsets, int S,
+                                  int n_rays, int n_rows, const int32_t* __restrict__ n_rows_dev,
+                                  float* __restrict__ g_o, float* __restrict__ g_d) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  const int rows = n_rows_dev ? min(*n_rows_dev, n_rows) : n_rows;
+  int b = ray_offsets ? ray_offsets[r] : r * S, e = ray_offsets ? ray_offsets[r + 1] : (r + 1) * S;
+  e = min(e, rows);
+  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int h = b; h < e; h = (h / 32 + 1) * 32) {
+    const float* sp = seg_part + (size_t)h * 9;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) acc[c] += sp[c];
+  }
+  if (b < e) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      g_o[3 * r + c] += acc[c];
+      g_d[3 * r + c] += acc[3 + c] + acc[6 + c];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(BWD_THREADS, 1) mlp_tc_bwd_k(const __grid_constant__ BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   chain_role<false>(a, smem, (int)gridDim.x, nullptr, 0);
@@ -34,7 +60,7 @@ constexpr int WG_MAX_CTAS = 160;
 extern "C" size_t mcnerf_mlp_tc_bwd_workspace(const mcnerf_mlp_params* p, int n_rows) {
   if (!mcnerf_mlp_tc_supported(p) || n_rows <= 0) return 0;
   return stash_tiles(n_rows) * ((size_t)(p->depth + 2) * ACT_BYTES + HEAD_BYTES) + mlp_tc_wgrad_scratch_bytes(WG_MAX_CTAS) +
-         mlp_tc_fused_extra_bytes(n_rows, p->depth + 2);
+         mlp_tc_fused_extra_bytes(n_rows, p->depth + 2) + stash_tiles(n_rows) * (size_t)TM * 9 * sizeof(float);
 }
 
 // Measurement aid: which phases mcnerf_mlp_tc_bwd launches (bit 0: data-gradient chain, bit 1: weight gradients).
@@ -77,6 +103,11 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
   a.sel_idx = in->sample_idx; a.n_rows = in->n_rows; a.n_rows_dev = in->n_rows_dev;
   a.x_enc = in->x_enc; a.ld_enc = in->ld_enc; a.dirs_rows = in->dirs_rows;
   a.g_rays_o = g_rays_o; a.g_rays_d = g_rays_d; a.g_x_enc = g_x_enc; a.g_dirs_rows = g_dirs_rows;
+  // ordered ray-gradient sums: the last region of the workspace holds one 9-float partial per row
+  const bool ordered = !explicit_mode && in->ordered_ray_grads && (in->sample_idx == nullptr || in->ray_offsets != nullptr);
+  a.seg_part = ordered ? (float*)((uint8_t*)workspace + tiles * ((size_t)n_slots * ACT_BYTES + HEAD_BYTES) +
+                                  mlp_tc_wgrad_scratch_bytes(WG_MAX_CTAS) + mlp_tc_fused_extra_bytes(in->n_rows, n_slots))
+                       : nullptr;
   // per device / context attribute: set on every call (cheap), not once per process
   MC_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BWD));
   const int n_tiles = (in->n_rows + TM - 1) / TM;
@@ -87,12 +118,20 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
   // Default: two back-to-back kernels (data-gradient chain, then weight gradients).  MCNERF_BWD_FUSED=1 selects the
   // experimental single launch in which chain CTA pairs hand every dY tile to weight-gradient CTA pairs through L2
   // (mlp_tc_bwd_fused.cu): same results up to summation order, measured 3-40 % SLOWER on B200.
+  auto reduce_rays = [&]() -> int {
+    if (!a.seg_part) return 0;
+    ray_grad_reduce_k<<<cdiv(in->n_rays, 128), 128, 0, st>>>(a.seg_part, in->ray_offsets, in->smp.S, in->n_rays, in->n_rows,
+                                                             in->n_rows_dev, g_rays_o, g_rays_d);
+    MC_LAUNCHED();
+    return 0;
+  };
   const bool fused = getenv("MCNERF_BWD_FUSED") && atoi(getenv("MCNERF_BWD_FUSED")) == 1;
   if (fused && g_bwd_phases == 3) {
     MC_ARG(sms <= WG_MAX_CTAS);
     float* scratch = (float*)(a.dy_head + tiles * HEAD_BYTES);
     void* extra = (uint8_t*)scratch + mlp_tc_wgrad_scratch_bytes(WG_MAX_CTAS);
-    return mlp_tc_bwd_fused_launch(p, L, a, stash_act, stash_enc, scratch, extra, g, sms, st);
+    if (int e = mlp_tc_bwd_fused_launch(p, L, a, stash_act, stash_enc, scratch, extra, g, sms, st)) return e;
+    return reduce_rays();
   }
   if (g_bwd_phases & 1) {
     int grid = n_pairs < sms ? n_pairs : sms;
@@ -110,6 +149,7 @@ extern "C" int mcnerf_mlp_tc_bwd(const mcnerf_mlp_params* p, const void* wb, con
     cfg.numAttrs = 1;
     MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_bwd_k, a));
     MC_LAUNCHED();
+    if (int e = reduce_rays()) return e;
   }
   if (!(g_bwd_phases & 2)) return 0;
   // weight gradients (tcgen05, reduction over all rows) and bias gradients (column sums of the dY stash)

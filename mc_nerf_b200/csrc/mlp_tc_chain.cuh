@@ -26,6 +26,8 @@ struct BwdArgs {
   int ld_enc;
   const float* dirs_rows;
   float *g_rays_o, *g_rays_d;     // rays mode: accumulated [n_rays,3]
+  float* seg_part;                // rays mode, ordered sums: [rows][9] partial (d o, d d, d d via the SH head) of the
+                                  // 32-row segment that STARTS at that row; null: fp32 atomics into g_rays_*
   float* g_x_enc;                 // explicit mode: [rows, ld_enc] overwritten
   float* g_dirs_rows;             // explicit mode: [rows,3] overwritten
 };
@@ -346,7 +348,10 @@ __device__ __forceinline__ void chain_role(const BwdArgs& a, uint8_t* smem, cons
           if (valid) { a.g_dirs_rows[3 * (size_t)row_g] = gd[0]; a.g_dirs_rows[3 * (size_t)row_g + 1] = gd[1]; a.g_dirs_rows[3 * (size_t)row_g + 2] = gd[2]; }
         } else {
           bool head = seg_reduce<3>(ray[t], gd, lane);
-          if (valid && head) { atomicAdd(a.g_rays_d + 3 * ray[t], gd[0]); atomicAdd(a.g_rays_d + 3 * ray[t] + 1, gd[1]); atomicAdd(a.g_rays_d + 3 * ray[t] + 2, gd[2]); }
+          if (valid && head) {
+            if (a.seg_part) { float* sp = a.seg_part + (size_t)row_g * 9 + 6; sp[0] = gd[0]; sp[1] = gd[1]; sp[2] = gd[2]; }
+            else { atomicAdd(a.g_rays_d + 3 * ray[t], gd[0]); atomicAdd(a.g_rays_d + 3 * ray[t] + 1, gd[1]); atomicAdd(a.g_rays_d + 3 * ray[t] + 2, gd[2]); }
+          }
         }
       }
       tc::fence_proxy_async();
@@ -479,10 +484,16 @@ __device__ __forceinline__ void chain_role(const BwdArgs& a, uint8_t* smem, cons
               }
               bool head = seg_reduce<6>(ry, gv, lane);
               if (valid && head) {
+                if (a.seg_part) {
+                  float* sp = a.seg_part + (size_t)row_g * 9;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                  atomicAdd(a.g_rays_o + 3 * ry + c, gv[c]);
-                  atomicAdd(a.g_rays_d + 3 * ry + c, gv[3 + c]);
+                  for (int c = 0; c < 6; ++c) sp[c] = gv[c];
+                } else {
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) {
+                    atomicAdd(a.g_rays_o + 3 * ry + c, gv[c]);
+                    atomicAdd(a.g_rays_d + 3 * ry + c, gv[3 + c]);
+                  }
                 }
               }
             }

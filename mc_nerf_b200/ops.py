@@ -640,7 +640,7 @@ class TcWeights:
         return self
 
 
-def make_tc_input_rays(rays_o, rays_d, jitter, smp, sel_idx, n_rows, n_rows_dev):
+def make_tc_input_rays(rays_o, rays_d, jitter, smp, sel_idx, n_rows, n_rows_dev, ray_offsets=None):
     t = TcInput()
     t.rays_o, t.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
     t.jitter = jitter.data_ptr() if jitter is not None else None
@@ -650,7 +650,10 @@ def make_tc_input_rays(rays_o, rays_d, jitter, smp, sel_idx, n_rows, n_rows_dev)
     t.n_rows = int(n_rows)
     t.n_rows_dev = n_rows_dev.data_ptr() if n_rows_dev is not None else None
     t.x_enc, t.ld_enc, t.dirs_rows = None, 0, None
-    t._keep = (rays_o, rays_d, jitter, sel_idx, n_rows_dev)      # the struct only holds raw pointers
+    # consecutive rows per ray (dense grid, or the compacted order of select_fine): ray gradients summed in a fixed order
+    t.ray_offsets = ray_offsets.data_ptr() if ray_offsets is not None else None
+    t.ordered_ray_grads = int(sel_idx is None or ray_offsets is not None)
+    t._keep = (rays_o, rays_d, jitter, sel_idx, n_rows_dev, ray_offsets)      # the struct only holds raw pointers
     return t
 
 
@@ -661,6 +664,7 @@ def make_tc_input_enc(x_enc, dirs):
     t.smp = make_sampling(0.0, 1.0, 2, 10)
     t.n_rows = x_enc.shape[0]
     t.x_enc, t.ld_enc, t.dirs_rows = x_enc.data_ptr(), x_enc.shape[1], dirs.data_ptr()
+    t.ray_offsets, t.ordered_ray_grads = None, 0
     t._keep = (x_enc, dirs)
     return t
 

@@ -126,7 +126,7 @@ def _tc_view(cfg, net, tensors, cache):
 
 
 def _branch_fwd(cfg, net, tensors, rays_o, rays_d, jitter, S, band_w, sel_idx, n_rows, n_rows_dev, train=True,
-                cache=None):
+                cache=None, ray_offsets=None):
     """encode + MLP for one branch.  Returns (out4 [n_rows,4], saved-for-backward tuple)."""
     depth, width, skips = net
     dev = rays_o.device
@@ -136,7 +136,7 @@ def _branch_fwd(cfg, net, tensors, rays_o, rays_d, jitter, S, band_w, sel_idx, n
         # fused sampling + encoding + MLP + SH head, bf16 tcgen05 (mlp_tc_fwd.cu)
         ps = ops.make_mlp_params(tensors, depth, width, skips, in_ch=cfg.in_ch)
         tcw = _tc_weights(ps, tensors, train, cache if cache is not None else {})
-        tin = ops.make_tc_input_rays(rays_o, rays_d, jitter, smp, sel_idx, n_rows, n_rows_dev)
+        tin = ops.make_tc_input_rays(rays_o, rays_d, jitter, smp, sel_idx, n_rows, n_rows_dev, ray_offsets)
         out4 = torch.empty(n_rows, 4, device=dev)
         stash = ops.tc_stash(ps, n_rows, dev) if train else None
         ops.mlp_tc_fwd(ps, tcw, tin, out4, stash)
@@ -266,7 +266,7 @@ class RenderFn(torch.autograd.Function):
         # fine
         if n_rows > 0:
             out_sel, saved_f = _branch_fwd(cfg, net_f, run_f, rays_o, rays_d, jitter, cfg.Sf, band_w, sel_idx,
-                                           n_rows, n_rows_dev, need_grad, cache_f)
+                                           n_rows, n_rows_dev, need_grad, cache_f, offs)
         else:
             out_sel, saved_f = torch.empty(0, 4, device=dev), None
         cf = ops.make_composite_cfg(cfg.near, cfg.far, cfg.Sf, cfg.white_back)

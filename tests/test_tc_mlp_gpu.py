@@ -205,3 +205,60 @@ def test_fused_backward_launch_matches_the_two_kernel_path(depth, skips, M, monk
     for k in tensors:
         a, b = res["1"][0][k], res["0"][0][k]
         assert float((a - b).norm()) <= 2e-4 * float(b.norm()) + 1e-12, (k, rel_err(a, b))
+
+
+def test_ray_gradients_are_summed_in_a_fixed_order():
+    """rays mode with consecutive rows per ray (dense grid; compacted rows with per-ray offsets): dL/d(rays_o, rays_d) come
+    from per-segment partials reduced per ray in ascending row order - bit-identical run to run and equal (up to
+    summation order) to the atomic accumulation used when the rows of a ray are scattered."""
+    ops, p, tensors, ps, tcw = setup(8, (4,))
+    g = torch.Generator().manual_seed(33)
+    B, S = 67, 48                                    # 48 rows per ray: segments straddle the 32-row warps
+    ro = (torch.randn(B, 3, generator=g) * 0.5).to(DEV).contiguous()
+    rd = F.normalize(torch.randn(B, 3, generator=g), dim=-1).to(DEV).contiguous()
+    jit = (torch.rand(B, generator=g) * 0.1).to(DEV)
+    smp = ops.make_sampling(1.0, 8.0, S, 10)
+    n = B * S
+    gout = torch.randn(n, 4, generator=g).to(DEV).contiguous()
+
+    def run(tin):
+        out = torch.empty(tin.n_rows, 4, device=DEV)
+        stash = ops.tc_stash(ps, tin.n_rows, DEV)
+        ops.mlp_tc_fwd(ps, tcw, tin, out, stash)
+        grads = {k: torch.zeros_like(v) for k, v in tensors.items()}
+        gs = ops.fill_mlp_struct(ops.MlpGrads(), grads, 8)
+        ws = ops.tc_bwd_workspace(ps, tin.n_rows, DEV)
+        g_o, g_d = torch.zeros(B, 3, device=DEV), torch.zeros(B, 3, device=DEV)
+        ops.mlp_tc_bwd(ps, tcw, tin, out, gout[:tin.n_rows], stash, ws, gs, g_rays_o=g_o, g_rays_d=g_d)
+        torch.cuda.synchronize()
+        return g_o, g_d
+
+    dense = ops.make_tc_input_rays(ro, rd, jit, smp, None, n, None)
+    assert dense.ordered_ray_grads == 1
+    a, b = run(dense), run(dense)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    atomic = ops.make_tc_input_rays(ro, rd, jit, smp, None, n, None)
+    atomic.ordered_ray_grads = 0
+    c = run(atomic)
+    torch.testing.assert_close(a[0], c[0], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(a[1], c[1], rtol=1e-4, atol=1e-6)
+    # compacted rows (every ray keeps a different number of leading samples) with per-ray offsets
+    keep = torch.randint(0, S + 1, (B,), generator=g)
+    keep[3] = 0
+    sel = torch.cat([r * S + torch.arange(int(k)) for r, k in enumerate(keep)]).to(torch.int32).to(DEV)
+    offs = torch.cat([torch.zeros(1, dtype=torch.int64), keep.cumsum(0)]).to(torch.int32).to(DEV)
+    m = int(sel.shape[0])
+    cap = m + 19
+    sel_pad = torch.cat([sel, torch.zeros(cap - m, dtype=torch.int32, device=DEV)])
+    n_dev = torch.tensor([m], dtype=torch.int32, device=DEV)
+    gout = torch.cat([gout[:m], torch.full((cap - m, 4), float("nan"), device=DEV)]).contiguous()
+    comp = ops.make_tc_input_rays(ro, rd, jit, smp, sel_pad, cap, n_dev, ray_offsets=offs)
+    assert comp.ordered_ray_grads == 1
+    d, e = run(comp), run(comp)
+    assert torch.equal(d[0], e[0]) and torch.equal(d[1], e[1]) and bool(torch.isfinite(d[0]).all())
+    scattered = ops.make_tc_input_rays(ro, rd, jit, smp, sel_pad, cap, n_dev)
+    assert scattered.ordered_ray_grads == 0
+    f = run(scattered)
+    torch.testing.assert_close(d[0], f[0], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(d[1], f[1], rtol=1e-4, atol=1e-6)
+    assert float(d[0][3].abs().max()) == 0.0          # the ray without samples receives nothing
