@@ -310,9 +310,10 @@ def run_ours(args):
             gbs = 9504.0 * rays_rank / (comp_ms / 1e3) / 1e9
             roof["compositing"] = dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s",
                                        frac=round(gbs / peaks["hbm"], 4), kernel_ms_per_step=round(comp_ms, 4))
-    cpu = None
+    cpu, ref_gpu = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_reference(steps=2, warmup=1, rays=args.rays)
+        ref_gpu = reference_gpu_eager(rays=args.rays)
     if rank == 0:
         def side(r):
             return dict(scaling="strong" if r["strong"] else "weak", value=round(r["value"], 1), unit=UNIT,
@@ -339,7 +340,7 @@ def run_ours(args):
                     allreduce_exposed_us=m.get("allreduce_exposed_us"), ranks_identical=m["ranks_identical"],
                     other_scaling=side(other) if other else None,
                     gpu_launches=int(m["launches"]), host_issue_ms_per_step=round(m["host_issue_ms"], 3), clocks=m["clocks"],
-                    roofline=roof, cpu_baseline=cpu, loss=m["loss"])
+                    roofline=roof, cpu_baseline=cpu, reference_gpu_eager=ref_gpu, loss=m["loss"])
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -681,6 +682,54 @@ def cpu_reference(steps, warmup, rays, budget_s=None):
                 sample=f"{steps} timed train steps (after {warmup} warm-up) of {rays} rays of the same workload "
                        f"(110 cameras, 800x800, 64+128 samples, 8x256 MLPs), torch CPU fp32, {cores} threads; {what}",
                 sec_per_step=round(sec, 3))
+
+
+def reference_gpu_eager(steps=5, warmup=3, rays=RAYS):
+    """Context only: the UNMODIFIED reference modules with device_type="cuda" - PyTorch eager on
+    the same B200, same workload and step (forward -> loss -> backward -> its own RAdam).  The reference ships no CUDA
+    kernels; this is the only "existing GPU implementation" of the path."""
+    ref = reference_modules()
+    if ref is None:
+        return dict(unavailable="baseline/_ref not installed")
+    try:
+        from mc_nerf_b200 import synthetic as syn
+        dev = "cuda:0"
+        MC_Model, _, MC_NeRF_Loss, _, net_utils = ref
+        sp = syn.make_sys_param(n_cam=N_CAM, img_h=IMG, img_w=IMG, batch=rays, samples=SC, scale=SCALE, device=dev,
+                                with_images=False)
+        torch.manual_seed(42)
+        m = MC_Model(sp).to(dev)
+        with torch.no_grad():
+            for k, v in syn.init_camera_weights(sp).items():
+                getattr(m, k).copy_(v)
+        loss_fn = MC_NeRF_Loss(sp)
+        opt = net_utils.RAdam([p for p in m.parameters()], lr=5e-4, eps=1e-8, weight_decay=4e-4)
+        batch = tuple(t.to(dev) for t in syn.make_train_batch(sp, img_id=3))
+
+        def one():
+            opt.zero_grad()
+            loss_dict, _, _, _ = m(batch, 25, STAGE, RATIO)
+            loss = loss_fn(loss_dict, STAGE)
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = dict(value=round(rays / (ms / 1e3), 1), unit=UNIT, ms_per_step=round(ms, 2), steps=steps,
+                   what="unmodified reference modules (baseline/_ref), device_type=cuda, PyTorch eager fp32, same step")
+        del m, opt
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:      # noqa: BLE001 - context measurement only
+        return dict(unavailable=repr(e)[:200])
 
 
 def run_reference(args):
