@@ -269,7 +269,8 @@ def run_ours(args):
         prof, n_fine = m["prof"], m["n_fine"]
         evals = rays_rank * SC + n_fine
         mlp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_mlp_")) / 3
-        comp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_composite") or k.startswith("mcnerf_sigma2w")) / 3
+        comp_ms = sum(v for k, v in prof.items() if k.startswith(("mcnerf_composite", "mcnerf_sigma2w", "mcnerf_coarse_tail",
+                                                                  "mcnerf_fine_tail"))) / 3
         peaks = load_peaks()
         flops = 6.0 * MACS_PER_EVAL * evals          # fwd + dgrad + wgrad
         ach = flops / (mlp_ms / 1e3) / 1e12
