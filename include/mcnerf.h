@@ -157,7 +157,11 @@ int mcnerf_mlp_f32_fwd(const mcnerf_mlp_params* p, const float* x_enc, int ld_en
 int mcnerf_mlp_f32_bwd(const mcnerf_mlp_params* p, const float* x_enc, int ld_enc, const mcnerf_dirs* d,
                        int n_rows, const int32_t* n_rows_dev, const float* g_out4, void* workspace,
                        const mcnerf_mlp_grads* g, float* g_x_enc, float* g_dirs, void* stream);
-/* eval_sh (deg 2) standalone: sh [n,3,9], dirs [n,3] -> out [n,3]  (ref: model/net_utils.py:103-191) */
+/* eval_sh standalone, degree 0..4: sh [n,3,(deg+1)^2], dirs [n,3] -> out [n,3]  (ref: model/net_utils.py:103-191) */
+int mcnerf_eval_sh_deg_fwd(int deg, const float* sh, const float* dirs, int n, float* out, void* stream);
+int mcnerf_eval_sh_deg_bwd(int deg, const float* sh, const float* dirs, const float* g_out, int n, float* g_sh,
+                           float* g_dirs, void* stream);
+/* the degree-2 form (sh [n,3,9]) */
 int mcnerf_eval_sh_fwd(const float* sh, const float* dirs, int n, float* out, void* stream);
 int mcnerf_eval_sh_bwd(const float* sh, const float* dirs, const float* g_out, int n,
                        float* g_sh, float* g_dirs, void* stream);

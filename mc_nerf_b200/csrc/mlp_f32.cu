@@ -119,22 +119,75 @@ __global__ void colsum_k(const float* __restrict__ X, int64_t ld, int M, int N, 
   }
 }
 
-// ---- SH (deg 2) colour head.  ref: model/net_utils.py:154-169, model/net_block.py:75-77
+// ---- SH colour head, degrees 0-4 ((deg+1)^2 = 1, 4, 9, 16, 25 basis functions per channel).
+// ref: model/net_utils.py:103-191 (eval_sh: hard-coded real SH polynomials), model/net_block.py:63-65, 75-77
 __constant__ float kC0 = 0.28209479177387814f;
 __constant__ float kC1 = 0.4886025119029199f;
 __constant__ float kC2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
                              -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float kC3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                             -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+__constant__ float kC4[9] = {2.5033429417967046f, -1.7701307697799304f, 0.9461746957575601f, -0.6690465435572892f,
+                             0.10578554691520431f, -0.6690465435572892f, 0.47308734787878004f, -1.7701307697799304f,
+                             0.6258357354491761f};
+constexpr int SH_MAX_NB = 25;
 
-__device__ __forceinline__ void sh_basis(float x, float y, float z, float Y[9]) {
-  Y[0] = kC0; Y[1] = -kC1 * y; Y[2] = kC1 * z; Y[3] = -kC1 * x;
-  Y[4] = kC2[0] * (x * y); Y[5] = kC2[1] * (y * z); Y[6] = kC2[2] * (2.f * z * z - x * x - y * y);
-  Y[7] = kC2[3] * (x * z); Y[8] = kC2[4] * (x * x - y * y);
+// Y_b(x, y, z) for b < nb
+__device__ __forceinline__ void sh_basis(float x, float y, float z, int nb, float Y[SH_MAX_NB]) {
+  Y[0] = kC0;
+  if (nb <= 1) return;
+  Y[1] = -kC1 * y; Y[2] = kC1 * z; Y[3] = -kC1 * x;
+  if (nb <= 4) return;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  Y[4] = kC2[0] * xy; Y[5] = kC2[1] * yz; Y[6] = kC2[2] * (2.f * zz - xx - yy);
+  Y[7] = kC2[3] * xz; Y[8] = kC2[4] * (xx - yy);
+  if (nb <= 9) return;
+  Y[9] = kC3[0] * y * (3.f * xx - yy);
+  Y[10] = kC3[1] * xy * z;
+  Y[11] = kC3[2] * y * (4.f * zz - xx - yy);
+  Y[12] = kC3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+  Y[13] = kC3[4] * x * (4.f * zz - xx - yy);
+  Y[14] = kC3[5] * z * (xx - yy);
+  Y[15] = kC3[6] * x * (xx - 3.f * yy);
+  if (nb <= 16) return;
+  Y[16] = kC4[0] * xy * (xx - yy);
+  Y[17] = kC4[1] * yz * (3.f * xx - yy);
+  Y[18] = kC4[2] * xy * (7.f * zz - 1.f);
+  Y[19] = kC4[3] * yz * (7.f * zz - 3.f);
+  Y[20] = kC4[4] * (zz * (35.f * zz - 30.f) + 3.f);
+  Y[21] = kC4[5] * xz * (7.f * zz - 3.f);
+  Y[22] = kC4[6] * (xx - yy) * (7.f * zz - 1.f);
+  Y[23] = kC4[7] * xz * (xx - 3.f * yy);
+  Y[24] = kC4[8] * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy));
 }
-// d(sum_b Y_b s_b)/d(x,y,z)
-__device__ __forceinline__ void sh_basis_grad(float x, float y, float z, const float s[9], float g[3]) {
-  g[0] = -kC1 * s[3] + kC2[0] * y * s[4] - 2.f * kC2[2] * x * s[6] + kC2[3] * z * s[7] + 2.f * kC2[4] * x * s[8];
-  g[1] = -kC1 * s[1] + kC2[0] * x * s[4] + kC2[1] * z * s[5] - 2.f * kC2[2] * y * s[6] - 2.f * kC2[4] * y * s[8];
-  g[2] = kC1 * s[2] + kC2[1] * y * s[5] + 4.f * kC2[2] * z * s[6] + kC2[3] * x * s[7];
+// d(sum_b Y_b s_b)/d(x,y,z), with x, y, z independent (as autograd differentiates the polynomials)
+__device__ __forceinline__ void sh_basis_grad(float x, float y, float z, int nb, const float s[SH_MAX_NB], float g[3]) {
+  g[0] = g[1] = g[2] = 0.f;
+  if (nb <= 1) return;
+  g[0] += -kC1 * s[3]; g[1] += -kC1 * s[1]; g[2] += kC1 * s[2];
+  if (nb <= 4) return;
+  g[0] += kC2[0] * y * s[4] - 2.f * kC2[2] * x * s[6] + kC2[3] * z * s[7] + 2.f * kC2[4] * x * s[8];
+  g[1] += kC2[0] * x * s[4] + kC2[1] * z * s[5] - 2.f * kC2[2] * y * s[6] - 2.f * kC2[4] * y * s[8];
+  g[2] += kC2[1] * y * s[5] + 4.f * kC2[2] * z * s[6] + kC2[3] * x * s[7];
+  if (nb <= 9) return;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  g[0] += kC3[0] * 6.f * xy * s[9] + kC3[1] * yz * s[10] - kC3[2] * 2.f * xy * s[11] - kC3[3] * 6.f * xz * s[12] +
+          kC3[4] * (4.f * zz - 3.f * xx - yy) * s[13] + kC3[5] * 2.f * xz * s[14] + kC3[6] * (3.f * xx - 3.f * yy) * s[15];
+  g[1] += kC3[0] * (3.f * xx - 3.f * yy) * s[9] + kC3[1] * xz * s[10] + kC3[2] * (4.f * zz - xx - 3.f * yy) * s[11] -
+          kC3[3] * 6.f * yz * s[12] - kC3[4] * 2.f * xy * s[13] - kC3[5] * 2.f * yz * s[14] - kC3[6] * 6.f * xy * s[15];
+  g[2] += kC3[1] * xy * s[10] + kC3[2] * 8.f * yz * s[11] + kC3[3] * (6.f * zz - 3.f * xx - 3.f * yy) * s[12] +
+          kC3[4] * 8.f * xz * s[13] + kC3[5] * (xx - yy) * s[14];
+  if (nb <= 16) return;
+  const float t1 = 7.f * zz - 1.f, t3 = 7.f * zz - 3.f;
+  g[0] += kC4[0] * y * (3.f * xx - yy) * s[16] + kC4[1] * 6.f * xy * z * s[17] + kC4[2] * y * t1 * s[18] +
+          kC4[5] * z * t3 * s[21] + kC4[6] * 2.f * x * t1 * s[22] + kC4[7] * z * (3.f * xx - 3.f * yy) * s[23] +
+          kC4[8] * (4.f * x * xx - 12.f * x * yy) * s[24];
+  g[1] += kC4[0] * x * (xx - 3.f * yy) * s[16] + kC4[1] * z * (3.f * xx - 3.f * yy) * s[17] + kC4[2] * x * t1 * s[18] +
+          kC4[3] * z * t3 * s[19] - kC4[6] * 2.f * y * t1 * s[22] - kC4[7] * 6.f * xy * z * s[23] +
+          kC4[8] * (4.f * y * yy - 12.f * xx * y) * s[24];
+  g[2] += kC4[1] * y * (3.f * xx - yy) * s[17] + kC4[2] * 14.f * xy * z * s[18] + kC4[3] * y * (21.f * zz - 3.f) * s[19] +
+          kC4[4] * (140.f * z * zz - 60.f * z) * s[20] + kC4[5] * x * (21.f * zz - 3.f) * s[21] +
+          kC4[6] * (xx - yy) * 14.f * z * s[22] + kC4[7] * x * (xx - 3.f * yy) * s[23];
 }
 
 __device__ __forceinline__ int dir_row(const mcnerf_dirs& d, int m) {
@@ -143,27 +196,26 @@ __device__ __forceinline__ int dir_row(const mcnerf_dirs& d, int m) {
   return m;
 }
 
-__global__ void head_fwd_k(const float* __restrict__ sig, const float* __restrict__ sh, int ld_sh, mcnerf_dirs d,
+__global__ void head_fwd_k(const float* __restrict__ sig, const float* __restrict__ sh, int ld_sh, int nb, mcnerf_dirs d,
                            int n, const int32_t* __restrict__ rows_dev, float4* __restrict__ out4) {
   if (rows_dev) n = min(n, *rows_dev);
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n) return;
   int dr = dir_row(d, m);
-  float Y[9];
-  sh_basis(d.dirs[3 * dr], d.dirs[3 * dr + 1], d.dirs[3 * dr + 2], Y);
+  float Y[SH_MAX_NB];
+  sh_basis(d.dirs[3 * dr], d.dirs[3 * dr + 1], d.dirs[3 * dr + 2], nb, Y);
   const float* s = sh + (size_t)m * ld_sh;
   float c[3];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     float v = 0.f;
-#pragma unroll
-    for (int b = 0; b < 9; ++b) v += Y[b] * s[9 * ch + b];
+    for (int b = 0; b < nb; ++b) v += Y[b] * s[nb * ch + b];
     c[ch] = sigmoid_f(v);
   }
   out4[m] = make_float4(sig[m], c[0], c[1], c[2]);
 }
 
-__global__ void head_bwd_k(const float4* __restrict__ out4, const float* __restrict__ sh, int ld_sh, mcnerf_dirs d,
+__global__ void head_bwd_k(const float4* __restrict__ out4, const float* __restrict__ sh, int ld_sh, int nb, mcnerf_dirs d,
                            int n, const int32_t* __restrict__ rows_dev, const float4* __restrict__ g_out4,
                            float* __restrict__ g_sig, float* __restrict__ g_sh, float* __restrict__ g_dirs) {
   if (rows_dev) n = min(n, *rows_dev);
@@ -171,26 +223,25 @@ __global__ void head_bwd_k(const float4* __restrict__ out4, const float* __restr
   if (m >= n) return;
   int dr = dir_row(d, m);
   float x = d.dirs[3 * dr], y = d.dirs[3 * dr + 1], z = d.dirs[3 * dr + 2];
-  float Y[9];
-  sh_basis(x, y, z, Y);
+  float Y[SH_MAX_NB];
+  sh_basis(x, y, z, nb, Y);
   float4 o = out4[m], g = g_out4[m];
   g_sig[m] = g.x;
   float gc[3] = {g.y * o.y * (1.f - o.y), g.z * o.z * (1.f - o.z), g.w * o.w * (1.f - o.w)};
   const float* s = sh + (size_t)m * ld_sh;
   float* gs = g_sh + (size_t)m * ld_sh;
-  float comb[9];
+  float comb[SH_MAX_NB];
 #pragma unroll
-  for (int b = 0; b < 9; ++b) comb[b] = 0.f;
+  for (int b = 0; b < SH_MAX_NB; ++b) comb[b] = 0.f;
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch)
-#pragma unroll
-    for (int b = 0; b < 9; ++b) {
-      gs[9 * ch + b] = gc[ch] * Y[b];
-      comb[b] += gc[ch] * s[9 * ch + b];
+    for (int b = 0; b < nb; ++b) {
+      gs[nb * ch + b] = gc[ch] * Y[b];
+      comb[b] += gc[ch] * s[nb * ch + b];
     }
   if (g_dirs) {
     float gd[3];
-    sh_basis_grad(x, y, z, comb, gd);
+    sh_basis_grad(x, y, z, nb, comb, gd);
     if (d.dir_idx || d.dir_S > 0) {
       atomicAdd(g_dirs + 3 * dr, gd[0]); atomicAdd(g_dirs + 3 * dr + 1, gd[1]); atomicAdd(g_dirs + 3 * dr + 2, gd[2]);
     } else {
@@ -199,42 +250,40 @@ __global__ void head_bwd_k(const float4* __restrict__ out4, const float* __restr
   }
 }
 
-__global__ void eval_sh_fwd_k(const float* __restrict__ sh, const float* __restrict__ dirs, int n,
+__global__ void eval_sh_fwd_k(const float* __restrict__ sh, const float* __restrict__ dirs, int n, int nb,
                               float* __restrict__ out) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n) return;
-  float Y[9];
-  sh_basis(dirs[3 * m], dirs[3 * m + 1], dirs[3 * m + 2], Y);
+  float Y[SH_MAX_NB];
+  sh_basis(dirs[3 * m], dirs[3 * m + 1], dirs[3 * m + 2], nb, Y);
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     float v = 0.f;
-#pragma unroll
-    for (int b = 0; b < 9; ++b) v += Y[b] * sh[(size_t)m * 27 + 9 * ch + b];
+    for (int b = 0; b < nb; ++b) v += Y[b] * sh[(size_t)m * 3 * nb + nb * ch + b];
     out[3 * m + ch] = v;
   }
 }
 
 __global__ void eval_sh_bwd_k(const float* __restrict__ sh, const float* __restrict__ dirs,
-                              const float* __restrict__ g_out, int n, float* __restrict__ g_sh,
+                              const float* __restrict__ g_out, int n, int nb, float* __restrict__ g_sh,
                               float* __restrict__ g_dirs) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n) return;
   float x = dirs[3 * m], y = dirs[3 * m + 1], z = dirs[3 * m + 2];
-  float Y[9], comb[9];
-  sh_basis(x, y, z, Y);
+  float Y[SH_MAX_NB], comb[SH_MAX_NB];
+  sh_basis(x, y, z, nb, Y);
 #pragma unroll
-  for (int b = 0; b < 9; ++b) comb[b] = 0.f;
+  for (int b = 0; b < SH_MAX_NB; ++b) comb[b] = 0.f;
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     float g = g_out[3 * m + ch];
-#pragma unroll
-    for (int b = 0; b < 9; ++b) {
-      g_sh[(size_t)m * 27 + 9 * ch + b] = g * Y[b];
-      comb[b] += g * sh[(size_t)m * 27 + 9 * ch + b];
+    for (int b = 0; b < nb; ++b) {
+      g_sh[(size_t)m * 3 * nb + nb * ch + b] = g * Y[b];
+      comb[b] += g * sh[(size_t)m * 3 * nb + nb * ch + b];
     }
   }
   float gd[3];
-  sh_basis_grad(x, y, z, comb, gd);
+  sh_basis_grad(x, y, z, nb, comb, gd);
   g_dirs[3 * m] = gd[0]; g_dirs[3 * m + 1] = gd[1]; g_dirs[3 * m + 2] = gd[2];
 }
 
@@ -283,7 +332,8 @@ struct Plan {
   }
 };
 
-constexpr int LD_SH = 28;
+// leading dimension of the raw SH coefficient rows (3 (deg+1)^2 = 3, 12, 27, 48, 75 floats, rounded up to 4)
+inline int ld_sh_of(const mcnerf_mlp_params* p) { return (p->sh_dim + 3) / 4 * 4; }
 
 struct Workspace {
   float* h[MCNERF_MAX_DEPTH];
@@ -291,7 +341,7 @@ struct Workspace {
 };
 
 size_t ws_floats(const mcnerf_mlp_params* p, int64_t n) {
-  return (size_t)n * ((size_t)p->width * (p->depth + 4) + 2 * LD_SH + 2);
+  return (size_t)n * ((size_t)p->width * (p->depth + 4) + 2 * ld_sh_of(p) + 2);
 }
 
 Workspace carve(const mcnerf_mlp_params* p, int64_t n, void* ws) {
@@ -303,15 +353,16 @@ Workspace carve(const mcnerf_mlp_params* p, int64_t n, void* ws) {
   w.c0 = f; f += n * W;
   w.bufA = f; f += n * W;
   w.bufB = f; f += n * W;
-  w.sh = f; f += n * LD_SH;
-  w.g_sh = f; f += n * LD_SH;
+  w.sh = f; f += n * ld_sh_of(p);
+  w.g_sh = f; f += n * ld_sh_of(p);
   w.sig = f; f += n;
   w.g_sig = f; f += n;
   return w;
 }
 
 int check_params(const mcnerf_mlp_params* p) {
-  MC_ARG(p && p->depth >= 1 && p->depth <= MCNERF_MAX_DEPTH && p->width >= 1 && p->in_ch >= 3 && p->sh_dim == 27);
+  MC_ARG(p && p->depth >= 1 && p->depth <= MCNERF_MAX_DEPTH && p->width >= 1 && p->in_ch >= 3 &&
+         (p->sh_dim == 3 || p->sh_dim == 12 || p->sh_dim == 27 || p->sh_dim == 48 || p->sh_dim == 75));
   MC_ARG((p->skip_mask & 1u) == 0);
   for (int i = 0; i < p->depth; ++i) MC_ARG(p->W[i] && p->b[i]);
   MC_ARG(p->W_sigma0 && p->b_sigma0 && p->W_sigma2 && p->b_sigma2 && p->W_sh0 && p->b_sh0 && p->W_sh2 && p->b_sh2);
@@ -333,7 +384,7 @@ extern "C" int mcnerf_mlp_f32_fwd(const mcnerf_mlp_params* p, const float* x_enc
   MC_ARG(((uintptr_t)out4 & 15) == 0 && p->width % 4 == 0);
   Workspace w = carve(p, n_rows, workspace);
   Plan pl{(cudaStream_t)stream, n_rows, n_rows_dev};
-  const int W = p->width, C = p->in_ch;
+  const int W = p->width, C = p->in_ch, LD_SH = ld_sh_of(p), SHD = p->sh_dim, NB = p->sh_dim / 3;
   for (int i = 0; i < p->depth; ++i) {
     if (i == 0) {
       pl.fwd(x_enc, ld_enc, C, p->W[0], C, W, p->b[0], w.h[0], W, F_RELU);
@@ -348,9 +399,9 @@ extern "C" int mcnerf_mlp_f32_fwd(const mcnerf_mlp_params* p, const float* x_enc
   pl.fwd(h, W, W, p->W_sigma0, W, W, p->b_sigma0, w.s0, W, F_RELU);
   pl.fwd(w.s0, W, W, p->W_sigma2, W, 1, p->b_sigma2, w.sig, 1, 0);
   pl.fwd(h, W, W, p->W_sh0, W, W, p->b_sh0, w.c0, W, F_RELU);
-  pl.fwd(w.c0, W, W, p->W_sh2, W, 27, p->b_sh2, w.sh, LD_SH, 0);
+  pl.fwd(w.c0, W, W, p->W_sh2, W, SHD, p->b_sh2, w.sh, LD_SH, 0);
   if (pl.err) return pl.err;
-  head_fwd_k<<<cdiv(n_rows, 256), 256, 0, pl.st>>>(w.sig, w.sh, LD_SH, *d, n_rows, n_rows_dev, (float4*)out4);
+  head_fwd_k<<<cdiv(n_rows, 256), 256, 0, pl.st>>>(w.sig, w.sh, LD_SH, NB, *d, n_rows, n_rows_dev, (float4*)out4);
   MC_LAUNCHED();
   return 0;
 }
@@ -363,13 +414,13 @@ extern "C" int mcnerf_mlp_f32_bwd(const mcnerf_mlp_params* p, const float* x_enc
   MC_ARG(x_enc && d && d->dirs && g_out4 && workspace && g && n_rows > 0 && ld_enc >= p->in_ch);
   Workspace w = carve(p, n_rows, workspace);
   Plan pl{(cudaStream_t)stream, n_rows, n_rows_dev};
-  const int W = p->width, C = p->in_ch, D = p->depth;
+  const int W = p->width, C = p->in_ch, D = p->depth, LD_SH = ld_sh_of(p), SHD = p->sh_dim, NB = p->sh_dim / 3;
   // the forward pass left out4 unknown to us: recompute the head output from sig/sh for the sigmoid derivative
   // by re-running head_fwd into bufA's first 4 columns' worth of space (n_rows*4 floats <= n_rows*W).
   MC_ARG(W >= 4);
-  head_fwd_k<<<cdiv(n_rows, 256), 256, 0, pl.st>>>(w.sig, w.sh, LD_SH, *d, n_rows, n_rows_dev, (float4*)w.bufA);
+  head_fwd_k<<<cdiv(n_rows, 256), 256, 0, pl.st>>>(w.sig, w.sh, LD_SH, NB, *d, n_rows, n_rows_dev, (float4*)w.bufA);
   MC_LAUNCHED();
-  head_bwd_k<<<cdiv(n_rows, 256), 256, 0, pl.st>>>((const float4*)w.bufA, w.sh, LD_SH, *d, n_rows, n_rows_dev,
+  head_bwd_k<<<cdiv(n_rows, 256), 256, 0, pl.st>>>((const float4*)w.bufA, w.sh, LD_SH, NB, *d, n_rows, n_rows_dev,
                                                     (const float4*)g_out4, w.g_sig, w.g_sh, g_dirs);
   MC_LAUNCHED();
   const float* h = w.h[D - 1];
@@ -381,9 +432,9 @@ extern "C" int mcnerf_mlp_f32_bwd(const mcnerf_mlp_params* p, const float* x_enc
   pl.bgrad(w.bufA, W, W, g->b_sigma0);
   pl.dgrad(w.bufA, W, W, p->W_sigma0, W, W, w.bufB, W, nullptr, 0, 0);          // d_h (partial, unmasked)
   // colour branch
-  pl.wgrad(w.g_sh, LD_SH, 27, w.c0, W, W, g->W_sh2, W);
-  pl.bgrad(w.g_sh, LD_SH, 27, g->b_sh2);
-  pl.dgrad(w.g_sh, LD_SH, 27, p->W_sh2, W, W, w.bufA, W, w.c0, W, 0);           // d_c0
+  pl.wgrad(w.g_sh, LD_SH, SHD, w.c0, W, W, g->W_sh2, W);
+  pl.bgrad(w.g_sh, LD_SH, SHD, g->b_sh2);
+  pl.dgrad(w.g_sh, LD_SH, SHD, p->W_sh2, W, W, w.bufA, W, w.c0, W, 0);          // d_c0
   pl.wgrad(w.bufA, W, W, h, W, W, g->W_sh0, W);
   pl.bgrad(w.bufA, W, W, g->b_sh0);
   pl.dgrad(w.bufA, W, W, p->W_sh0, W, W, w.bufB, W, h, W, F_ACCUM);             // d_h total, masked by h > 0
@@ -412,19 +463,28 @@ extern "C" int mcnerf_mlp_f32_bwd(const mcnerf_mlp_params* p, const float* x_enc
   return pl.err;
 }
 
-extern "C" int mcnerf_eval_sh_fwd(const float* sh, const float* dirs, int n, float* out, void* stream) {
-  MC_ARG(sh && dirs && out && n >= 0);
+extern "C" int mcnerf_eval_sh_deg_fwd(int deg, const float* sh, const float* dirs, int n, float* out, void* stream) {
+  MC_ARG(deg >= 0 && deg <= 4 && sh && dirs && out && n >= 0);
   if (n == 0) return 0;
-  eval_sh_fwd_k<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(sh, dirs, n, out);
+  eval_sh_fwd_k<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(sh, dirs, n, (deg + 1) * (deg + 1), out);
   MC_LAUNCHED();
   return 0;
 }
 
-extern "C" int mcnerf_eval_sh_bwd(const float* sh, const float* dirs, const float* g_out, int n, float* g_sh,
-                                  float* g_dirs, void* stream) {
-  MC_ARG(sh && dirs && g_out && g_sh && g_dirs && n >= 0);
+extern "C" int mcnerf_eval_sh_deg_bwd(int deg, const float* sh, const float* dirs, const float* g_out, int n, float* g_sh,
+                                      float* g_dirs, void* stream) {
+  MC_ARG(deg >= 0 && deg <= 4 && sh && dirs && g_out && g_sh && g_dirs && n >= 0);
   if (n == 0) return 0;
-  eval_sh_bwd_k<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(sh, dirs, g_out, n, g_sh, g_dirs);
+  eval_sh_bwd_k<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(sh, dirs, g_out, n, (deg + 1) * (deg + 1), g_sh, g_dirs);
   MC_LAUNCHED();
   return 0;
+}
+
+extern "C" int mcnerf_eval_sh_fwd(const float* sh, const float* dirs, int n, float* out, void* stream) {
+  return mcnerf_eval_sh_deg_fwd(2, sh, dirs, n, out, stream);
+}
+
+extern "C" int mcnerf_eval_sh_bwd(const float* sh, const float* dirs, const float* g_out, int n, float* g_sh,
+                                  float* g_dirs, void* stream) {
+  return mcnerf_eval_sh_deg_bwd(2, sh, dirs, g_out, n, g_sh, g_dirs, stream);
 }

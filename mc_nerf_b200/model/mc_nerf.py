@@ -479,6 +479,7 @@ class NeRF_Model(nn.Module):
         if (model_coarse.cfg(), model_fine.cfg()) != (cfg.coarse, cfg.fine):
             cfg = render.RenderCfg(cfg.near, cfg.far, cfg.Sc, cfg.scale, cfg.n_freqs, cfg.white_back, cfg.sigma_default,
                                    cfg.thresh, model_coarse.cfg(), model_fine.cfg(), cfg.precision, cfg.device_rng)
+            cfg.sh_dim = self.render_cfg.sh_dim
         _, rgb_f, depth_f, opa_f = render.render(cfg, model_coarse.param_dict(), model_fine.param_dict(),
                                                  rays_d, rays_o, False, band_w, rng, None)
         return rgb_f, depth_f, opa_f

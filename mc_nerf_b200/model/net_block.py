@@ -33,8 +33,9 @@ class SinCosEmbedding(nn.Module):
 
 
 class CorseFine_NeRF(nn.Module):
-    """D x W ReLU MLP with one input skip, sigma head (W->W->1) and SH head (W->W->27) -> (sigma_raw, rgb).
-    ref: model/net_block.py:37-78.  Submodule and parameter names match the reference's state_dict."""
+    """D x W ReLU MLP with one input skip, sigma head (W->W->1) and SH head (W->W->3 (MLP_deg+1)^2) -> (sigma_raw, rgb).
+    ref: model/net_block.py:37-78.  Submodule and parameter names match the reference's state_dict.  MLP_deg = 2 (the
+    shipped value) runs on the tcgen05 path; other degrees on the fp32 kernels."""
 
     def __init__(self, sys_params, type="coarse"):
         super().__init__()
@@ -43,8 +44,8 @@ class CorseFine_NeRF(nn.Module):
         self.depth = sys_params[f"{type}_MLP_depth"]
         self.width = sys_params[f"{type}_MLP_width"]
         self.skips = sys_params[f"{type}_MLP_skip"]
-        if self.deg != 2:
-            raise NotImplementedError("libmcnerf implements the SH colour head for MLP_deg = 2 (the reference default)")
+        if not 0 <= self.deg <= 4:
+            raise ValueError("MLP_deg must be 0..4 (the degrees eval_sh implements, ref: model/net_utils.py:150)")
         for i in range(self.depth):
             if i == 0:
                 k = self.in_channels_xyz

@@ -12,22 +12,17 @@ from mc_nerf_b200._lib import lib
 
 
 def eval_sh(deg, sh, dirs):
-    """Real spherical harmonics (degree <= 2) dotted with coefficients.
-    sh [..., C, (deg+1)^2], dirs [..., 3] -> [..., C].  ref: model/net_utils.py:103-191.
-    Degrees 0 and 1 use the degree-2 kernel with zero-padded coefficients; the reference's degree 3-4
-    branches are not used by any shipped config and are not implemented."""
+    """Real spherical harmonics of degree 0..4 dotted with coefficients.
+    sh [..., C, (deg+1)^2], dirs [..., 3] -> [..., C].  ref: model/net_utils.py:103-191 (the same hard-coded polynomials
+    and constants, evaluated by one kernel; gradients flow into the coefficients and the directions)."""
     assert 0 <= deg <= 4
     assert (deg + 1) ** 2 == sh.shape[-1]
-    if deg > 2:
-        raise NotImplementedError("eval_sh: libmcnerf implements SH degree <= 2 (config.yaml MLP_deg: 2)")
     if sh.shape[-2] != 3:
-        raise NotImplementedError("eval_sh: 3 colour channels expected")
+        raise NotImplementedError("eval_sh: libmcnerf evaluates 3 colour channels (the reference's only use)")
     lead = sh.shape[:-2]
     sh2 = sh.reshape(-1, 3, sh.shape[-1])
-    if deg < 2:
-        sh2 = torch.cat([sh2, sh2.new_zeros(sh2.shape[0], 3, 9 - sh2.shape[-1])], -1)
     d2 = dirs.expand(*lead, 3).reshape(-1, 3)
-    return ops.EvalSHFn.apply(sh2, d2).reshape(*lead, 3)
+    return ops.EvalSHFn.apply(sh2, d2, deg).reshape(*lead, 3)
 
 
 class RAdam(Optimizer):

@@ -334,8 +334,10 @@ def fill_mlp_struct(struct, tensors, depth):
     return struct
 
 
-def make_mlp_params(tensors, depth, width, skips, in_ch=63, sh_dim=27):
+def make_mlp_params(tensors, depth, width, skips, in_ch=63, sh_dim=None):
     p = MlpParams()
+    if sh_dim is None:       # 3 (MLP_deg + 1)^2 output rows of the colour head (ref: model/net_block.py:63-65)
+        sh_dim = int(tensors["sh.2.bias"].numel())
     p.depth, p.width, p.in_ch, p.sh_dim = depth, width, in_ch, sh_dim
     p.skip_mask = sum(1 << int(s) for s in skips if 0 < int(s) < depth)
     return fill_mlp_struct(p, tensors, depth)
@@ -395,23 +397,25 @@ class MLPFn(torch.autograd.Function):
 
 
 class EvalSHFn(torch.autograd.Function):
-    """eval_sh(deg=2): sh [n,3,9], dirs [n,3] -> [n,3].  ref: model/net_utils.py:103-191."""
+    """eval_sh(deg): sh [n,3,(deg+1)^2], dirs [n,3] -> [n,3], deg 0..4.  ref: model/net_utils.py:103-191."""
 
     @staticmethod
-    def forward(ctx, sh, dirs):
+    def forward(ctx, sh, dirs, deg=2):
         sh, dirs = _f32(sh), _f32(dirs)
         n = dirs.shape[0]
         out = torch.empty(n, 3, device=sh.device)
-        lib().call("mcnerf_eval_sh_fwd", _p(sh), _p(dirs), n, _p(out), _stream())
+        lib().call("mcnerf_eval_sh_deg_fwd", int(deg), _p(sh), _p(dirs), n, _p(out), _stream())
         ctx.save_for_backward(sh, dirs)
+        ctx.deg = int(deg)
         return out
 
     @staticmethod
     def backward(ctx, g):
         sh, dirs = ctx.saved_tensors
         g_sh, g_d = torch.empty_like(sh), torch.empty_like(dirs)
-        lib().call("mcnerf_eval_sh_bwd", _p(sh), _p(dirs), _p(_f32(g)), dirs.shape[0], _p(g_sh), _p(g_d), _stream())
-        return g_sh, g_d
+        lib().call("mcnerf_eval_sh_deg_bwd", ctx.deg, _p(sh), _p(dirs), _p(_f32(g)), dirs.shape[0], _p(g_sh), _p(g_d),
+                   _stream())
+        return g_sh, g_d, None
 
 # --------------------------------------------------------------------------- compositing / selection
 

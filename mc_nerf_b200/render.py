@@ -44,6 +44,7 @@ class RenderCfg:
         # generator: same distributions as the reference's uniform_/randn draws, not the same values);
         # False: torch.rand / torch.randn in the reference's order (draw-for-draw replay, tests)
         self.device_rng = bool(device_rng)
+        self.sh_dim = 27                           # 3 (MLP_deg + 1)^2; from_sys_param sets it
 
     @staticmethod
     def from_sys_param(sp, precision=None):
@@ -55,10 +56,12 @@ class RenderCfg:
         # `noise_sampler` ("device" | "torch") follows `pixel_sampler` unless given: "device" is the package default
         device_rng = sp.get("noise_sampler", "torch" if sp.get("pixel_sampler", "device") == "randperm" else "device") \
             == "device" and str(sp.get("device_type", "cuda")).startswith("cuda")
-        return RenderCfg(sp["near"], sp["far"], sp["samples"], sp["scale"], sp["emb_freqs_xyz"], sp["white_back"],
-                         sp["sigma_default"], sp["sample_weight_thresh"],
-                         (sp["coarse_MLP_depth"], sp["coarse_MLP_width"], tuple(sp["coarse_MLP_skip"])),
-                         (sp["fine_MLP_depth"], sp["fine_MLP_width"], tuple(sp["fine_MLP_skip"])), precision, device_rng)
+        cfg = RenderCfg(sp["near"], sp["far"], sp["samples"], sp["scale"], sp["emb_freqs_xyz"], sp["white_back"],
+                        sp["sigma_default"], sp["sample_weight_thresh"],
+                        (sp["coarse_MLP_depth"], sp["coarse_MLP_width"], tuple(sp["coarse_MLP_skip"])),
+                        (sp["fine_MLP_depth"], sp["fine_MLP_width"], tuple(sp["fine_MLP_skip"])), precision, device_rng)
+        cfg.sh_dim = 3 * (int(sp.get("MLP_deg", 2)) + 1) ** 2
+        return cfg
 
 
 def _owner_cache(params):
@@ -103,11 +106,13 @@ def prefetch_weights(cfg, params_c, params_f, need_bwd=True):
         tcw.prefetch(ps, tensors, need_bwd, side)
 
 
-def use_tc(cfg, net):
+def use_tc(cfg, net, tensors=None):
     """bf16 tcgen05 path when asked for and the network shape is one the tensor-core kernels implement: width 256
     natively, narrower networks through a zero-padded 256-wide shadow (ops.PaddedNet)."""
     depth, width, skips = net
     if width != ops.TC_WIDTH and os.environ.get("MCNERF_TC_PAD", "1") == "0":      # A/B switch for measurements
+        return False
+    if getattr(cfg, "sh_dim", 27) != 27:           # the tensor-core SH epilogue is specialised for MLP_deg = 2
         return False
     return (cfg.precision == "bf16" and 8 <= width <= ops.TC_WIDTH and cfg.n_freqs == 10 and 2 <= depth <= 12
             and len([s for s in skips if 0 < s < depth]) <= 1)

@@ -146,6 +146,38 @@ def eval_sh_deg2(sh, dirs):
     return res
 
 
+SH_C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+         1.445305721320277, -0.5900435899266435]
+SH_C4 = [2.5033429417967046, -1.7701307697799304, 0.9461746957575601, -0.6690465435572892, 0.10578554691520431,
+         -0.6690465435572892, 0.47308734787878004, -1.7701307697799304, 0.6258357354491761]
+
+
+def eval_sh(deg, sh, dirs):
+    """sh [M,3,(deg+1)^2], dirs [M,3] -> [M,3], degree 0..4.  model/net_utils.py:103-191 (every branch)."""
+    res = SH_C0 * sh[..., 0]
+    if deg > 0:
+        x, y, z = dirs[..., 0:1], dirs[..., 1:2], dirs[..., 2:3]
+        res = res - SH_C1 * y * sh[..., 1] + SH_C1 * z * sh[..., 2] - SH_C1 * x * sh[..., 3]
+    if deg > 1:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        res = (res + SH_C2[0] * xy * sh[..., 4] + SH_C2[1] * yz * sh[..., 5]
+               + SH_C2[2] * (2.0 * zz - xx - yy) * sh[..., 6]
+               + SH_C2[3] * xz * sh[..., 7] + SH_C2[4] * (xx - yy) * sh[..., 8])
+    if deg > 2:
+        res = (res + SH_C3[0] * y * (3 * xx - yy) * sh[..., 9] + SH_C3[1] * xy * z * sh[..., 10]
+               + SH_C3[2] * y * (4 * zz - xx - yy) * sh[..., 11]
+               + SH_C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * sh[..., 12]
+               + SH_C3[4] * x * (4 * zz - xx - yy) * sh[..., 13]
+               + SH_C3[5] * z * (xx - yy) * sh[..., 14] + SH_C3[6] * x * (xx - 3 * yy) * sh[..., 15])
+    if deg > 3:
+        res = (res + SH_C4[0] * xy * (xx - yy) * sh[..., 16] + SH_C4[1] * yz * (3 * xx - yy) * sh[..., 17]
+               + SH_C4[2] * xy * (7 * zz - 1) * sh[..., 18] + SH_C4[3] * yz * (7 * zz - 3) * sh[..., 19]
+               + SH_C4[4] * (zz * (35 * zz - 30) + 3) * sh[..., 20] + SH_C4[5] * xz * (7 * zz - 3) * sh[..., 21]
+               + SH_C4[6] * (xx - yy) * (7 * zz - 1) * sh[..., 22] + SH_C4[7] * xz * (xx - 3 * yy) * sh[..., 23]
+               + SH_C4[8] * (xx * (xx - 3 * yy) - yy * (3 * xx - yy)) * sh[..., 24])
+    return res
+
+
 def mlp_forward(params, x_enc, dirs, depth, skips, deg=2):
     """CorseFine_NeRF.forward.  model/net_block.py:67-78.
     `params` maps the reference's state_dict names ('xyz_encoding_1.0.weight', 'sigma.0.bias',
@@ -159,8 +191,7 @@ def mlp_forward(params, x_enc, dirs, depth, skips, deg=2):
     sigma = F.linear(s, params["sigma.2.weight"], params["sigma.2.bias"])
     c = F.relu(F.linear(h, params["sh.0.weight"], params["sh.0.bias"]))
     sh = F.linear(c, params["sh.2.weight"], params["sh.2.bias"])
-    assert deg == 2
-    rgb = torch.sigmoid(eval_sh_deg2(sh.reshape(-1, 3, 9), dirs))
+    rgb = torch.sigmoid(eval_sh(deg, sh.reshape(-1, 3, (deg + 1) ** 2), dirs))
     return torch.cat([sigma, rgb], -1)
 
 

@@ -302,6 +302,38 @@ def make_cam_stage():
                 g_mlp_none=all(v is None for k, v in grads.items() if k.startswith("nerf.")))
 
 
+def make_sh_degrees():
+    """eval_sh for every degree the reference implements (0..4, model/net_utils.py:103-191) with autograd gradients, and a
+    CorseFine_NeRF with MLP_deg = 3 (model/net_block.py:63-65, 75-77: SH head of 3 * 16 coefficients), fwd + bwd."""
+    g = torch.Generator().manual_seed(17)
+    n = 33
+    fx = {}
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    for deg in range(5):
+        sh = torch.randn(n, 3, (deg + 1) ** 2, generator=g).requires_grad_(True)
+        dd = d.clone().requires_grad_(True)
+        out = net_utils.eval_sh(deg, sh, dd)
+        gout = torch.randn(n, 3, generator=g)
+        out.backward(gout)
+        fx[deg] = dict(sh=sh.detach().clone(), dirs=d, out=out.detach(), gout=gout, g_sh=sh.grad.clone(),
+                       g_dirs=(dd.grad.clone() if dd.grad is not None else torch.zeros_like(d)))
+    sp = syn.make_sys_param(n_cam=4, img_h=8, img_w=8, batch=8, samples=8, scale=2, coarse=(3, 64, (1,)), fine=(3, 64, (1,)),
+                            deg=3)
+    p = orc.init_mlp_params(3, 64, (1,), deg=3, seed=5)
+    net = net_block.CorseFine_NeRF(sp, type="coarse")
+    net.load_state_dict(p)
+    x = (torch.rand(n, 3, generator=g) - 0.5) * 6
+    xe = orc.sincos_encode(x, 10).requires_grad_(True)
+    dd = d.clone().requires_grad_(True)
+    out = net(xe, dd)
+    gout = torch.randn(out.shape, generator=g)
+    out.backward(gout)
+    fx["mlp_deg3"] = dict(cfg=(3, 64, (1,)), seed=5, x_enc=xe.detach().clone(), dirs=d, out=out.detach(), gout=gout,
+                          g_x=xe.grad.clone(), g_dirs=dd.grad.clone(),
+                          g_params={k: v.grad.clone() for k, v in net.named_parameters()})
+    return fx
+
+
 def make_radam():
     """Trajectory of the reference's RAdam (model/net_utils.py:10-101) over 14 steps: crosses the N_sma >= 5
     switch (step 6) and wraps the 10-slot step-size cache."""
@@ -329,6 +361,8 @@ if __name__ == "__main__":
             torch.save(make_cfg2(), os.path.join(HERE, "cfg2.pt"))
         if "cfg2_bf16emu" in only:
             torch.save(make_cfg2_bf16emu(), os.path.join(HERE, "cfg2_bf16emu.pt"))
+        if "sh_degrees" in only:
+            torch.save(make_sh_degrees(), os.path.join(HERE, "sh_degrees.pt"))
         if "cam_stage" in only:
             torch.save(make_cam_stage(), os.path.join(HERE, "cam_stage.pt"))
         sys.exit(0)
@@ -342,5 +376,6 @@ if __name__ == "__main__":
     torch.save(make_cfg2(), os.path.join(HERE, "cfg2.pt"))
     torch.save(make_cam_stage(), os.path.join(HERE, "cam_stage.pt"))
     torch.save(make_cfg2_bf16emu(), os.path.join(HERE, "cfg2_bf16emu.pt"))
+    torch.save(make_sh_degrees(), os.path.join(HERE, "sh_degrees.pt"))
     for f in ("modules.pt", "tiny.pt", "tiny_ft.pt", "cfg1.pt", "cfg2.pt", "cam_stage.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

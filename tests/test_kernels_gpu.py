@@ -392,3 +392,39 @@ def test_fused_camera_model_equals_the_separate_kernels():
                 assert ga is None and gb is None
             else:
                 close(ga, gb, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3, 4])
+def test_eval_sh_every_degree_matches_reference(deg):
+    """model.net_utils.eval_sh for the degrees the reference implements (0..4), values and gradients w.r.t. the
+    coefficients and the directions, against the unmodified reference's autograd (tests/golden/sh_degrees.pt)."""
+    from mc_nerf_b200.model.net_utils import eval_sh
+    f = load_golden("sh_degrees.pt")[deg]
+    sh = f["sh"].to(DEV).requires_grad_(True)
+    d = f["dirs"].to(DEV).requires_grad_(True)
+    out = eval_sh(deg, sh, d)
+    close(out, f["out"], rtol=1e-5, atol=1e-6)
+    out.backward(f["gout"].to(DEV))
+    close(sh.grad, f["g_sh"], rtol=1e-5, atol=1e-6)
+    close(d.grad, f["g_dirs"], rtol=1e-4, atol=2e-6)
+
+
+def test_network_with_sh_degree_3_matches_reference():
+    """CorseFine_NeRF with MLP_deg = 3 (48 SH coefficients; ref: model/net_block.py:63-65, 75-77) on the fp32 kernels:
+    forward, input gradients and every parameter gradient against the unmodified reference."""
+    from mc_nerf_b200.model.net_block import CorseFine_NeRF
+    f = load_golden("sh_degrees.pt")["mlp_deg3"]
+    dep, wid, skips = f["cfg"]
+    sp = syn.make_sys_param(n_cam=4, img_h=8, img_w=8, batch=8, samples=8, scale=2, coarse=(dep, wid, skips),
+                            fine=(dep, wid, skips), deg=3, device=DEV)
+    net = CorseFine_NeRF(sp, type="coarse").to(DEV)
+    net.load_state_dict(orc.init_mlp_params(dep, wid, skips, deg=3, seed=f["seed"]))
+    x = f["x_enc"].to(DEV).requires_grad_(True)
+    d = f["dirs"].to(DEV).requires_grad_(True)
+    out = net(x, d)
+    close(out, f["out"], rtol=1e-4, atol=1e-5)
+    out.backward(f["gout"].to(DEV))
+    close(x.grad, f["g_x"], rtol=1e-3, atol=1e-5)
+    close(d.grad, f["g_dirs"], rtol=1e-3, atol=1e-5)
+    for k, v in net.named_parameters():
+        close(v.grad, f["g_params"][k], rtol=1e-3, atol=1e-5)

@@ -213,3 +213,27 @@ def test_philox_known_answers_and_sampler_oracle_properties():
     assert a.shape == (512,) and len(np.unique(a)) == 512 and a.min() >= 0 and a.max() < 10000
     assert not np.array_equal(a, b)
     assert sorted(orc.sample_pixels(37, 100, 5, 6).tolist()) == list(range(37))
+
+
+def test_eval_sh_all_degrees_and_deg3_network():
+    """eval_sh degrees 0..4 and a CorseFine_NeRF with MLP_deg = 3 (ref: model/net_utils.py:103-191, net_block.py:63-77)."""
+    fx = load_golden("sh_degrees.pt")
+    for deg in range(5):
+        f = fx[deg]
+        sh, d = f["sh"].clone().requires_grad_(True), f["dirs"].clone().requires_grad_(True)
+        out = orc.eval_sh(deg, sh, d)
+        close(out, f["out"])
+        out.backward(f["gout"])
+        close(sh.grad, f["g_sh"])
+        close(d.grad if d.grad is not None else torch.zeros_like(f["dirs"]), f["g_dirs"], rtol=1e-5, atol=1e-6)
+    f = fx["mlp_deg3"]
+    dep, wid, skips = f["cfg"]
+    p = {k: v.clone().requires_grad_(True) for k, v in orc.init_mlp_params(dep, wid, skips, deg=3, seed=f["seed"]).items()}
+    x, d = f["x_enc"].clone().requires_grad_(True), f["dirs"].clone().requires_grad_(True)
+    out = orc.mlp_forward(p, x, d, dep, skips, deg=3)
+    close(out, f["out"])
+    out.backward(f["gout"])
+    close(x.grad, f["g_x"], rtol=1e-4, atol=1e-6)
+    close(d.grad, f["g_dirs"], rtol=1e-4, atol=1e-6)
+    for k, v in p.items():
+        close(v.grad, f["g_params"][k], rtol=1e-4, atol=1e-6)
