@@ -412,6 +412,7 @@ def test_eval_sh_every_degree_matches_reference(deg):
 def test_network_with_sh_degree_3_matches_reference():
     """CorseFine_NeRF with MLP_deg = 3 (48 SH coefficients; ref: model/net_block.py:63-65, 75-77) on the fp32 kernels:
     forward, input gradients and every parameter gradient against the unmodified reference."""
+    from mc_nerf_b200 import synthetic as syn
     from mc_nerf_b200.model.net_block import CorseFine_NeRF
     f = load_golden("sh_degrees.pt")["mlp_deg3"]
     dep, wid, skips = f["cfg"]
