@@ -291,6 +291,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------ A operand from TENSOR MEMORY (".ts" form)
+// D[tmem] (+)= A[tmem] * B[smem]: A is K-major only, row = TMEM lane, one 32-bit column holds the bf16 pair
+// (k even in the low half, k odd in the high half) - a K=16 step reads 8 columns.  cta_group::2: each CTA of the pair
+// holds its own 128 rows of A in its own tensor memory at the same address (pinned by tests/test_tc_gpu.py).
+__device__ __forceinline__ void umma2_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// registers -> TMEM: thread i of the warp writes lane (base_lane + i), 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // relu + round-to-nearest bf16 pack in ONE instruction (negative / NaN inputs clamp to +0)
 __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
   uint32_t r;

@@ -204,7 +204,121 @@ tc_selftest2_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restr
   if (warp == 0) tc::tmem_dealloc2(tmem, 256);
 }
 
+// CTA-pair product with the A operand in TENSOR MEMORY: D[256,N] = A[256,K] * B[N,K]^T.  Each CTA writes its 128 rows
+// of A (bf16 pairs, row = lane) into columns [256, 256 + K/2) of its tensor memory with tcgen05.st and stages its N/2
+// rows of B in shared memory; the leader issues K/16 .ts MMAs per pass.  n_split = 2 runs the product as two N/2-wide
+// passes into column halves of the accumulator (the schedule of a kernel that drains one half while the other is
+// being computed).  bg > 0: warps 4-7 keep tcgen05.ld/st traffic on columns [384, 512) going meanwhile (port probe).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
+tc_selftest_ts_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int N, int K,
+                 int n_split, int reps, int bg, long long* cycles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t rank = tc::cluster_ctarank();
+  const int NH = N / 2;                 // rows of B in this CTA
+  const int NP = NH / n_split;          // ... per pass
+  uint8_t* sB = smem;                   // n_split images of [NP x K]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // pass h of the pair covers D columns [h*N/n_split, +N/n_split): this CTA supplies B rows h*(N/n_split) + rank*NP + r
+  for (int i = tid; i < NH * K; i += blockDim.x) {
+    int rr = i / K, k = i % K, h = rr / NP, r = rr % NP;
+    *reinterpret_cast<__nv_bfloat16*>(sB + (size_t)h * NP * K * 2 + canon_off(r, k, NP)) =
+        B[(size_t)(h * (N / n_split) + rank * NP + r) * K + k];
+  }
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+  }
+  if (warp == 0) tc::tmem_alloc2(&tmem_base, 512);
+  tc::fence_proxy_async();
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (warp < 4) {
+    const int row = warp * 32 + lane;
+    const __nv_bfloat16* arow = A + (size_t)(rank * 128 + row) * K;
+    for (int c = 0; c < K / 2; c += 8) {
+      uint32_t w[8];
+      for (int j = 0; j < 8; ++j) {
+        uint32_t lo = __bfloat16_as_ushort(arow[2 * (c + j)]), hi = __bfloat16_as_ushort(arow[2 * (c + j) + 1]);
+        w[j] = lo | (hi << 16);
+      }
+      tc::tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c, w);
+    }
+    tc::tmem_st_wait();
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::cluster_sync();
+  tc::tcgen05_fence_after();
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = tc::umma_idesc_bf16(256, N / n_split);
+    const uint32_t hi = tc::umma_desc_hi(128);
+    const uint32_t b_inc = (2 * NP * 16) >> 4;
+    const int nk = K / 16;
+    const long long t0 = clock64();
+    for (int rep = 0; rep < reps; ++rep)
+      for (int h = 0; h < n_split; ++h) {
+        uint32_t b_lo = tc::umma_desc_lo(tc::smem_u32(sB + (size_t)h * NP * K * 2), NP * 16);
+        uint32_t a_t = tmem + 256;
+        const uint32_t d_t = tmem + h * (N / n_split);
+        tc::umma2_bf16_ts(d_t, a_t, b_lo, hi, idesc, rep > 0);
+#pragma unroll 4
+        for (int k = 1; k < nk; ++k) {
+          a_t += 8; b_lo += b_inc;
+          tc::umma2_bf16_ts(d_t, a_t, b_lo, hi, idesc, true);
+        }
+      }
+    tc::umma2_commit_multicast_addr(tc::smem_u32(&bar), (uint16_t)3);
+    const long long t1 = clock64();
+    tc::mbar_wait(&bar, 0);
+    if (cycles) { cycles[0] = t1 - t0; cycles[1] = clock64() - t0; }
+  }
+  if (warp >= 4 && bg > 0) {
+    const uint32_t t = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384;
+    for (int i = 0; i < bg; ++i) {
+      uint32_t v[32];
+      tc::tmem_ld32(t + (i & 3) * 32, v);
+      tc::tmem_ld_wait();
+      uint32_t w[8];
+      for (int j = 0; j < 8; ++j) w[j] = v[j] + v[j + 8] + v[j + 16] + v[j + 24];
+      tc::tmem_st8(t + (i & 3) * 32, w);
+      tc::tmem_st8(t + (i & 3) * 32 + 8, w);
+    }
+    tc::tmem_st_wait();
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::tcgen05_fence_after();
+  if (warp < 4) {
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t v[32];
+      tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tc::tmem_ld_wait();
+      for (int j = 0; j < 32 && c0 + j < N; ++j) D[(size_t)(rank * 128 + row) * N + c0 + j] = __uint_as_float(v[j]);
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::cluster_sync();
+  if (warp == 0) tc::tmem_dealloc2(tmem, 512);
+}
+
 }  // namespace
+
+extern "C" int mcnerf_tc_selftest_ts(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int n_split, int reps,
+                                     int bg, long long* cycles_out, void* stream) {
+  MC_ARG(A_bf16 && B_bf16 && D && N >= 64 && N <= 256 && N % 64 == 0 && K >= 16 && K <= 256 && K % 16 == 0 && reps >= 1);
+  MC_ARG(n_split == 1 || n_split == 2);
+  size_t smem = (size_t)(N / 2) * K * 2;
+  MC_CUDA(cudaFuncSetAttribute(tc_selftest_ts_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest_ts_k<<<2, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A_bf16, (const __nv_bfloat16*)B_bf16, D, N, K,
+                                                            n_split, reps, bg, cycles_out);
+  MC_LAUNCHED();
+  return 0;
+}
 
 extern "C" int mcnerf_tc_selftest2(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int reps,
                                    long long* cycles_out, const float* bias, void* stream) {

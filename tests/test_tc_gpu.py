@@ -67,3 +67,21 @@ def test_cta_pair_tile(N, K):
                ops._p(bias), ops._stream())
     torch.cuda.synchronize()
     assert (D2 - D - bias[None, :]).abs().max().item() < 2e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,K,n_split", [(256, 256, 1), (256, 256, 2), (128, 64, 1), (64, 16, 1), (256, 32, 2)])
+def test_cta_pair_tile_with_the_a_operand_in_tensor_memory(N, K, n_split):
+    """tcgen05.mma with A read from TMEM (row = lane, one 32-bit column = bf16 pair k even | k odd << 16), cta_group::2,
+    whole-N and two-half-N passes: D = A B^T."""
+    from mc_nerf_b200 import ops
+    from mc_nerf_b200._lib import lib
+    g = torch.Generator().manual_seed(7 + N + K)
+    A = torch.randn(256, K, generator=g).to(DEV).bfloat16()
+    B = torch.randn(N, K, generator=g).to(DEV).bfloat16()
+    D = torch.full((256, N), float("nan"), device=DEV)
+    lib().call("mcnerf_tc_selftest_ts", ops._p(A, torch.bfloat16), ops._p(B, torch.bfloat16), ops._p(D), N, K, n_split, 1, 0,
+               None, ops._stream())
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    assert (D - ref).abs().max().item() < 1e-2
