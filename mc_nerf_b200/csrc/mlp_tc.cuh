@@ -1,5 +1,6 @@
 // Shared definitions of the bf16 tcgen05 NeRF-MLP kernels (forward, backward chain, weight gradients).
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -109,5 +110,17 @@ __host__ __device__ inline uint32_t stash_off(int row, int kg, int n_planes) {
 }
 
 int build_layout(const mcnerf_mlp_params* p, PackLayout* L);
+
+// Which forward kernel runs: the first generation (activation tile in shared memory, mlp_tc_fwd_k) or the second (A operand
+// in tensor memory, mlp_tc_fwd2.cuh).  The packed forward image holds both layouts back to back (wf_bytes each).
+// MCNERF_FWD_V2: 0 = never, 1 = training launches only, 2 = all launches.  Read once.
+inline int fwd_v2_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MCNERF_FWD_V2");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 
 }  // namespace mlptc

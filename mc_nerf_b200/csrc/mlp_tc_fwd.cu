@@ -123,7 +123,7 @@ int build_layout(const mcnerf_mlp_params* p, PackLayout* L) {
 
 // One launch packs every matrix of a network: a table of jobs, each thread resolves its job by a linear scan
 // over the (<= 48) element-count prefixes.
-constexpr int MAX_PACK_JOBS = 64;
+constexpr int MAX_PACK_JOBS = 96;
 struct PackJob {
   const float* src;
   int64_t sn, sk;          // source strides of the (n, k) indices (floats); bias jobs: unused
@@ -131,6 +131,9 @@ struct PackJob {
   int pad_k, pad_n, n_valid, k_valid;
   int pair;                // 1: CTA-pair layout (forward images); 2: bias block of a forward image (src = bias[n]):
                            //    rows n, 16 k: k=0 bf16(b), k=1 bf16(b - bf16(b)), rest 0 - multiplied by the ones operand
+                           // 3 / 4: the same two for the second-generation forward kernel (mlp_tc_fwd2.cuh): per step
+                           //    [pass h][CTA rank][K/8 weight planes + 2 bias planes][NP rows][16 B], NP = rows per CTA and pass
+  int kw;                  // pair 4: reduction length K of the step's weight matrix (the bias planes follow its K/8 planes)
   int is_bias;             // 1: fp32 copy of n_valid floats padded with zeros to N
   size_t dst_off;          // byte offset in wf / wb (is_bias: float offset in the bias block)
   int dst_sel;             // 0: wf, 1: wb, 2: bias block
@@ -160,16 +163,23 @@ __global__ void __launch_bounds__(256) pack_all_k(const __grid_constant__ PackAr
   uint4* dst = reinterpret_cast<uint4*>((pj.dst_sel == 0 ? a.wf : a.wb) + pj.dst_off);
   float v[8];
   int64_t dg = t;                                                    // destination group index (16-byte units)
-  if (pj.pair == 2) {
+  if (pj.pair == 2 || pj.pair == 4) {
     const int NH = N / 2;                                            // K = 16: kgi in {0, 1}
     dg = ((int64_t)(n / NH) * 2 + kgi) * NH + n % NH;
+    if (pj.pair == 4) {
+      const int NPP = N == WID ? WID / 2 : N, NP = NPP / 2, planes = pj.kw / 8 + 2;
+      dg = ((int64_t)((n / NPP) * 2 + (n % NPP) / NP) * planes + pj.kw / 8 + kgi) * NP + n % NP;
+    }
     const float b = n < pj.n_valid ? pj.src[n] : 0.f;
     const float hi = __bfloat162float(__float2bfloat16(b));
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
     if (kgi == 0) { v[0] = hi; v[1] = b - hi; }
   } else {
-    if (pj.pair) {
+    if (pj.pair == 3) {
+      const int NPP = N == WID ? WID / 2 : N, NP = NPP / 2, planes = pj.K / 8 + 2;
+      dg = ((int64_t)((n / NPP) * 2 + (n % NPP) / NP) * planes + kgi) * NP + n % NP;
+    } else if (pj.pair) {
       const int NH = N / 2, kgc = pj.K >= KC2 ? KC2 / 8 : pj.K / 8;   // k-groups per chunk
       dg = (((int64_t)(kgi / kgc) * 2 + n / NH) * kgc + (kgi % kgc)) * NH + n % NH;
     }
@@ -642,6 +652,8 @@ __global__ void __launch_bounds__(TRAIN ? FWD_THREADS_TRAIN : FWD_THREADS, 1) ml
 
 }  // namespace mlptc
 
+#include "mlp_tc_fwd2.cuh"
+
 using namespace mlptc;
 
 extern "C" int mcnerf_mlp_tc_supported(const mcnerf_mlp_params* p) {
@@ -655,7 +667,7 @@ extern "C" int mcnerf_mlp_tc_pack_sizes(const mcnerf_mlp_params* p, size_t* wf_b
                                         size_t* bias_bytes) {
   PackLayout L;
   if (int e = build_layout(p, &L)) return e;
-  if (wf_bytes) *wf_bytes = L.wf_bytes;
+  if (wf_bytes) *wf_bytes = (fwd_v2_mode() > 0 ? 2 : 1) * L.wf_bytes;      // second layout only when that kernel is enabled
   if (wb_bytes) *wb_bytes = L.wb_bytes;
   if (bias_bytes) *bias_bytes = (size_t)L.bias_floats * sizeof(float);
   return 0;
@@ -676,8 +688,10 @@ extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb
                  int is_bias, size_t dst_off, int dst_sel) {
     PackJob& j = a.j[nj];
     j.src = src; j.sn = sn; j.sk = sk; j.N = N; j.K = K; j.pad_k = pad_k; j.pad_n = pad_n; j.n_valid = n_valid;
-    j.k_valid = k_valid; j.is_bias = is_bias; j.dst_off = dst_off; j.dst_sel = dst_sel; j.pair = 1;
+    j.k_valid = k_valid; j.is_bias = is_bias; j.dst_off = dst_off; j.dst_sel = dst_sel; j.pair = 1; j.kw = 0;
     if (dst_sel == 3) { j.dst_sel = 0; j.pair = 2; }
+    if (dst_sel == 4) { j.dst_sel = 0; j.pair = 3; }
+    if (dst_sel == 5) { j.dst_sel = 0; j.pair = 4; }
     a.prefix[nj] = tot;
     tot += is_bias ? (int64_t)N * K : (int64_t)N * K / 8;      // work units (see pack_all_k)
     ++nj;
@@ -708,6 +722,12 @@ extern "C" int mcnerf_mlp_tc_pack(const mcnerf_mlp_params* p, void* wf, void* wb
     }
     add(bs, 0, 0, 256, 1, 0, 0, n_out, 0, 1, sp.bias_off, 2);
     add(bs, 0, 0, sp.N, BIAS_K, 0, 0, n_out, BIAS_K, 0, sp.w_off + (size_t)sp.N * K * 2, 3);   // bias block of the forward image
+    if (fwd_v2_mode() > 0) {
+      // the same matrix and bias block in the layout of the second-generation kernel, behind the first image
+      add(W, ld, 1, sp.N, K, pad, 0, n_out, k_in, 0, L.wf_bytes + sp.w_off, 4);
+      add(bs, 0, 0, sp.N, BIAS_K, 0, 0, n_out, BIAS_K, 0, L.wf_bytes + sp.w_off, 5);
+      a.j[nj - 1].kw = K;
+    }
   }
   add(p->W_sigma2, 0, 0, 256, 1, 0, 0, WID, 0, 1, L.sig2_off, 2);
   add(p->b_sigma2, 0, 0, 8, 1, 0, 0, 1, 0, 1, L.sig2_off + 256, 2);
@@ -746,6 +766,7 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
     static long long* dbg_buf = nullptr;
     if (atoi(dbg) == 7) {
       if (!dbg_buf) cudaMalloc(&dbg_buf, 10 * 32 * sizeof(long long));
+      cudaStreamSynchronize((cudaStream_t)stream);
       cudaMemsetAsync(dbg_buf, 0, 10 * 32 * sizeof(long long), (cudaStream_t)stream);
       a.dbg = dbg_buf;
     }
@@ -767,8 +788,16 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
     a.stash = nullptr; a.stash_enc = nullptr; a.stash_sh = nullptr; a.stash_bits = nullptr;
   }
   // per device / context attribute: set on every call (cheap), not once per process
-  MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
-  MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+  const bool v2 = fwd_v2_mode() >= (stash ? 1 : 2);
+  const int smem_bytes = v2 ? smem_fwd2(stash != nullptr) : SMEM_FWD;
+  if (v2) {
+    a.wpack += L.wf_bytes;
+    MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd2_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd2(true)));
+    MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd2_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fwd2(false)));
+  } else {
+    MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+    MC_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_FWD));
+  }
   int n_pairs = ((in->n_rows + TM - 1) / TM + 1) / 2;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -778,18 +807,35 @@ extern "C" int mcnerf_mlp_tc_fwd(const mcnerf_mlp_params* p, const void* wf, con
   if (grid > sms) grid = sms & ~1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(stash ? FWD_THREADS_TRAIN : FWD_THREADS);
-  cfg.dynamicSmemBytes = SMEM_FWD;
+  cfg.blockDim = dim3(v2 ? (stash ? F2_THREADS_TRAIN : F2_THREADS) : stash ? FWD_THREADS_TRAIN : FWD_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (stash) MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<true>, a));
+  if (v2) {
+    if (stash) MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd2_k<true>, a));
+    else MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd2_k<false>, a));
+  } else if (stash) MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<true>, a));
   else MC_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_fwd_k<false>, a));
   MC_LAUNCHED();
-  if (a.dbg) {     // debug trace: clock64 deltas of CTA 0's third tile pair (steady state)
+  if (a.dbg && v2) {     // MMA issuer of CTA 0, iterations >= 1: where it waits
+    cudaStreamSynchronize((cudaStream_t)stream);
+    long long h[10 * 32];
+    cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const double np = (double)h[3];
+    printf("fwd2 trace (CTA 0, iterations >= 1): passes %lld  span %lld cycles = %.0f per pass;  issuer waits per pass: enc %.0f  "
+           "epilogue %.0f  weights %.0f;  epilogue duration warp 0: %.0f  warp 15: %.0f cycles per pass\n", h[3], h[5] - h[4],
+           (h[5] - h[4]) / np, h[0] / np, h[1] / np, h[2] / np, h[7] ? (double)h[6] / h[7] : 0., h[9] ? (double)h[8] / h[9] : 0.);
+    for (int w = 0; w < 2; ++w)
+      for (int hh = 0; hh < 2; ++hh) {
+        printf("  step 2 slot %d pass %d epilogue (cycles after wake: before ld / after wait, x4 groups; arrived):", w, hh);
+        for (int k = 0; k < 9; ++k) printf(" %lld", h[128 + w * 32 + hh * 16 + k]);
+        printf("\n");
+      }
+  } else if (a.dbg) {     // debug trace: clock64 deltas of CTA 0's third tile pair (steady state)
     cudaStreamSynchronize((cudaStream_t)stream);
     long long h[10 * 32];
     cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);

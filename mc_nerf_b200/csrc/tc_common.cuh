@@ -37,6 +37,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking phase test (polling loops that serve more than one barrier)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Address-based forms for the MMA issue loops (barrier address = base + stage * 8, no pointer re-conversion).
 __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity) {
   uint32_t ok;
@@ -303,6 +315,38 @@ __device__ __forceinline__ void umma2_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, 
       "setp.ne.b32 p, %5, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// ---- "whole warp runs the issue loop" forms: every lane executes the call (so that the compiler sees warp-uniform
+// operands and keeps them in uniform registers), one elected lane issues.
+__device__ __forceinline__ void umma2_bf16_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_w_e(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_multicast_addr_e(uint32_t bar_addr, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar_addr), "h"(cta_mask)
       : "memory");
 }
 // registers -> TMEM: thread i of the warp writes lane (base_lane + i), 8 consecutive 32-bit columns

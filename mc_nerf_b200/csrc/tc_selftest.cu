@@ -211,7 +211,12 @@ tc_selftest2_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restr
 // being computed).  bg > 0: warps 4-7 keep tcgen05.ld/st traffic on columns [384, 512) going meanwhile (port probe).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256)
 tc_selftest_ts_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, float* __restrict__ D, int N, int K,
-                 int n_split, int reps, int bg, long long* cycles) {
+                 int n_split_flags, int reps, int bg, long long* cycles) {
+  const int n_split = n_split_flags & 3, bg_mode = (n_split_flags >> 4) & 3;     // bg_mode 1: loads only, 2: stores only
+  const int kl = (n_split_flags >> 8) & 1;   // 1: the fused kernel's layout - A at columns [0,128), every pass accumulates at [128,256) (timing only)
+  const uint32_t a_col = kl ? 0 : 256;
+  const int commit_each = (n_split_flags >> 9) & 1;   // 1: a tcgen05.commit (to a barrier nobody waits on) after every pass
+  __shared__ uint64_t bar2;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -228,6 +233,7 @@ tc_selftest_ts_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __res
   }
   if (tid == 0) {
     tc::mbar_init(&bar, 1);
+    tc::mbar_init(&bar2, 1u << 19);
     tc::mbar_init_fence();
   }
   if (warp == 0) tc::tmem_alloc2(&tmem_base, 512);
@@ -245,7 +251,7 @@ tc_selftest_ts_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __res
         uint32_t lo = __bfloat16_as_ushort(arow[2 * (c + j)]), hi = __bfloat16_as_ushort(arow[2 * (c + j) + 1]);
         w[j] = lo | (hi << 16);
       }
-      tc::tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c, w);
+      tc::tmem_st8(tmem + ((uint32_t)(warp * 32) << 16) + a_col + c, w);
     }
     tc::tmem_st_wait();
   }
@@ -262,14 +268,15 @@ tc_selftest_ts_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __res
     for (int rep = 0; rep < reps; ++rep)
       for (int h = 0; h < n_split; ++h) {
         uint32_t b_lo = tc::umma_desc_lo(tc::smem_u32(sB + (size_t)h * NP * K * 2), NP * 16);
-        uint32_t a_t = tmem + 256;
-        const uint32_t d_t = tmem + h * (N / n_split);
+        uint32_t a_t = tmem + a_col;
+        const uint32_t d_t = tmem + (kl ? 128 : h * (N / n_split));
         tc::umma2_bf16_ts(d_t, a_t, b_lo, hi, idesc, rep > 0);
 #pragma unroll 4
         for (int k = 1; k < nk; ++k) {
           a_t += 8; b_lo += b_inc;
           tc::umma2_bf16_ts(d_t, a_t, b_lo, hi, idesc, true);
         }
+        if (commit_each) tc::umma2_commit_multicast_addr(tc::smem_u32(&bar2), (uint16_t)3);
       }
     tc::umma2_commit_multicast_addr(tc::smem_u32(&bar), (uint16_t)3);
     const long long t1 = clock64();
@@ -278,14 +285,19 @@ tc_selftest_ts_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __res
   }
   if (warp >= 4 && bg > 0) {
     const uint32_t t = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 384;
+    uint32_t v[32], w[8];
+    for (int j = 0; j < 8; ++j) w[j] = j;
     for (int i = 0; i < bg; ++i) {
-      uint32_t v[32];
-      tc::tmem_ld32(t + (i & 3) * 32, v);
-      tc::tmem_ld_wait();
-      uint32_t w[8];
-      for (int j = 0; j < 8; ++j) w[j] = v[j] + v[j + 8] + v[j + 16] + v[j + 24];
-      tc::tmem_st8(t + (i & 3) * 32, w);
-      tc::tmem_st8(t + (i & 3) * 32 + 8, w);
+      if (bg_mode != 2) {
+        tc::tmem_ld32(t + (i & 3) * 32, v);
+        tc::tmem_ld_wait();
+        for (int j = 0; j < 8; ++j) w[j] += v[j] + v[j + 8] + v[j + 16] + v[j + 24];
+      }
+      if (bg_mode != 1) {
+        tc::tmem_st8(t + (i & 3) * 32, w);
+        tc::tmem_st8(t + (i & 3) * 32 + 8, w);
+        if (bg_mode == 2) tc::tmem_st_wait();
+      }
     }
     tc::tmem_st_wait();
   }
@@ -311,7 +323,7 @@ tc_selftest_ts_k(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __res
 extern "C" int mcnerf_tc_selftest_ts(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int n_split, int reps,
                                      int bg, long long* cycles_out, void* stream) {
   MC_ARG(A_bf16 && B_bf16 && D && N >= 64 && N <= 256 && N % 64 == 0 && K >= 16 && K <= 256 && K % 16 == 0 && reps >= 1);
-  MC_ARG(n_split == 1 || n_split == 2);
+  MC_ARG((n_split & 3) == 1 || (n_split & 3) == 2);
   size_t smem = (size_t)(N / 2) * K * 2;
   MC_CUDA(cudaFuncSetAttribute(tc_selftest_ts_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest_ts_k<<<2, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)A_bf16, (const __nv_bfloat16*)B_bf16, D, N, K,

@@ -262,3 +262,17 @@ def test_ray_gradients_are_summed_in_a_fixed_order():
     torch.testing.assert_close(d[0], f[0], rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(d[1], f[1], rtol=1e-4, atol=1e-6)
     assert float(d[0][3].abs().max()) == 0.0          # the ray without samples receives nothing
+
+
+@pytest.mark.gpu
+def test_second_generation_forward_kernel_passes_the_same_tests():
+    """MCNERF_FWD_V2=2 routes every forward launch (inference and training) through mlp_tc_fwd2_k (A operand in tensor
+    memory, mlp_tc_fwd2.cuh - opt-in); the flag is read once per process, so the tests above are re-run
+    in a child process."""
+    import os, subprocess, sys
+    if os.environ.get("MCNERF_FWD_V2"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, MCNERF_FWD_V2="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
