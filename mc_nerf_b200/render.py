@@ -45,6 +45,9 @@ class RenderCfg:
         # False: torch.rand / torch.randn in the reference's order (draw-for-draw replay, tests)
         self.device_rng = bool(device_rng)
         self.sh_dim = 27                           # 3 (MLP_deg + 1)^2; from_sys_param sets it
+        # train-only cap on the selected fine samples, per ray (the reference hard-codes 128, model/mc_nerf.py:630;
+        # sys_param key `fine_sample_cap` - a value >= Sf switches the cap off, bench.py --workload stress reports both)
+        self.fine_cap = 128
 
     @staticmethod
     def from_sys_param(sp, precision=None):
@@ -61,6 +64,7 @@ class RenderCfg:
                         (sp["coarse_MLP_depth"], sp["coarse_MLP_width"], tuple(sp["coarse_MLP_skip"])),
                         (sp["fine_MLP_depth"], sp["fine_MLP_width"], tuple(sp["fine_MLP_skip"])), precision, device_rng)
         cfg.sh_dim = 3 * (int(sp.get("MLP_deg", 2)) + 1) ** 2
+        cfg.fine_cap = int(sp.get("fine_sample_cap", 128))
         return cfg
 
 
@@ -201,14 +205,14 @@ def _flat_zero_grads(*nets):
 
 def select_and_cap(cfg, w_sel, w_max, B, train, cap_perm=None):
     """Device-side compaction of the selected fine samples from the selection weights; the reference's train-only
-    128-per-ray cap (model/mc_nerf.py:630-632) is reproduced when it can trigger (Sf > 128).
+    128-per-ray cap (model/mc_nerf.py:630-632) is reproduced when it can trigger (Sf > cfg.fine_cap = 128).
     -> (sel_idx, n_rows capacity, n_rows_dev, sel_offsets or None when the cap reshuffled the rows)"""
     dev = w_sel.device
     sel_idx, offs, n_sel = ops.select_fine(w_sel, w_max, cfg.scale, cfg.thresh)
     n_rows, n_rows_dev = B * cfg.Sf, n_sel
-    if train and cfg.Sf > 128:
+    if train and cfg.Sf > cfg.fine_cap:
         offs = None                                # capped rows are a random subset: no per-ray structure left
-        K = B * 128
+        K = B * cfg.fine_cap
         if cap_perm is not None:                   # test hook: an explicit permutation of the n selected samples
             n = int(n_sel.item())                  # (host synchronisation, as in the reference)
             if n > K:

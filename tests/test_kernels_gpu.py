@@ -320,6 +320,12 @@ def test_device_side_sample_cap_keeps_a_uniform_subset():
     idx2, n_rows2, n_dev2, _ = render.select_and_cap(cfg, w2, wm2, B, train=True)
     assert n_rows2 == K and int(n_dev2.item()) == n2
     assert torch.equal(torch.sort(idx2[:n2]).values, all2[:n2])
+    # sys_param `fine_sample_cap` >= Sf switches the cap off (bench.py --workload stress reports both): training then
+    # selects exactly what the un-capped test path selects, per-ray offsets included
+    cfg.fine_cap = Sc * scale
+    idx3, n_rows3, n_dev3, offs3 = render.select_and_cap(cfg, w_sel, w_max, B, train=True)
+    assert n_rows3 == B * Sc * scale and int(n_dev3.item()) == n and offs3 is not None
+    assert torch.equal(idx3[:n], all_idx[:n])
 
 
 def test_p2p_allreduce_kernel_two_virtual_ranks_on_one_gpu():
