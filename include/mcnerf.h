@@ -231,6 +231,15 @@ int mcnerf_fine_tail_bwd(const float* out_sel, const float* w_sel, const float* 
 int mcnerf_select_fine(const float* weights, const float* w_max, int n_rays, int Sc, int scale, float thresh,
                        int32_t* sel_idx /*[B*Sc*scale] capacity*/, int32_t* sel_offsets /*[B+1]*/,
                        int32_t* n_sel, void* stream);
+
+/* Train-only cap on the selected fine samples (ref: model/mc_nerf.py:630-632: `torch.randperm(n)[:K]` on the CPU after a
+ * host synchronisation): out_idx[0 .. min(n,K)) = a uniformly random K-subset of sel_idx[0 .. n) (all of them when
+ * n <= K), in ascending slot order; *n_out_dev = min(n, K).  n = min(*n_sel_dev, capacity).  Keys are a seeded bijection
+ * of the slot index, the K-th smallest is found by a two-level radix select: no sort, no host synchronisation,
+ * deterministic for a given `seed` (two words, as for mcnerf_philox_fill).  workspace: mcnerf_cap_select_workspace bytes. */
+int mcnerf_cap_select_workspace(int capacity, size_t* bytes);
+int mcnerf_cap_select(const int32_t* sel_idx, const int32_t* n_sel_dev, int capacity, int K, const int64_t* seed,
+                      int32_t* out_idx, int32_t* n_out_dev, void* workspace, void* stream);
 /* out_dense [B*Sf,4] = (sigma_default,1,1,1) everywhere, then out_dense[sel_idx[m]] = out_sel[m]
  * (ref: model/mc_nerf.py:692-694, 700-701). */
 int mcnerf_scatter_fine(const float* out_sel, const int32_t* sel_idx, int n_sel, const int32_t* n_sel_dev,

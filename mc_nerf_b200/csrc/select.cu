@@ -101,6 +101,131 @@ __global__ void gather_k(const float4* __restrict__ src, const int32_t* __restri
   if (i < rows) dst[i] = src[idx[i]];
 }
 
+// ------------------------------------------------------------------ uniform K-subset of the selected samples
+// ref: model/mc_nerf.py:630-632 (train-only cap: `rand_idx = torch.randperm(n)[:K]` on the CPU, after a host sync).
+// Same distribution without leaving the device and without sorting: slot i < n gets the 32-bit key
+//   key(i) = mix(i * 0x9E3779B1 + seed0) ^ seed1,   mix = the murmur3 finaliser,
+// which is a BIJECTION of i, so all keys are distinct; the K-th smallest key T is found by a two-level radix select
+// (65536-bin histograms of the high, then the low 16 bits) and {i : key(i) <= T} - exactly K slots - is compacted in
+// ascending i.  n <= K keeps everything.  Deterministic for a given seed.
+__device__ __forceinline__ uint32_t cap_key(uint32_t i, uint32_t s0, uint32_t s1) {
+  uint32_t h = i * 0x9E3779B1u + s0;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h ^ s1;
+}
+struct CapState { uint32_t b1, below1, all, T, n_out; };
+constexpr int CAP_BINS = 65536, CAP_BLOCK = 1024;
+
+__global__ void cap_hist_k(const int32_t* __restrict__ n_dev, int capacity, const int64_t* __restrict__ seed, int level,
+                           const CapState* __restrict__ st, uint32_t* __restrict__ hist) {
+  const int n = min(*n_dev, capacity);
+  const uint32_t s0 = (uint32_t)seed[0], s1 = (uint32_t)seed[1];
+  if (level == 1 && st->all) return;
+  const uint32_t b1 = level == 1 ? st->b1 : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t k = cap_key((uint32_t)i, s0, s1);
+    if (level == 0) atomicAdd(&hist[k >> 16], 1u);
+    else if ((k >> 16) == b1) atomicAdd(&hist[k & 0xFFFFu], 1u);
+  }
+}
+
+// one block: smallest bin b whose inclusive prefix reaches the wanted rank; level 0 -> (b1, below1, all), level 1 -> T, n_out
+__global__ void __launch_bounds__(CAP_BLOCK) cap_pick_k(const uint32_t* __restrict__ hist, int K, int level, CapState* st,
+                                                        int32_t* __restrict__ n_out_dev) {
+  __shared__ uint32_t part[CAP_BLOCK];
+  __shared__ uint32_t warp_tot[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int PER = CAP_BINS / CAP_BLOCK;       // 64 consecutive bins per thread
+  uint32_t sum = 0;
+  for (int j = 0; j < PER; ++j) sum += hist[tid * PER + j];
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t t = warp_tot[lane], ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    warp_tot[lane] = ti - t;
+  }
+  __syncthreads();
+  const uint32_t excl = warp_tot[wid] + inc - sum;      // keys in bins before this thread's
+  part[tid] = excl;
+  __syncthreads();
+  const uint32_t total = part[CAP_BLOCK - 1] + (tid == CAP_BLOCK - 1 ? sum : 0);
+  __shared__ uint32_t total_s;
+  if (tid == CAP_BLOCK - 1) total_s = total;
+  __syncthreads();
+  uint32_t want;                                        // 1-based rank inside this histogram
+  if (level == 0) {
+    if (total_s <= (uint32_t)K) {
+      if (tid == 0) { st->all = 1; st->b1 = 0; st->below1 = 0; st->T = 0xFFFFFFFFu; st->n_out = total_s; *n_out_dev = (int32_t)total_s; }
+      return;
+    }
+    want = (uint32_t)K;
+  } else {
+    if (st->all) return;
+    want = (uint32_t)K - st->below1;
+  }
+  if (excl < want && want <= excl + sum) {              // the wanted rank falls into this thread's 64 bins
+    uint32_t c = excl;
+    for (int j = 0; j < PER; ++j) {
+      const uint32_t h = hist[tid * PER + j];
+      if (c + h >= want) {
+        if (level == 0) { st->all = 0; st->b1 = (uint32_t)(tid * PER + j); st->below1 = c; }
+        else { st->T = (st->b1 << 16) | (uint32_t)(tid * PER + j); st->n_out = (uint32_t)K; *n_out_dev = K; }
+        break;
+      }
+      c += h;
+    }
+  }
+}
+
+// per block of CAP_BLOCK slots: how many are kept
+__global__ void __launch_bounds__(CAP_BLOCK) cap_count_k(const int32_t* __restrict__ n_dev, int capacity,
+                                                         const int64_t* __restrict__ seed, const CapState* __restrict__ st,
+                                                         int32_t* __restrict__ block_counts) {
+  const int n = min(*n_dev, capacity);
+  const int i = blockIdx.x * CAP_BLOCK + threadIdx.x;
+  const bool keep = i < n && cap_key((uint32_t)i, (uint32_t)seed[0], (uint32_t)seed[1]) <= st->T;
+  const int c = __syncthreads_count(keep);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(CAP_BLOCK) cap_write_k(const int32_t* __restrict__ sel_idx, const int32_t* __restrict__ n_dev,
+                                                         int capacity, const int64_t* __restrict__ seed,
+                                                         const CapState* __restrict__ st, const int32_t* __restrict__ block_offs,
+                                                         int K, int32_t* __restrict__ out_idx) {
+  __shared__ int warp_tot[32];
+  const int n = min(*n_dev, capacity);
+  const int i = blockIdx.x * CAP_BLOCK + threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool keep = i < n && cap_key((uint32_t)i, (uint32_t)seed[0], (uint32_t)seed[1]) <= st->T;
+  const unsigned m = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) warp_tot[wid] = __popc(m);
+  __syncthreads();
+  if (wid == 0) {
+    int t = warp_tot[lane], ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += u;
+    }
+    warp_tot[lane] = ti - t;
+  }
+  __syncthreads();
+  if (keep) {
+    const int pos = block_offs[blockIdx.x] + warp_tot[wid] + __popc(m & ((1u << lane) - 1));
+    if (pos < K) out_idx[pos] = sel_idx[i];
+  }
+}
+
 }  // namespace
 
 extern "C" int mcnerf_select_fine(const float* weights, const float* w_max, int n_rays, int Sc, int scale,
@@ -139,6 +264,43 @@ extern "C" int mcnerf_gather_fine(const float* g_dense, const int32_t* sel_idx, 
   MC_ARG(g_dense && sel_idx && g_sel && ((uintptr_t)g_dense & 15) == 0 && ((uintptr_t)g_sel & 15) == 0);
   gather_k<<<cdiv(n_sel, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)g_dense, sel_idx, n_sel, n_sel_dev,
                                                                (float4*)g_sel);
+  MC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int mcnerf_cap_select_workspace(int capacity, size_t* bytes) {
+  MC_ARG(capacity >= 0 && bytes);
+  const size_t nb = (size_t)(capacity + CAP_BLOCK - 1) / CAP_BLOCK;
+  *bytes = 2 * (size_t)CAP_BINS * 4 + 64 + (2 * nb + 2) * 4;
+  return 0;
+}
+
+extern "C" int mcnerf_cap_select(const int32_t* sel_idx, const int32_t* n_sel_dev, int capacity, int K, const int64_t* seed,
+                                 int32_t* out_idx, int32_t* n_out_dev, void* workspace, void* stream) {
+  MC_ARG(sel_idx && n_sel_dev && seed && out_idx && n_out_dev && workspace && capacity > 0 && K > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* hist1 = (uint32_t*)workspace;
+  uint32_t* hist2 = hist1 + CAP_BINS;
+  CapState* state = (CapState*)(hist2 + CAP_BINS);
+  int32_t* counts = (int32_t*)((uint8_t*)state + 64);
+  const int nb = (capacity + CAP_BLOCK - 1) / CAP_BLOCK;
+  int32_t* offs = counts + nb + 1;
+  MC_CUDA(cudaMemsetAsync(workspace, 0, 2 * (size_t)CAP_BINS * 4 + 64, st));
+  const int hb = nb < 1184 ? nb : 1184;                  // 8 blocks per SM, grid-stride
+  cap_hist_k<<<hb, CAP_BLOCK, 0, st>>>(n_sel_dev, capacity, seed, 0, state, hist1);
+  MC_LAUNCHED();
+  cap_pick_k<<<1, CAP_BLOCK, 0, st>>>(hist1, K, 0, state, n_out_dev);
+  MC_LAUNCHED();
+  cap_hist_k<<<hb, CAP_BLOCK, 0, st>>>(n_sel_dev, capacity, seed, 1, state, hist2);
+  MC_LAUNCHED();
+  cap_pick_k<<<1, CAP_BLOCK, 0, st>>>(hist2, K, 1, state, n_out_dev);
+  MC_LAUNCHED();
+  cap_count_k<<<nb, CAP_BLOCK, 0, st>>>(n_sel_dev, capacity, seed, state, counts);
+  MC_LAUNCHED();
+  int32_t* total = offs + nb;                            // offs has nb + 1 entries
+  select_scan_k<<<1, 1024, 0, st>>>(counts, nb, offs, total);
+  MC_LAUNCHED();
+  cap_write_k<<<nb, CAP_BLOCK, 0, st>>>(sel_idx, n_sel_dev, capacity, seed, state, offs, K, out_idx);
   MC_LAUNCHED();
   return 0;
 }

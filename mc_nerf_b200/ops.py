@@ -503,6 +503,21 @@ def select_fine(weights, w_max, scale, thresh):
     return sel_idx, offs, n_sel
 
 
+def cap_select(sel_idx, n_sel, K, seed):
+    """-> (out_idx int32 [K], n_out int32 [1]): a uniformly random K-subset of the first n_sel entries of sel_idx (all of
+    them when n_sel <= K), ascending; no sort, no host sync.  ref: model/mc_nerf.py:630-632."""
+    dev = sel_idx.device
+    cap = int(sel_idx.shape[0])
+    sz = ctypes.c_size_t()
+    lib().call("mcnerf_cap_select_workspace", cap, ctypes.byref(sz))
+    ws = torch.empty(sz.value, dtype=torch.uint8, device=dev)
+    out = torch.empty(int(K), dtype=torch.int32, device=dev)
+    n_out = torch.empty(1, dtype=torch.int32, device=dev)
+    lib().call("mcnerf_cap_select", _p(sel_idx, torch.int32), _p(n_sel, torch.int32), cap, int(K), _p(seed, torch.int64),
+               _p(out, torch.int32), _p(n_out, torch.int32), _p(ws, torch.uint8), _stream())
+    return out, n_out
+
+
 class ScatterFineFn(torch.autograd.Function):
     """out_dense[B*Sf,4] = defaults; out_dense[idx] = out_sel.  ref: model/mc_nerf.py:692-694, 700-701."""
 

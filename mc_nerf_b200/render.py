@@ -203,7 +203,7 @@ def _flat_zero_grads(*nets):
     return outs
 
 
-def select_and_cap(cfg, w_sel, w_max, B, train, cap_perm=None):
+def select_and_cap(cfg, w_sel, w_max, B, train, cap_perm=None, seed=None):
     """Device-side compaction of the selected fine samples from the selection weights; the reference's train-only
     128-per-ray cap (model/mc_nerf.py:630-632) is reproduced when it can trigger (Sf > cfg.fine_cap = 128).
     -> (sel_idx, n_rows capacity, n_rows_dev, sel_offsets or None when the cap reshuffled the rows)"""
@@ -222,13 +222,12 @@ def select_and_cap(cfg, w_sel, w_max, B, train, cap_perm=None):
                 n_rows, n_rows_dev = n, None
         elif sel_idx.shape[0] > K:
             # The reference synchronises, draws torch.randperm(n) on the CPU (~40 ms for the shipped config's 3.4 M
-            # selected samples) and keeps the first K.  Same uniform K-subset without leaving the device: one uniform
-            # key per capacity slot, slots beyond the device-side count n pushed to the end, argsort, first K.
-            # (When n <= K all n samples survive, in shuffled row order - which no result depends on.)
-            keys = torch.rand(sel_idx.shape[0], device=dev)
-            keys.masked_fill_(torch.arange(sel_idx.shape[0], device=dev, dtype=torch.int32) >= n_sel, 2.0)
-            sel_idx = sel_idx[torch.argsort(keys)[:K]].contiguous()
-            n_rows, n_rows_dev = K, torch.clamp(n_sel, max=K)
+            # selected samples) and keeps the first K.  Same uniform K-subset without leaving the device and without a
+            # sort: seeded bijective keys + a two-level radix select (mcnerf_cap_select); n <= K keeps all n.
+            if seed is None:
+                seed = ops.draw_seed(dev)
+            sel_idx, n_rows_dev = ops.cap_select(sel_idx, n_sel, K, seed)
+            n_rows = K
     return sel_idx, n_rows, n_rows_dev, offs
 
 
@@ -270,7 +269,7 @@ class RenderFn(torch.autograd.Function):
             w_sel = ops.sigma2weights(out_c, noise_sel, jitter=jitter, near=cfg.near, far=cfg.far, sigma_stride=4,
                                       n_rays=B, S=cfg.Sc, w_max=w_max)
         # selection
-        sel_idx, n_rows, n_rows_dev, offs = select_and_cap(cfg, w_sel, w_max, B, train, cap_perm)
+        sel_idx, n_rows, n_rows_dev, offs = select_and_cap(cfg, w_sel, w_max, B, train, cap_perm, seed)
         LAST["n_rows"], LAST["n_rows_dev"] = n_rows, n_rows_dev
         # fine
         if n_rows > 0:

@@ -309,6 +309,22 @@ def test_device_side_sample_cap_keeps_a_uniform_subset():
         draws.append(kept)
     assert abs(first_half / 6 - 0.5) < 0.02
     assert not torch.equal(draws[0], draws[1])
+    # the kept subset is emitted in ascending slot order, and a given seed reproduces it exactly
+    assert bool((draws[0][1:] > draws[0][:-1]).all())
+    seed = ops.draw_seed(DEV)
+    a1, _, _, _ = render.select_and_cap(cfg, w_sel, w_max, B, train=True, seed=seed)
+    a2, _, _, _ = render.select_and_cap(cfg, w_sel, w_max, B, train=True, seed=seed)
+    assert torch.equal(a1, a2)
+    # uniformity over many draws: every pool member is kept with probability K / n
+    hits = torch.zeros(int(pool.max()) + 1)
+    R = 40
+    for _ in range(R):
+        kept = render.select_and_cap(cfg, w_sel, w_max, B, train=True)[0].cpu().long()
+        hits[kept] += 1
+    p_keep = K / n
+    freq = hits[pool.long()] / R
+    assert abs(float(freq.mean()) - p_keep) < 1e-6                       # exactly K kept each time
+    assert float(freq.std()) < 1.25 * (p_keep * (1 - p_keep) / R) ** 0.5   # binomial spread, no favoured slots
     # fewer than 128*B selected: everything survives (row order is free)
     sparse = out_c.clone()
     sparse[:, 0] = -30.0
