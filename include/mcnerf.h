@@ -380,9 +380,12 @@ int mcnerf_tc_selftest2(const void* A_bf16, const void* B_bf16, float* D, int N,
                         long long* cycles_out, const float* bias, void* stream);
 
 /* The same CTA-pair product with the A operand read from TENSOR MEMORY (tcgen05.mma "[a_tmem]" form): pins the TMEM
- * layout of a bf16 A operand (row = lane, one 32-bit column = the pair k even | k odd << 16).  n_split = 2 computes the
- * product as two N/2-wide passes into the two column halves of the accumulator; bg > 0 adds background tcgen05.ld/st
- * traffic on unused columns (port-contention probe); cycles_out as in mcnerf_tc_mma_rate. */
+ * layout of a bf16 A operand (row = lane, one 32-bit column = the pair k even | k odd << 16).  n_split (low 2 bits) = 2
+ * computes the product as two N/2-wide passes into the two column halves of the accumulator; bg > 0 adds background
+ * tcgen05.ld/st traffic on unused columns (port-contention probe); cycles_out as in mcnerf_tc_mma_rate.
+ * Probe-only flag bits of n_split (results then serve timing, not the product): bits 4-5 = 1 background loads only,
+ * 2 stores only; bit 8 = the fused kernel's placement (A at columns [0,128), every pass accumulates at [128,256));
+ * bit 9 = a tcgen05.commit after every pass. */
 int mcnerf_tc_selftest_ts(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int n_split, int reps, int bg,
                           long long* cycles_out, void* stream);
 
