@@ -517,7 +517,12 @@ __global__ void __launch_bounds__(TRAIN ? FWD_THREADS_TRAIN : FWD_THREADS, 1) ml
           MC_TRACE(if (a.dbg && blockIdx.x == 0 && it == 2 && warp == 0 && lane == 0) a.dbg[(4 + t) * 32 + s] = clock64();)
           tc::tcgen05_fence_after();
           if (st.epi == EPI_OUT) {
-            // sigma.2: gather the four column-quarter partial sums through the (now idle) activation tile
+            // sigma.2: gather the four column-quarter partial sums through the (now idle) activation tile.
+            // Training: the tile still holds relu(sh.0) until the stash warps have copied it - without this wait the
+            // partial sums could land in the first 1.5 KB of the stashed tile (features 0..7 of rows 0..95: found with
+            // compute-sanitizer, whose slowdown of the stash warps made the race visible as NaN sh.2 weight gradients).
+            // Same parity as the next ReLU step's wait for this copy; not toggled here.
+            if (TRAIN) tc::mbar_wait(&bars->st_done[t], (stpar >> t & 1) ^ 1);
             float* part = reinterpret_cast<float*>(act + t * ACT_BYTES);
             if (cq != 0) part[(cq - 1) * 128 + q] = sig_dot[t];
             named_bar_sync(1 + t * 4 + lq, 128);       // the 4 warps of this lane quarter
