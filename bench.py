@@ -417,8 +417,16 @@ def run_demo(args):
     from mc_nerf_b200._lib import lib
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the MC-NeRF hot path has no CPU fallback)")
-    dev = "cuda:0"
-    torch.cuda.set_device(0)
+    # N > 1 (torchrun): the 110 views are independent units - every rank renders its own views with its own replica of
+    # the networks, no data-path collective (SURVEY 8e / "replicas"); the process group only serves the barrier and the
+    # max-over-ranks time
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dev = f"cuda:{local}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
     kw = dict(n_cam=N_CAM, img_h=args.img, img_w=args.img, batch=DEMO_CHUNK, samples=SC, scale=SCALE, with_images=False)
     sp = syn.make_sys_param(device=dev, **kw)
     sp["mlp_precision"] = args.precision
@@ -445,18 +453,25 @@ def run_demo(args):
 
     def timed(fn, steps):
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            fn((i + 1) % N_CAM)
+            fn((1 + i * world + rank) % N_CAM)
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
     with torch.no_grad():
         for i in range(max(args.warmup, 3)):
-            view_resident(i % N_CAM)
-        sampler = ClockSampler(0)
+            view_resident((i * world + rank) % N_CAM)
+        sampler = ClockSampler(local)
         sampler.start()
         ms = timed(view_resident, args.steps)
         clocks = sampler.stop()
@@ -486,14 +501,21 @@ def run_demo(args):
                 kernel_ms_per_step=round(mlp_ms, 3), mlp_evals_per_step=evals,
                 fine_selected_frac=round(sum(fine_rows) / (n * SC * SCALE), 4),
                 kernel_ms_by_name={k: round(v, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])[:8]})
-    cpu = None if args.no_cpu else cpu_reference_demo(steps=1, warmup=1, rays=8192)
-    line = dict(metric=DEMO_METRIC, value=round(n * args.steps / (ms / 1e3), 1), unit=UNIT, n_gpus=1, steps=args.steps,
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+    cpu = None if (args.no_cpu or world > 1) else cpu_reference_demo(steps=1, warmup=1, rays=8192)
+    n = n * world                                   # rays of one "step" = one view per rank
+    line = dict(metric=DEMO_METRIC, value=round(n * args.steps / (ms / 1e3), 1), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
-                config=demo_config(args.img, DEMO_CHUNK),
+                config=dict(demo_config(args.img, DEMO_CHUNK), parallelism="single device" if world == 1 else
+                            f"{world} replicas, one view per rank and step, no collective"),
                 e2e=dict(value=round(n * args.steps / (ms_e2e / 1e3), 1), unit=UNIT, h2d_bytes_per_step=8,
                          d2h_bytes_per_step=n * 5 * 4, ms_per_step=round(ms_e2e / args.steps, 3)),
-                gpu_launches=int(launches) * args.steps, clocks=clocks, roofline=roof, cpu_baseline=cpu)
+                gpu_launches=int(launches) * args.steps * world, clocks=clocks, roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
 
 
