@@ -15,7 +15,12 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OUT = os.path.join(CSRC, "libmcnerf.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = (["-DMCNERF_SPIN_TEST_WAIT"] if os.environ.get("MCNERF_SPIN") else []) + (["-DMCNERF_TC_TRACE"] if os.environ.get("MCNERF_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+# measurement / debugging variants (environment): MCNERF_SPIN (test_wait spinning), MCNERF_TRACE (clock64 traces of the
+# tensor-core kernels, tools/trace_fwd.py), MCNERF_CHAOS (random delays at every mbarrier hand-off: shakes out protocol
+# races - the parity and bit-exact determinism tests must still pass)
+VARIANT = [f for f, e in (("-DMCNERF_SPIN_TEST_WAIT", "MCNERF_SPIN"), ("-DMCNERF_TC_TRACE", "MCNERF_TRACE"),
+                          ("-DMCNERF_CHAOS", "MCNERF_CHAOS")) if os.environ.get(e)]
+FLAGS = VARIANT + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC",
          "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
@@ -33,6 +38,9 @@ def build(force=False, verbose=False):
     hdrs.append(os.path.join(ROOT, "include", "mcnerf.h"))
     bdir = os.path.join(CSRC, "build")
     os.makedirs(bdir, exist_ok=True)
+    stamp = os.path.join(bdir, "variant.txt")         # objects built with other variant flags are stale
+    if not os.path.exists(stamp) or open(stamp).read() != " ".join(VARIANT):
+        force = True
     jobs = []
     for s in srcs:
         src = os.path.join(CSRC, s)
@@ -52,6 +60,8 @@ def build(force=False, verbose=False):
                 sys.stderr.write(f"--- nvcc {name}\n{r.stdout}{r.stderr}\n")
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed on {name}")
+    with open(stamp, "w") as f:
+        f.write(" ".join(VARIANT))
     objs = [os.path.join(bdir, s[:-3] + ".o") for s in srcs]
     if force or jobs or _stale(OUT, objs):
         cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]

@@ -10,6 +10,19 @@ namespace tc {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ------------------------------------------------------------------ mbarrier
+// MCNERF_CHAOS build (python -m mc_nerf_b200.build with MCNERF_CHAOS=1): a pseudo-random delay of up to 4 us after one
+// in eight successful mbarrier waits and before one in eight arrivals, identical for the lanes of a warp.  The kernels'
+// results must not depend on the relative timing of their warp roles; the parity and determinism tests are run on this
+// build to check exactly that (profiles/r02_compute_sanitizer.txt).
+#ifdef MCNERF_CHAOS
+__device__ __forceinline__ void chaos_delay(uint32_t salt) {
+  uint32_t h = ((uint32_t)clock64() * 2654435761u) ^ (salt * 0x9E3779B1u) ^ (blockIdx.x * 7919u + (threadIdx.x >> 5) * 104729u);
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+  if ((h & 7u) == 0) __nanosleep(((h >> 8) & 0x7FFu) * 2);
+}
+#else
+__device__ __forceinline__ void chaos_delay(uint32_t) {}
+#endif
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -17,9 +30,11 @@ __device__ __forceinline__ void mbar_init_fence() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  chaos_delay(1);
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  chaos_delay(2);
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
@@ -62,7 +77,7 @@ __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t p
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
-  if (mbar_try_wait_addr(bar_addr, parity)) return;
+  if (mbar_try_wait_addr(bar_addr, parity)) { chaos_delay(7 + parity); return; }
   long long t0 = clock64();
   while (!mbar_try_wait_addr(bar_addr, parity)) {
     if (clock64() - t0 > 4000000000LL) {
@@ -70,6 +85,7 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parit
       __trap();
     }
   }
+  chaos_delay(9 + parity);
 }
 // Wait with acquire at cluster scope: the phase was (partly) completed by arrives from the peer CTA.
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar_addr, uint32_t parity) {
@@ -93,7 +109,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar_addr, uint32_t pa
 }
 // Bounded wait: ~2 s at 2 GHz, then trap (a wrong phase or a lost arrive must not hang the box).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) { chaos_delay(3 + parity); return; }
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
@@ -102,6 +118,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+  chaos_delay(5 + parity);
 }
 
 // ------------------------------------------------------------------ proxies / fences
@@ -196,6 +213,7 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 // arrive publishes is shared memory of the ARRIVING CTA, read only by that CTA's own tensor core (async proxy, made
 // visible by fence.proxy.async before the arrive) once the leader issues the pair MMA.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
+  chaos_delay(11);
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 
