@@ -344,6 +344,36 @@ def test_device_side_sample_cap_keeps_a_uniform_subset():
     assert torch.equal(idx3[:n], all_idx[:n])
 
 
+@pytest.mark.parametrize("cap,n,K", [(1, 0, 1), (1, 1, 1), (7, 5, 3), (1000, 1000, 1), (1024, 1024, 1023), (1025, 1025, 1024),
+                                     (5000, 4000, 4000), (5000, 4001, 4000), (70000, 65537, 1000), (300000, 299999, 150000),
+                                     (300000, 20, 150000)])
+def test_cap_select_edge_shapes(cap, n, K):
+    """mcnerf_cap_select over awkward sizes: empty input, n <= K (everything kept, in order), n = K + 1, capacities that are
+    not multiples of the block size, n much smaller than the capacity.  Exactly min(n, K) distinct entries, ascending,
+    all from the valid prefix; entries beyond n are never read."""
+    from mc_nerf_b200 import ops
+    g = torch.Generator().manual_seed(cap + n + K)
+    sel = (torch.randperm(cap, generator=g).to(torch.int32) * 3 + 1).to(DEV)
+    sel[:n] = torch.sort(sel[:n]).values                 # the selection emits ascending indices
+    sel[n:] = -12345                                      # poison: must not appear in the output
+    n_dev = torch.tensor([n], dtype=torch.int32, device=DEV)
+    seed = torch.tensor([cap * 7919 + n, -K], dtype=torch.int64, device=DEV)
+    out, n_out = ops.cap_select(sel, n_dev, K, seed)
+    m = min(n, K)
+    assert int(n_out.item()) == m and out.shape[0] == K
+    kept = out[:m].cpu()
+    assert bool(torch.isin(kept, sel[:n].cpu()).all()) and len(torch.unique(kept)) == m
+    assert m < 2 or bool((kept[1:] > kept[:-1]).all())
+    if n <= K:
+        assert torch.equal(kept, sel[:n].cpu())
+    out2, _ = ops.cap_select(sel, n_dev, K, seed)
+    assert torch.equal(out2[:m].cpu(), kept)              # same seed, same subset
+    if n > K + 8:
+        seed2 = seed + 1
+        out3, _ = ops.cap_select(sel, n_dev, K, seed2)
+        assert not torch.equal(out3[:m].cpu(), kept)
+
+
 def test_p2p_allreduce_kernel_two_virtual_ranks_on_one_gpu():
     """mcnerf_allreduce_p2p (csrc/allreduce.cu): the two-shot NVLink all-reduce, exercised on ONE device by two
     "ranks" whose buffers both live on it and whose kernels run concurrently on two streams - the flag barriers,
