@@ -350,6 +350,8 @@ def run_ours(args):
             roof["compositing"] = dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s",
                                        frac=round(gbs / peaks["hbm"], 4), kernel_ms_per_step=round(comp_ms, 4))
     cpu, ref_gpu = None, None
+    if rank == 0 and world == 1 and roof is not None:
+        roof["dense"] = dense_leg(args, device)
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_reference(steps=2, warmup=1, rays=args.rays)
         ref_gpu = reference_gpu_eager(rays=args.rays)
@@ -385,6 +387,57 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def dense_leg(args, device, steps=10, warmup=3):
+    """at random init only ~77 % of the fine samples pass the selection threshold, so the roofline is also
+    reported for the DENSE step - the same workload with sample_weight_thresh = 0 (every one of the 64 + 128 samples of
+    every ray goes through both networks: 724.9 MFLOP per ray).  Eager launches, device-resident inputs."""
+    from mc_nerf_b200 import synthetic as syn
+    from mc_nerf_b200.model import MC_Model, MC_NeRF_Loss, RAdam
+    from mc_nerf_b200._lib import lib
+    sp = syn.make_sys_param(n_cam=N_CAM, img_h=args.img, img_w=args.img, batch=args.rays, samples=SC, scale=SCALE, device=device,
+                            with_images=False)
+    sp["mlp_precision"] = args.precision
+    sp["pixel_sampler"] = "device"
+    sp["sample_weight_thresh"] = 0.0
+    torch.manual_seed(42)
+    model = MC_Model(sp).to(device)
+    with torch.no_grad():
+        for k, v in syn.init_camera_weights(sp).items():
+            getattr(model, k).copy_(v)
+    loss_fn = MC_NeRF_Loss(sp)
+    opt = RAdam([p for p in model.parameters()], lr=5e-4, eps=1e-8, weight_decay=4e-4)
+    batch = tuple(t.to(device) for t in syn.make_train_batch(sp, img_id=3, seed=11))
+
+    def step():
+        opt.zero_grad()
+        loss_dict, _, _, _ = model(batch, 25, STAGE, RATIO)
+        loss_fn(loss_dict, STAGE).backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    L = lib()
+    L.profile_begin()
+    step()
+    torch.cuda.synchronize()
+    prof = L.profile_end()
+    mlp_ms = sum(v for k, v in prof.items() if k.startswith("mcnerf_mlp_tc_fwd") or k.startswith("mcnerf_mlp_tc_bwd"))
+    evals = args.rays * (SC + SC * SCALE)
+    peaks = load_peaks()
+    ach = 6.0 * MACS_PER_EVAL * evals / (mlp_ms / 1e3) / 1e12
+    return dict(what="same step with sample_weight_thresh = 0: all 64 + 128 samples of every ray evaluated", value=round(args.rays / (ms / 1e3), 1),
+                unit=UNIT, ms_per_step=round(ms, 3), steps=steps, mlp_evals_per_step=evals, kernel_ms_per_step=round(mlp_ms, 3),
+                achieved=round(ach, 2), peak=peaks["tensor"], frac=round(ach / peaks["tensor"], 4), issue="eager launches")
 
 
 # --------------------------------------------------------------------------------------------- other BASELINE configs
