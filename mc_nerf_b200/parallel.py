@@ -79,6 +79,8 @@ class GradSync:
       kernel (csrc/allreduce.cu): ~3 launches of NCCL cost 110-120 us of exposed time per step, this costs a fraction;
     transport = "nccl": torch.distributed all-reduces (any topology; also the gloo CPU tests).
 
+    `install()` sets the renderer's process-global hooks (render.GRAD_HOOK / GRAD_ALLOC): one GradSync per process;
+    `uninstall()` before rendering another model with gradients in the same process.
     Works eagerly and under CUDA-graph capture (append `finish` to GraphedTrainStep.after_backward: the fork and the
     join of the communication stream are then part of the captured graph).  Requires gradients to be None before
     backward (zero_grad(set_to_none=True), the default): the in-place reduction must not race an accumulation."""
